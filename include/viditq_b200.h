@@ -1,0 +1,88 @@
+/* viditq_b200 — C ABI of the B200-native low-bit path behind ViDiT-Q's qdiff QuantLayer operator.
+ *
+ * The reference (thu-nics/ViDiT-Q) has no FFI: its operator boundary is the Python nn.Module contract
+ * QuantLayer.forward(input) (qdiff/models/quant_layer.py:99) and its five subclasses. These entry points are what a
+ * patched QuantLayer.forward binds (ctypes stub in INTEGRATION.md). Conventions:
+ *   - plain device pointers + sizes, no torch types; fp16 tensors are passed as `const void*` (IEEE binary16);
+ *   - `stream` is a cudaStream_t; nothing here allocates, synchronises or reads back to the host;
+ *   - return 0 (VQ_OK) or a negative VQ_ERR_* code; kernels never fall back to a CPU path.
+ */
+#ifndef VIDITQ_B200_H_
+#define VIDITQ_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  VQ_OK = 0,
+  VQ_ERR_ARG = -1,     /* bad shape / alignment / null pointer */
+  VQ_ERR_DRIVER = -2,  /* cuTensorMapEncodeTiled entry point not found */
+  VQ_ERR_TMAP = -3,    /* tensor-map encode failed */
+  VQ_ERR_LAUNCH = -4,  /* kernel launch failed */
+  VQ_ERR_UNSUPPORTED = -5
+};
+
+/* epilogue selector of vq_gemm_w8a8 / vq_linear_w8a8 */
+enum {
+  VQ_EPI_BIAS = 0,          /* out = y                         (QuantLayer / attn q,k,v / cross-attn linears) */
+  VQ_EPI_GELU_TANH = 1,     /* out = gelu_tanh(y)              (mlp.fc1 -> act, modules.py:52-57)              */
+  VQ_EPI_GATE_RESIDUAL = 2  /* out = res + gate * y            (stdit.py:109,118,123,127 gated residual)       */
+};
+
+/* sticky device status bits (vq_status_*): set by kernels, polled by the host outside the hot loop */
+enum {
+  VQ_STATUS_EPS_DEGENERATE = 1 /* a token row had delta < 1e-6: reference quirk Q4 (base_quantizer.py:220-223) */
+};
+
+/* Per-output-channel constants of a prepared weight, one 16-byte record per channel n:
+ *   c1   = sum_k wq[n,k] - K * zw[n]   (so that sum_k (xq - zx)(wq - zw) = acc - zx*c1 - zw*rowsum_x)
+ *   zw   = weight zero point (integer), dw = weight step size, bias = layer bias (0 if none)            */
+typedef struct VqColParam {
+  int32_t c1;
+  int32_t zw;
+  float dw;
+  float bias;
+} VqColParam;
+
+/* Library / device ------------------------------------------------------------------------------------------- */
+int vq_version(void);
+int vq_num_sms(void);
+
+/* (a2) WeightQuantizer.forward, base_quantizer.py:112-144, hoisted to load time (the reference re-runs it every call,
+ * quant_layer.py:185). w: fp16 [N,K] row-major; delta, zp: fp16 [N] (per-output-channel buffers from ckpt.pth);
+ * smooth: fp16 [K] channel_wise_scale or NULL (quant_layer.py:178: weight * channel_wise_scale, fp16 product);
+ * bias: fp16 [N] or NULL. Outputs: codes u8 [N,K] (n_bits <= 8; values < 2^n_bits), col [N].                     */
+int vq_prep_weight(const void* w, const void* delta, const void* zp, const void* smooth, const void* bias, int N,
+                   int K, int n_bits, uint8_t* codes, VqColParam* col, void* stream);
+
+/* (a1) DynamicActQuantizer.forward, dynamic_quantizer.py:16-45 + init_quant_params 'token' branch
+ * base_quantizer.py:177-228. x: fp16, logically [G, rows, K] with element (g, r, k) at x[g*group_stride + r*ld + k];
+ * statistics of token r are pooled over the G batch entries (quirk Q1). smooth: fp16 [K] or NULL (input /
+ * channel_wise_scale, quant_layer.py:140). Outputs: codes u8 [G*rows, K] (row g*rows + r), delta/zp fp16 [rows],
+ * rowsum i32 [G*rows]. status: device word, VQ_STATUS_EPS_DEGENERATE is OR-ed in if any delta < 1e-6.            */
+int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, int64_t ld, const void* smooth,
+                 int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream);
+
+/* LayerNorm(eps=1e-6, no affine) + t2i_modulate (blocks.py:51: x*(1+scale)+shift) + (a1), one pass.
+ * x: fp16 [G*rows, K]; shift, scale: fp16 [G, K] (per sample); y_out (optional, may be NULL): fp16 modulated x.   */
+int vq_ln_modulate_act_quant(const void* x, const void* shift, const void* scale, int G, int rows, int K,
+                             int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp, int32_t* rowsum,
+                             uint32_t* status, void* stream);
+
+/* (a3-a7) integer GEMM + dequant epilogue on prepared operands. a_codes u8 [M,K]; a_delta/a_zp fp16 [rows] indexed
+ * by (m % a_rows_period) — pass a_rows_period = M when every row has its own scale; w_codes u8 [N,K]; out fp16
+ * [M, ldo]. res fp16 [M, ldr], gate fp16 [M / rows_per_gate, N] for VQ_EPI_GATE_RESIDUAL.                          */
+int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const void* a_zp, const int32_t* a_rowsum,
+                 int a_rows_period, const uint8_t* w_codes, const VqColParam* col, int M, int N, int K, int epi, const void* res,
+                 int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* stream);
+
+/* status word helpers (host side; the only calls here that synchronise) */
+int vq_status_read(const uint32_t* status_dev, uint32_t* host_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDITQ_B200_H_ */

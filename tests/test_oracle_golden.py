@@ -1,0 +1,118 @@
+"""Pin oracle/qdiff_oracle.py against vectors produced by the unmodified reference (tests/golden/qdiff_golden.npz).
+
+Bit-exact for everything the quantiser defines (delta, zero point, integer codes, fake-quantised tensors); the fp16
+F.linear output is compared within fp16 accumulation-order noise (the reference's CPU half GEMM and our fp32-accumulate
+restatement may round the last bit differently).
+"""
+import numpy as np
+import pytest
+
+from oracle import qdiff_oracle as O
+
+
+def _cases(golden, prefix):
+    return sorted(k for k in golden if k.startswith(prefix))
+
+
+def test_golden_has_expected_cases(golden):
+    assert len(_cases(golden, "act/")) >= 8
+    assert len(_cases(golden, "layer/")) >= 14
+
+
+@pytest.mark.parametrize("name", ["act/basic", "act/pooled_b2", "act/heavy_tail", "act/ragged_kv", "act/fc2_k4608",
+                                  "act/signs_and_ranges", "act/bits6", "act/bits4"])
+def test_act_quantizer_bit_exact(golden, name):
+    c = golden[name]
+    r = O.dynamic_act_quant(c["x"], int(c["n_bits"]))
+    assert not r["degenerate"]
+    np.testing.assert_array_equal(r["delta"], c["delta"].astype(np.float32))
+    np.testing.assert_array_equal(r["zp"], c["zp"].astype(np.float32))
+    np.testing.assert_array_equal(r["codes"], c["codes"])
+    np.testing.assert_array_equal(r["xhat"], c["xhat"])
+    np.testing.assert_array_equal(r["rowsum"], c["codes"].astype(np.int64).sum(-1))
+
+
+def _layer_inputs(c):
+    """Re-derive what each reference subclass feeds its act quantiser (the view tricks of stdit_quant_layer.py:70,161)."""
+    x = c["x"]
+    smooth = None
+    if "act_scale" in c:
+        tr = c["timerange"]
+        t = int(c["t_eval"])
+        idx = next(i for i, (lo, hi) in enumerate(tr) if lo <= t <= hi)
+        smooth = O.smooth_channel_scale(c["act_scale"][idx].reshape(-1), c["weight"], float(c["alpha"][idx]))
+    return x, smooth
+
+
+LAYER_VIEWS = {
+    # name -> (pool batch B, tokens) given x.shape; spatial/temporal layers view (B*T,S,C)->(B,T*S,C) with T=4,S=16
+    "layer/mlp_fc1": lambda s: (s[0], s[1]),
+    "layer/mlp_fc2_k4608": lambda s: (s[0], s[1]),
+    "layer/spatial_attn": lambda s: (s[0] // 4, 4 * s[1]),
+    "layer/spatial_attn_b2": lambda s: (s[0] // 4, 4 * s[1]),
+    "layer/temporal_attn": lambda s: (s[0] // 16, 16 * s[1]),
+    "layer/cross_q": lambda s: (s[0], s[1]),
+    "layer/cross_kv": lambda s: (s[0], s[1]),
+    "layer/pixart_qkv_b2": lambda s: (s[0], s[1]),
+    "layer/pixart_cross_kv": lambda s: (s[0], s[1]),
+    "layer/nobias": lambda s: (s[0], s[1]),
+    "layer/w4_plain": lambda s: (s[0], s[1]),
+    "layer/w4_smooth_t100": lambda s: (s[0] // 4, 4 * s[1]),
+    "layer/w4_smooth_t900": lambda s: (s[0] // 4, 4 * s[1]),
+    "layer/w8_smooth_mlp_t700": lambda s: (s[0], s[1]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LAYER_VIEWS))
+def test_quant_layer_family(golden, name):
+    c = golden[name]
+    x, smooth = _layer_inputs(c)
+    B, n = LAYER_VIEWS[name](x.shape)
+    xv = x.reshape(B, n, x.shape[-1])
+    a = O.dynamic_act_quant(xv, 8, smooth)
+    np.testing.assert_array_equal(a["delta"], c["adelta"].astype(np.float32))
+    np.testing.assert_array_equal(a["zp"], c["azp"].astype(np.float32))
+    w_bits = int(c["w_bits"])
+    bias = c["bias"] if "bias" in c else None
+    fake = O.quant_linear_fake(xv, c["weight"], bias, c["wdelta"], c["wzp"], w_bits, 8, smooth)
+    ref = c["out"].reshape(B, n, -1).astype(np.float32)
+    diff = np.abs(fake.astype(np.float32) - ref)
+    # same fake-quant operands, different fp16 GEMM accumulation order: at most a couple of fp16 ulps
+    assert diff.max() <= 4 * np.spacing(np.abs(ref).max().astype(np.float16)).astype(np.float32)
+    assert (diff > 0).mean() < 0.35
+    # integer decomposition (what the CUDA kernel evaluates) against the reference's fake-quant output: <= 1e-3 relative
+    wq = O.weight_quant(c["weight"], c["wdelta"], c["wzp"], w_bits, smooth)
+    assert wq["codes"].max() <= 2 ** w_bits - 1
+    y = O.quant_linear_int(a["codes"], a["delta"], a["zp"], a["rowsum"], wq["codes"], c["wdelta"], c["wzp"], bias)
+    rel_inf = np.abs(y.astype(np.float32) - ref).max() / np.abs(ref).max()
+    rel_l2 = np.linalg.norm(y.astype(np.float32) - ref) / np.linalg.norm(ref)
+    assert rel_inf <= 1e-3 and rel_l2 <= 1e-3, (rel_inf, rel_l2)
+
+
+def test_smooth_quant_uses_timerange0_weight_grid(golden):
+    """Quirk Q7: after init_done the weight delta/zero-point never switch timerange (base_quantizer.py:114-127)."""
+    a, b = golden["layer/w4_smooth_t100"], golden["layer/w4_smooth_t900"]
+    np.testing.assert_array_equal(a["wdelta"], b["wdelta"])
+    np.testing.assert_array_equal(a["wzp"], b["wzp"])
+    assert not np.array_equal(a["out"], b["out"])  # but the channel scale (alpha, act_scale) does switch
+
+
+def test_eps_quirk_flags_degenerate():
+    """Quirk Q4 (base_quantizer.py:220-223): one ~zero-range token makes delta.fill_(1e-6) hit every row."""
+    x = np.random.default_rng(0).standard_normal((1, 8, 64)).astype(np.float16)
+    x[0, 3] = 0
+    r = O.dynamic_act_quant(x, 8)
+    assert r["degenerate"]
+    assert np.all(r["delta"] == np.float32(np.float16(1e-6)))
+
+
+def test_div_by_levels_matches_reciprocal_multiply():
+    """The CUDA build of torch divides a half tensor by a Python scalar as a * (1/b) in fp32; the CPU build divides.
+    Both round to the same fp16 for every positive half and every level count the configs use, so the pinned CPU
+    behaviour is also the GPU reference's."""
+    allh = np.arange(0, 0x7C00, dtype=np.uint16).view(np.float16).astype(np.float32)
+    for qmax in (15.0, 63.0, 255.0):
+        a = (allh / np.float32(qmax)).astype(np.float16)
+        b = (allh * (np.float32(1.0) / np.float32(qmax))).astype(np.float16)
+        mism = int((a != b).sum())
+        assert mism == 0, (qmax, mism)

@@ -1,0 +1,356 @@
+// W8A8 QuantLinear GEMM for sm_100a: u8 activation codes x u8 weight codes -> s32 (tcgen05.mma.kind::i8,
+// accumulators in TMEM), fused zero-point correction + per-token x per-channel dequant + bias
+// (+ GELU-tanh | + gate*y + residual) epilogue, fp16 out.
+//
+// Replaces, for one QuantLayer-family forward (reference qdiff/models/quant_layer.py:185-211,
+// stdit_quant_layer.py:76-96, dit_quant_layer.py:18-29), the chain
+//     x_hat = (x_q - zx) * dx ; w_hat = (w_q - zw) * dw ; F.linear(x_hat, w_hat, bias)
+// by the algebraically identical integer form
+//     out[m,n] = (sum_k xq[m,k] wq[n,k] - zx[m] * c1[n] - zw[n] * rowsum[m]) * dx[m] * dw[n] + bias[n]
+// with c1[n] = sum_k wq[n,k] - K * zw[n]  (prepared once per weight by vq_prep_weight).
+//
+// Structure (one CTA per SM, persistent over 128x192 output tiles, m-fastest so co-resident CTAs share a B tile in L2):
+//   warp 0      : TMA producer   (one elected lane; A box 128 rows x 128 B, B box 192 rows x 128 B, SWIZZLE_128B)
+//   warp 1      : MMA issuer     (one elected lane; 4 x tcgen05.mma 128x192x32 per 128-byte K block)
+//   warp 2      : TMEM allocator (512 columns = 2 accumulator stages x 256)
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half)
+// Pipelines: smem full/empty ring (5 stages x 40 KB) and TMEM full/empty (2 stages), all mbarrier based.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "vq_ptx.cuh"
+#include "vq_internal.h"
+
+namespace vq {
+
+constexpr int BM = 128;
+constexpr int BN = 192;
+constexpr int BK = 128;  // bytes == u8 elements per K block (one 128B swizzle row)
+constexpr int UMMA_K = 32;
+constexpr int STAGES = 5;
+constexpr int A_STAGE_BYTES = BM * BK;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK;  // 24 KB
+constexpr int ACC_STAGES = 2;
+constexpr int ACC_COLS = 256;  // TMEM column stride between accumulator stages
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
+
+struct GemmArgs {
+  int M, N, K;
+  const __half* a_delta;    // [M] per-token step size (fp16, as the reference's DynamicActQuantizer.delta)
+  const __half* a_zp;       // [M] per-token zero point (integer valued fp16)
+  const int32_t* a_rowsum;  // [M] sum_k xq[m,k]
+  int a_period;             // delta/zp row index = m % a_period (token statistics pooled over the batch, Q1)
+  const VqColParam* col;    // [N] {c1, zw, dw, bias}
+  __half* out;              // [M, ldo]
+  int ldo;
+  int epi;                  // VQ_EPI_*
+  const __half* res;        // [M, ldr] residual (VQ_EPI_GATE_RESIDUAL)
+  int ldr;
+  const __half* gate;       // [M / rows_per_gate, N]
+  int rows_per_gate;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // nn.GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&v)[32], int row, int col0,
+                                               int32_t zx, int32_t rs, float dx, bool row_ok) {
+  // 32 consecutive output columns of one row: dequantise, apply the epilogue op, pack to fp16 and store 4 x 16 B.
+  const int4* colp = reinterpret_cast<const int4*>(p.col);
+  const int nmax = p.N - 1;
+  uint32_t packed[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float f[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int n = col0 + j + e;
+      int4 cp = __ldg(colp + (n < nmax ? n : nmax));
+      int32_t t = static_cast<int32_t>(v[j + e]) - zx * cp.x - rs * cp.y;
+      float s = dx * __int_as_float(cp.z);
+      f[e] = fmaf(static_cast<float>(t), s, __int_as_float(cp.w));
+    }
+    __half2 h2 = __floats2half2_rn(f[0], f[1]);
+    if (EPI == VQ_EPI_GELU_TANH) {
+      float2 y = __half22float2(h2);
+      h2 = __floats2half2_rn(gelu_tanh_f(y.x), gelu_tanh_f(y.y));
+    }
+    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  if (!row_ok) return;
+  if (EPI == VQ_EPI_GATE_RESIDUAL) {
+    // x_new = res + gate * y, each op rounded to fp16 like the reference's half tensors (stdit.py:109,118,123,127)
+    const __half* gate_row = p.gate + static_cast<size_t>(row / p.rows_per_gate) * p.N;
+    const __half* res_row = p.res + static_cast<size_t>(row) * p.ldr;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      int n = col0 + g * 8;
+      if (n < p.N) {
+        uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+        uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
+        const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+        const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
+          __half2 o = __hadd2(r2[e], __hmul2(g2[e], y));
+          packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
+        }
+      }
+    }
+  }
+  __half* out_row = p.out + static_cast<size_t>(row) * p.ldo;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    int n = col0 + g * 8;
+    if (n < p.N) {
+      uint4 o = make_uint4(packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+      *reinterpret_cast<uint4*>(out_row + n) = o;
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m_tiles = (p.M + BM - 1) / BM;
+  const int num_n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = (tile % num_m_tiles) * BM;
+        const int n_idx = (tile / num_m_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx);
+          tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx);
+          if (++s == STAGES) { s = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_i8(BM, BN, /*a_signed=*/0, /*b_signed=*/0);
+      int s = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing K by 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) start-address field
+            tc_mma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          if (++s == STAGES) { s = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int h = (warp - 4) >> 2;   // column half
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int m_idx = (tile % num_m_tiles) * BM;
+      const int n_idx = (tile / num_m_tiles) * BN;
+      const int row = m_idx + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int row_c = row_ok ? row : p.M - 1;
+      const int srow = row_c % p.a_period;
+      const float dx = __half2float(p.a_delta[srow]);
+      const int32_t zx = __float2int_rn(__half2float(p.a_zp[srow]));
+      const int32_t rs = p.a_rowsum[row_c];
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2 / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_base + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_idx + h * (BN / 2) + c * 32;
+        if (col0 < p.N) epilogue_chunk<EPI>(p, v, row, col0, zx, rs, dx, row_ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+// rows x cols_bytes u8 matrix, row pitch = pitch bytes; box = box_rows x 128 B, 128B swizzle, zero OOB fill.
+int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch,
+                        uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return VQ_ERR_DRIVER;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch};
+  cuuint32_t box[2] = {128u, box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int grid,
+                       cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BYTES);
+    if (e != cudaSuccess) return VQ_ERR_LAUNCH;
+    attr_set = true;
+  }
+  vq_gemm_w8a8_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tb, args);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+}  // namespace vq
+
+extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const void* a_zp, const int32_t* a_rowsum,
+                            int a_rows_period, const uint8_t* w_codes, const VqColParam* col, int M, int N, int K, int epi,
+                            const void* res, int ldr, const void* gate, int rows_per_gate, void* out, int ldo,
+                            void* stream) {
+  using namespace vq;
+  if (M <= 0 || N <= 0 || K <= 0 || a_rows_period <= 0) return VQ_ERR_ARG;
+  if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0) return VQ_ERR_ARG;
+  if (epi == VQ_EPI_GATE_RESIDUAL && (!res || !gate || rows_per_gate <= 0 || (ldr % 8) != 0)) return VQ_ERR_ARG;
+  if (epi < 0 || epi > VQ_EPI_GATE_RESIDUAL) return VQ_ERR_ARG;
+  CUtensorMap ta, tb;
+  int rc = make_u8_kmajor_tmap(&ta, a_codes, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM);
+  if (rc != VQ_OK) return rc;
+  rc = make_u8_kmajor_tmap(&tb, w_codes, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN);
+  if (rc != VQ_OK) return rc;
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.a_delta = static_cast<const __half*>(a_delta);
+  args.a_zp = static_cast<const __half*>(a_zp);
+  args.a_rowsum = a_rowsum;
+  args.a_period = a_rows_period;
+  args.col = col;
+  args.out = static_cast<__half*>(out);
+  args.ldo = ldo;
+  args.epi = epi;
+  args.res = static_cast<const __half*>(res);
+  args.ldr = ldr;
+  args.gate = static_cast<const __half*>(gate);
+  args.rows_per_gate = rows_per_gate;
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (epi) {
+    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, args, grid, st);
+    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, args, grid, st);
+    default: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, args, grid, st);
+  }
+}
