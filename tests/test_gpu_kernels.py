@@ -1,0 +1,217 @@
+"""GPU parity tests (run on the B200 with `pytest -m gpu`): the CUDA path, called through the C ABI, against
+(a) vectors produced by the unmodified reference (tests/golden) and (b) the CPU oracle on seeded inputs.
+
+Bar: integer codes / delta / zero-point / row sums bit-exact; GEMM output equal to the oracle's integer decomposition
+(same operation order) and within 1e-3 relative (inf-norm and L2) of the reference's fake-quant fp16 output.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import qdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ACT_CASES = ["act/basic", "act/pooled_b2", "act/heavy_tail", "act/ragged_kv", "act/fc2_k4608",
+             "act/signs_and_ranges", "act/bits6", "act/bits4"]
+LAYER_VIEWS = {
+    "layer/mlp_fc1": None, "layer/mlp_fc2_k4608": None, "layer/spatial_attn": 4, "layer/spatial_attn_b2": 4,
+    "layer/temporal_attn": 16, "layer/cross_q": None, "layer/cross_kv": None, "layer/pixart_qkv_b2": None,
+    "layer/pixart_cross_kv": None, "layer/nobias": None, "layer/w4_plain": None, "layer/w4_smooth_t100": 4,
+    "layer/w4_smooth_t900": 4, "layer/w8_smooth_mlp_t700": None,
+}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from viditq_b200 import ops as _ops
+    return _ops
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def _pool_view(x, group):
+    """(B*g, s, C) -> (B, g*s, C): the reshape the reference's spatial/temporal subclasses apply before quantising."""
+    if group is None:
+        return x
+    return x.reshape(x.shape[0] // group, group * x.shape[1], x.shape[2])
+
+
+def _smooth_for(c):
+    if "act_scale" not in c:
+        return None
+    t = int(c["t_eval"])
+    idx = next(i for i, (lo, hi) in enumerate(c["timerange"]) if lo <= t <= hi)
+    return O.smooth_channel_scale(c["act_scale"][idx].reshape(-1), c["weight"], float(c["alpha"][idx]))
+
+
+@pytest.mark.parametrize("name", ACT_CASES)
+def test_act_quant_matches_reference_vectors(ops, golden, name):
+    c = golden[name]
+    x = dev(c["x"])
+    a = ops.act_quant(x, n_bits=int(c["n_bits"]))
+    torch.cuda.synchronize()
+    B, n, C = c["x"].shape
+    np.testing.assert_array_equal(a.delta.cpu().numpy(), c["delta"])
+    np.testing.assert_array_equal(a.zp.cpu().numpy(), c["zp"])
+    np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(B, n, C), c["codes"])
+    np.testing.assert_array_equal(a.rowsum.cpu().numpy().reshape(B, n), c["codes"].astype(np.int64).sum(-1))
+    assert ops.check_status() == 0
+
+
+@pytest.mark.parametrize("name", sorted(LAYER_VIEWS))
+def test_quant_layer_family_matches_reference(ops, golden, name):
+    c = golden[name]
+    xv = _pool_view(c["x"], LAYER_VIEWS[name])
+    B, n, C = xv.shape
+    smooth = _smooth_for(c)
+    w_bits = int(c["w_bits"])
+    bias = c["bias"] if "bias" in c else None
+    # weight prep (a2): codes and c1 bit-exact vs the oracle restatement of WeightQuantizer.forward
+    pw = ops.prep_weight(dev(c["weight"]), dev(c["wdelta"]), dev(c["wzp"]), n_bits=w_bits,
+                         smooth=None if smooth is None else dev(smooth), bias=None if bias is None else dev(bias))
+    wq = O.weight_quant(c["weight"], c["wdelta"], c["wzp"], w_bits, smooth)
+    np.testing.assert_array_equal(pw.codes.cpu().numpy(), wq["codes"])
+    zw = np.rint(c["wzp"].astype(np.float32)).astype(np.int64)
+    col = pw.col.cpu().numpy()
+    np.testing.assert_array_equal(col[:, 0], wq["colsum"].astype(np.int64) - C * zw)
+    np.testing.assert_array_equal(col[:, 1], zw)
+    # act quant (a1): delta / zp as the reference left them in its act_quantizer buffers
+    a = ops.act_quant(dev(xv), n_bits=8, smooth=None if smooth is None else dev(smooth))
+    np.testing.assert_array_equal(a.delta.cpu().numpy(), c["adelta"])
+    np.testing.assert_array_equal(a.zp.cpu().numpy(), c["azp"])
+    oa = O.dynamic_act_quant(xv, 8, smooth)
+    np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(B, n, C), oa["codes"])
+    # GEMM + dequant epilogue (a3-a7)
+    y = ops.gemm_w8a8(a, pw).cpu().numpy().reshape(B, n, -1)
+    yo = O.quant_linear_int(oa["codes"], oa["delta"], oa["zp"], oa["rowsum"], wq["codes"], c["wdelta"], c["wzp"], bias)
+    mism = (y.view(np.uint16) != yo.view(np.uint16))
+    assert mism.mean() <= 1e-5, mism.mean()      # fma vs float64 double rounding can flip a last bit, nothing else
+    ref = c["out"].reshape(B, n, -1).astype(np.float32)
+    yf = y.astype(np.float32)
+    assert np.abs(yf - ref).max() / np.abs(ref).max() <= 1e-3
+    assert np.linalg.norm(yf - ref) / np.linalg.norm(ref) <= 1e-3
+
+
+def _rand_layer(seed, M, K, N, heavy=True):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((1, M, K)).astype(np.float32)
+    if heavy:
+        x[..., [3, 77, 500, 901]] *= 20.0
+    w = (rng.standard_normal((N, K)) * 0.02).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.01).astype(np.float16)
+    wd, wz = O.weight_init_params(w, 8)
+    wd = (wd * rng.uniform(0.5, 1.5, size=N)).astype(np.float16)   # "random calib scales" (BASELINE config 1)
+    return x.astype(np.float16), w.astype(np.float16), b, wd, wz.astype(np.float16)
+
+
+@pytest.mark.parametrize("epi", ["bias", "gelu_tanh", "gate_residual"])
+def test_gemm_epilogues_vs_oracle(ops, epi):
+    M, K, N = 512, 1152, 384
+    x, w, b, wd, wz = _rand_layer(1, M, K, N)
+    a = ops.act_quant(dev(x))
+    pw = ops.prep_weight(dev(w), dev(wd), dev(wz), bias=dev(b))
+    oa = O.dynamic_act_quant(x)
+    wq = O.weight_quant(w, wd, wz)
+    rng = np.random.default_rng(5)
+    res = rng.standard_normal((1, M, N)).astype(np.float16)
+    gate = (rng.standard_normal((1, N)) * 0.5).astype(np.float16)
+    code = {"bias": ops.VQ_EPI_BIAS, "gelu_tanh": ops.VQ_EPI_GELU_TANH, "gate_residual": ops.VQ_EPI_GATE_RESIDUAL}[epi]
+    y = ops.gemm_w8a8(a, pw, epi=code, res=dev(res.reshape(M, N)), gate=dev(gate), rows_per_gate=M)
+    yo = O.quant_linear_int(oa["codes"], oa["delta"], oa["zp"], oa["rowsum"], wq["codes"], wd, wz, b, epi=epi,
+                            res16=res, gate16=gate)
+    y = y.cpu().numpy().reshape(1, M, N)
+    ulp = np.abs(y.view(np.int16).astype(np.int32) - yo.view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1, ulp.max()              # gelu: __expf vs float64 tanh -> at most the last fp16 bit
+    assert (ulp > 0).mean() <= (2e-3 if epi == "gelu_tanh" else 1e-5)
+
+
+def test_config1_full_size_w8a8_linear(ops):
+    """BASELINE config 1 at full size: QuantLinear W8A8 in=1152 out=4608, M=16384 tokens."""
+    M, K, N = 16384, 1152, 4608
+    x, w, b, wd, wz = _rand_layer(7, M, K, N)
+    xd = dev(x)
+    a = ops.act_quant(xd)
+    pw = ops.prep_weight(dev(w), dev(wd), dev(wz), bias=dev(b))
+    y = ops.gemm_w8a8(a, pw)
+    torch.cuda.synchronize()
+    oa = O.dynamic_act_quant(x)
+    np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(1, M, K), oa["codes"])
+    np.testing.assert_array_equal(a.delta.cpu().numpy().astype(np.float32), oa["delta"])
+    np.testing.assert_array_equal(a.zp.cpu().numpy().astype(np.float32), oa["zp"])
+    np.testing.assert_array_equal(a.rowsum.cpu().numpy().reshape(1, M), oa["rowsum"])
+    wq = O.weight_quant(w, wd, wz)
+    np.testing.assert_array_equal(pw.codes.cpu().numpy(), wq["codes"])
+    rows = np.random.default_rng(0).choice(M, 256, replace=False)
+    rows.sort()
+    sub = dict(codes=oa["codes"][:, rows], delta=oa["delta"][rows], zp=oa["zp"][rows], rowsum=oa["rowsum"][:, rows])
+    yo = O.quant_linear_int(sub["codes"], sub["delta"], sub["zp"], sub["rowsum"], wq["codes"], wd, wz, b)
+    ys = y.cpu().numpy()[rows].reshape(1, len(rows), N)
+    assert (ys.view(np.uint16) != yo.view(np.uint16)).mean() <= 1e-5
+    # against the reference-style fake-quant path (fp16 operands, fp32 accumulate) on the same rows
+    fake = O.linear_f16(oa["xhat"][0, rows], wq["what"], b).astype(np.float32)
+    yf = ys[0].astype(np.float32)
+    assert np.abs(yf - fake).max() / np.abs(fake).max() <= 1e-3
+    assert np.linalg.norm(yf - fake) / np.linalg.norm(fake) <= 1e-3
+    # size-independent property: the integer form is exactly linear in the bias (shift by a constant vector)
+    pw2 = ops.prep_weight(dev(w), dev(wd), dev(wz), bias=None)
+    y0 = ops.gemm_w8a8(a, pw2).float()
+    d = (y.float() - y0 - dev(b).float()[None, :]).abs().max().item()
+    assert d <= 2 * float(np.spacing(np.float16(np.abs(yf).max())))
+
+
+def test_pooled_batch_statistics_and_rows_period(ops):
+    """Quirk Q1: PixArt-style batch-2 forward shares one (delta, zp) per token across the batch."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 256, 1152)).astype(np.float16)
+    x[1] *= 4
+    w, b = (rng.standard_normal((192, 1152)) * 0.02).astype(np.float16), None
+    wd, wz = O.weight_init_params(w.astype(np.float32), 8)
+    a = ops.act_quant(dev(x))
+    oa = O.dynamic_act_quant(x)
+    np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(2, 256, 1152), oa["codes"])
+    pw = ops.prep_weight(dev(w), dev(wd.astype(np.float16)), dev(wz.astype(np.float16)))
+    y = ops.gemm_w8a8(a, pw).cpu().numpy().reshape(2, 256, 192)
+    wq = O.weight_quant(w, wd.astype(np.float16), wz.astype(np.float16))
+    yo = O.quant_linear_int(oa["codes"], oa["delta"], oa["zp"], oa["rowsum"], wq["codes"], wd.astype(np.float16),
+                            wz.astype(np.float16), b)
+    assert (y.view(np.uint16) != yo.view(np.uint16)).mean() <= 1e-5
+
+
+@pytest.mark.parametrize("G,rows,K", [(1, 300, 1152), (2, 64, 1152), (1, 40, 4608)])
+def test_ln_modulate_act_quant(ops, G, rows, K):
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal((G, rows, K)) * 2 + 0.3).astype(np.float16)
+    shift = (rng.standard_normal((G, K)) * 0.2).astype(np.float16)
+    scale = (rng.standard_normal((G, K)) * 0.2).astype(np.float16)
+    a, y = ops.ln_modulate_act_quant(dev(x), dev(shift), dev(scale), want_y=True)
+    y = y.cpu().numpy()
+    yo = O.ln_modulate(x, shift, scale)
+    ulp = np.abs(y.view(np.int16).astype(np.int32) - yo.view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1 and (ulp > 0).mean() < 5e-3   # fp32 vs fp64 LayerNorm statistics: last-bit only
+    # given the kernel's own modulated tensor, the quantiser part must be bit-exact
+    oa = O.dynamic_act_quant(y)
+    np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(G, rows, K), oa["codes"])
+    np.testing.assert_array_equal(a.delta.cpu().numpy().astype(np.float32), oa["delta"])
+    np.testing.assert_array_equal(a.zp.cpu().numpy().astype(np.float32), oa["zp"])
+    np.testing.assert_array_equal(a.rowsum.cpu().numpy().reshape(G, rows), oa["rowsum"])
+
+
+def test_eps_degenerate_row_sets_status_and_raises(ops):
+    x = np.random.default_rng(0).standard_normal((1, 64, 1152)).astype(np.float16)
+    x[0, 5] = 0
+    ops.status_word().zero_()
+    ops.act_quant(dev(x))
+    with pytest.raises(Exception, match="delta < 1e-6"):
+        ops.check_status()
+    assert ops.check_status() == 0   # sticky bit cleared after being reported
+
+
+def test_cpu_tensor_is_rejected_no_fallback(ops):
+    with pytest.raises(Exception, match="no CPU path"):
+        ops.act_quant(torch.zeros(1, 8, 64, dtype=torch.float16))

@@ -22,8 +22,8 @@
 
 __device__ float ref_gelu(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  float u = k0 * (x + k1 * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
 
 __global__ void ref_gemm(const uint8_t* a, const __half* ad, const __half* az, const int32_t* ars, int period,
@@ -155,6 +155,18 @@ static int run_case(int M, int N, int K, int epi, int period, bool timeit) {
     double us = ms * 1e3 / iters;
     double tops = 2.0 * M * N * (double)K / (us * 1e-6) / 1e12;
     printf("   time %.2f us  -> %.1f TOPS (warm L2, back-to-back)\n", us, tops);
+    // internal debug epilogue 3: accumulators discarded -> TMA->MMA pipeline alone
+    for (int i = 0; i < 3; ++i)
+      vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, 3, dres, N, dgate, rpg, dout, N, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i)
+      vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, 3, dres, N, dgate, rpg, dout, N, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    us = ms * 1e3 / iters;
+    printf("   mainloop-only %.2f us -> %.1f TOPS\n", us, 2.0 * M * N * (double)K / (us * 1e-6) / 1e12);
   }
   cudaFree(da); cudaFree(dw); cudaFree(dad); cudaFree(daz); cudaFree(dars); cudaFree(dcol);
   cudaFree(dres); cudaFree(dgate); cudaFree(dout); cudaFree(dref);
@@ -168,6 +180,10 @@ int main(int argc, char** argv) {
   printf("device %s sm_%d%d SMs=%d lib version %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
          vq_version());
   int fails = 0;
+  if (argc > 5 && !strcmp(argv[1], "--case")) {  // single case, no timing loop: for ncu captures
+    int M = atoi(argv[2]), N = atoi(argv[3]), K = atoi(argv[4]), epi = atoi(argv[5]);
+    return run_case(M, N, K, epi, M, false);
+  }
   fails += run_case(128, 192, 128, VQ_EPI_BIAS, 128, false);    // one tile, one K block
   fails += run_case(128, 192, 1152, VQ_EPI_BIAS, 128, false);   // full K pipeline (9 blocks > 5 stages)
   fails += run_case(256, 384, 1152, VQ_EPI_BIAS, 256, false);   // 4 tiles

@@ -14,7 +14,9 @@
 //   warp 1      : MMA issuer     (one elected lane; 4 x tcgen05.mma 128x192x32 per 128-byte K block)
 //   warp 2      : TMEM allocator (512 columns = 2 accumulator stages x 256)
 //   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half)
-// Pipelines: smem full/empty ring (5 stages x 40 KB) and TMEM full/empty (2 stages), all mbarrier based.
+// Pipelines: smem full/empty ring (4 stages x 40 KB) and TMEM full/empty (2 stages), all mbarrier based.
+// Epilogue output path: registers -> per-warp 32x32 fp16 staging tile in smem (64B swizzle, bank-conflict free)
+// -> TMA store (cp.async.bulk.tensor, coalesced, clipped at the M/N edges by the tensor map).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -30,7 +32,7 @@ constexpr int BM = 128;
 constexpr int BN = 192;
 constexpr int BK = 128;  // bytes == u8 elements per K block (one 128B swizzle row)
 constexpr int UMMA_K = 32;
-constexpr int STAGES = 5;
+constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK;  // 24 KB
 constexpr int ACC_STAGES = 2;
@@ -38,7 +40,10 @@ constexpr int ACC_COLS = 256;  // TMEM column stride between accumulator stages
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
+constexpr int EPI_CHUNK = 32;                         // output columns per epilogue step (64 B of fp16 per row)
+constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one warp's staging tile: 32 rows x 64 B, SWIZZLE_64B
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 2 * EPI_BUF_BYTES;  // double-buffered per warp
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + 256 + 1024;
 
 struct GemmArgs {
   int M, N, K;
@@ -58,15 +63,20 @@ struct GemmArgs {
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // nn.GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+  // 0.5 (1 + tanh(u)) == 1 / (1 + exp(-2u)); __expf/__fdividef error (~1e-6 rel) is far below one fp16 ulp
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  float u = k0 * (x + k1 * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
 
+constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (measures the TMA->MMA pipeline alone)
+
+// Dequantise 32 consecutive output columns of one row, apply the epilogue op and write the fp16 results into this
+// warp's staging tile (row-major 64 B rows, 16-byte chunk index XOR ((row >> 1) & 3) == CU_TENSOR_MAP_SWIZZLE_64B).
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&v)[32], int row, int col0,
-                                               int32_t zx, int32_t rs, float dx, bool row_ok) {
-  // 32 consecutive output columns of one row: dequantise, apply the epilogue op, pack to fp16 and store 4 x 16 B.
+                                               int32_t zx, int32_t rs, float dx, bool row_ok, uint8_t* stage,
+                                               int lane) {
   const int4* colp = reinterpret_cast<const int4*>(p.col);
   const int nmax = p.N - 1;
   uint32_t packed[16];
@@ -88,49 +98,48 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
     }
     packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
   }
-  if (!row_ok) return;
   if (EPI == VQ_EPI_GATE_RESIDUAL) {
     // x_new = res + gate * y, each op rounded to fp16 like the reference's half tensors (stdit.py:109,118,123,127)
-    const __half* gate_row = p.gate + static_cast<size_t>(row / p.rows_per_gate) * p.N;
-    const __half* res_row = p.res + static_cast<size_t>(row) * p.ldr;
+    if (row_ok) {
+      const __half* gate_row = p.gate + static_cast<size_t>(row / p.rows_per_gate) * p.N;
+      const __half* res_row = p.res + static_cast<size_t>(row) * p.ldr;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      int n = col0 + g * 8;
-      if (n < p.N) {
-        uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
-        uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
-        const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
-        const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+      for (int g = 0; g < 4; ++g) {
+        int n = col0 + g * 8;
+        if (n < p.N) {
+          uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+          uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
+          const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+          const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
-          __half2 o = __hadd2(r2[e], __hmul2(g2[e], y));
-          packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
+          for (int e = 0; e < 4; ++e) {
+            __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
+            __half2 o = __hadd2(r2[e], __hmul2(g2[e], y));
+            packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
+          }
         }
       }
     }
   }
-  __half* out_row = p.out + static_cast<size_t>(row) * p.ldo;
+  const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+  uint4* srow = reinterpret_cast<uint4*>(stage + lane * (EPI_CHUNK * 2));
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    int n = col0 + g * 8;
-    if (n < p.N) {
-      uint4 o = make_uint4(packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
-      *reinterpret_cast<uint4*>(out_row + n) = o;
-    }
+    srow[g ^ sw] = make_uint4(packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
   }
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmArgs p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* smem_epi = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -148,6 +157,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -221,13 +231,16 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== epilogue =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int h = (warp - 4) >> 2;   // column half
+    uint8_t* stage0 = smem_epi + (warp - 4) * 2 * EPI_BUF_BYTES;
+    int buf = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int m_idx = (tile % num_m_tiles) * BM;
       const int n_idx = (tile / num_m_tiles) * BN;
-      const int row = m_idx + q * 32 + lane;
+      const int row0 = m_idx + q * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int row_c = row_ok ? row : p.M - 1;
       const int srow = row_c % p.a_period;
@@ -238,18 +251,36 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * (BN / 2);
+      constexpr int NCHUNK = BN / 2 / EPI_CHUNK;
 #pragma unroll 1
-      for (int c = 0; c < BN / 2 / 32; ++c) {
+      for (int c = 0; c < NCHUNK; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(t_base + c * 32, v);
+        tmem_ld_32x32b_x32(t_base + c * EPI_CHUNK, v);
         tmem_ld_wait();
-        const int col0 = n_idx + h * (BN / 2) + c * 32;
-        if (col0 < p.N) epilogue_chunk<EPI>(p, v, row, col0, zx, rs, dx, row_ok);
+        if (c == NCHUNK - 1) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        const int col0 = n_idx + h * (BN / 2) + c * EPI_CHUNK;
+        if (EPI != VQ_EPI_DEBUG_MAINLOOP && col0 < p.N && row0 < p.M) {
+          uint8_t* stage = stage0 + buf * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();  // the TMA store that last read this buffer has drained
+          __syncwarp();
+          epilogue_chunk<EPI>(p, v, row, col0, zx, rs, dx, row_ok, stage, lane);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stage, col0, row0);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) tma_store_wait<0>();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -291,6 +322,20 @@ int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
 }
 
+// rows x cols fp16 matrix (row pitch ld elements); box = 32 rows x 32 cols (64 B), 64B swizzle: the epilogue staging tile.
+int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return VQ_ERR_DRIVER;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -302,8 +347,8 @@ int num_sms() {
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int grid,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& args,
+                       int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -311,7 +356,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     if (e != cudaSuccess) return VQ_ERR_LAUNCH;
     attr_set = true;
   }
-  vq_gemm_w8a8_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tb, args);
+  vq_gemm_w8a8_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, args);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
@@ -323,13 +368,15 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
                             void* stream) {
   using namespace vq;
   if (M <= 0 || N <= 0 || K <= 0 || a_rows_period <= 0) return VQ_ERR_ARG;
-  if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0) return VQ_ERR_ARG;
+  if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0 || !out) return VQ_ERR_ARG;
   if (epi == VQ_EPI_GATE_RESIDUAL && (!res || !gate || rows_per_gate <= 0 || (ldr % 8) != 0)) return VQ_ERR_ARG;
-  if (epi < 0 || epi > VQ_EPI_GATE_RESIDUAL) return VQ_ERR_ARG;
-  CUtensorMap ta, tb;
+  if (epi < 0 || epi > VQ_EPI_DEBUG_MAINLOOP) return VQ_ERR_ARG;
+  CUtensorMap ta, tb, to;
   int rc = make_u8_kmajor_tmap(&ta, a_codes, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM);
   if (rc != VQ_OK) return rc;
   rc = make_u8_kmajor_tmap(&tb, w_codes, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN);
+  if (rc != VQ_OK) return rc;
+  rc = make_f16_out_tmap(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo);
   if (rc != VQ_OK) return rc;
   GemmArgs args;
   args.M = M; args.N = N; args.K = K;
@@ -349,8 +396,9 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   const int grid = tiles < num_sms() ? tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, args, grid, st);
-    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, args, grid, st);
-    default: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, args, grid, st);
+    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, args, grid, st);
+    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, args, grid, st);
+    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, args, grid, st);
+    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, args, grid, st);
   }
 }

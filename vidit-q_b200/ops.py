@@ -1,0 +1,152 @@
+"""Tensor-level wrappers over the C ABI: torch is used for device memory and the current stream only.
+
+Every function launches hand-written sm_100a kernels from libviditq_b200.so; none has a PyTorch/CPU fallback.
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import VQ_EPI_BIAS, VQ_EPI_GELU_TANH, VQ_EPI_GATE_RESIDUAL  # noqa: F401
+
+_launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+_status = {}           # device index -> uint32 status word
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda_f16(t, name):
+    if not (t.is_cuda and t.dtype == torch.float16 and t.is_contiguous()):
+        raise _lib.VqError(f"{name}: expected a contiguous CUDA fp16 tensor, got {t.dtype} {t.device} "
+                           f"contiguous={t.is_contiguous()} (viditq_b200 has no CPU path)")
+
+
+def status_word(device=None):
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev not in _status:
+        _status[dev] = torch.zeros(1, dtype=torch.int32, device=f"cuda:{dev}")
+    return _status[dev]
+
+
+def check_status(device=None):
+    """Poll the sticky device status word (synchronises; call outside the hot loop). Raises on the reference's
+    degenerate-eps quirk (base_quantizer.py:220-223), whose fp16 result is non-finite garbage in the reference."""
+    word = int(status_word(device).item())
+    if word & _lib.VQ_STATUS_EPS_DEGENERATE:
+        status_word(device).zero_()
+        raise _lib.VqError("dynamic act quant: a token row had delta < 1e-6 (reference quirk Q4: delta.fill_(1e-6) "
+                           "for ALL rows; in fp16 that yields inf/NaN) — refusing to continue")
+    return word
+
+
+@dataclass
+class PreparedWeight:
+    """u8 codes [N,K] + per-channel {c1, zw, dw, bias} records (16 B each) of one (layer, n_bits, timerange)."""
+    codes: torch.Tensor
+    col: torch.Tensor
+    N: int
+    K: int
+    n_bits: int
+
+
+@dataclass
+class ActCodes:
+    """u8 codes [G*rows,K], fp16 delta/zp [rows] (token statistics pooled over G), i32 rowsum [G*rows]."""
+    codes: torch.Tensor
+    delta: torch.Tensor
+    zp: torch.Tensor
+    rowsum: torch.Tensor
+    G: int
+    rows: int
+    K: int
+
+
+def prep_weight(w, delta, zp, n_bits=8, smooth=None, bias=None) -> PreparedWeight:
+    _need_cuda_f16(w, "weight")
+    N, K = w.shape
+    delta = delta.reshape(-1).to(torch.float16).contiguous()
+    zp = zp.reshape(-1).to(torch.float16).contiguous()
+    if delta.numel() != N or zp.numel() != N:
+        raise _lib.VqError("prep_weight: per-output-channel delta/zero_point expected")
+    if smooth is not None:
+        smooth = smooth.reshape(-1).to(torch.float16).contiguous()
+    if bias is not None:
+        bias = bias.reshape(-1).to(torch.float16).contiguous()
+    codes = torch.empty((N, K), dtype=torch.uint8, device=w.device)
+    col = torch.empty((N, 4), dtype=torch.int32, device=w.device)
+    rc = _lib.lib().vq_prep_weight(_ptr(w), _ptr(delta), _ptr(zp), _ptr(smooth), _ptr(bias), N, K, n_bits,
+                                   _ptr(codes), _ptr(col), _stream())
+    _lib.check(rc, "vq_prep_weight")
+    _count()
+    return PreparedWeight(codes, col, N, K, n_bits)
+
+
+def _alloc_act(G, rows, K, device):
+    return ActCodes(torch.empty((G * rows, K), dtype=torch.uint8, device=device),
+                    torch.empty(rows, dtype=torch.float16, device=device),
+                    torch.empty(rows, dtype=torch.float16, device=device),
+                    torch.empty(G * rows, dtype=torch.int32, device=device), G, rows, K)
+
+
+def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None) -> ActCodes:
+    """x: fp16 [G, rows, K] (reference layout [BS, n_token, C]); statistics per token pooled over G."""
+    _need_cuda_f16(x, "x")
+    G, rows, K = x.shape
+    a = out if out is not None else _alloc_act(G, rows, K, x.device)
+    if smooth is not None:
+        _need_cuda_f16(smooth, "smooth")
+    rc = _lib.lib().vq_act_quant(_ptr(x), G, rows, K, rows * K, K, _ptr(smooth), n_bits, _ptr(a.codes), _ptr(a.delta),
+                                 _ptr(a.zp), _ptr(a.rowsum), _ptr(status_word(x.device)), _stream())
+    _lib.check(rc, "vq_act_quant")
+    _count()
+    return a
+
+
+def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional[ActCodes] = None):
+    """x: fp16 [G, rows, K]; shift/scale: fp16 [G, K]. Returns (ActCodes, y or None)."""
+    _need_cuda_f16(x, "x")
+    _need_cuda_f16(shift, "shift")
+    _need_cuda_f16(scale, "scale")
+    G, rows, K = x.shape
+    a = out if out is not None else _alloc_act(G, rows, K, x.device)
+    y = torch.empty_like(x) if want_y else None
+    rc = _lib.lib().vq_ln_modulate_act_quant(_ptr(x), _ptr(shift), _ptr(scale), G, rows, K, n_bits, _ptr(y),
+                                             _ptr(a.codes), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum),
+                                             _ptr(status_word(x.device)), _stream())
+    _lib.check(rc, "vq_ln_modulate_act_quant")
+    _count()
+    return a, y
+
+
+def gemm_w8a8(a: ActCodes, w: PreparedWeight, epi=VQ_EPI_BIAS, res=None, gate=None, rows_per_gate=0, out=None):
+    """out[M,N] fp16 = epilogue(dequant(a.codes @ w.codes^T)); M = G*rows."""
+    M = a.G * a.rows
+    if a.K != w.K:
+        raise _lib.VqError(f"gemm_w8a8: K mismatch {a.K} vs {w.K}")
+    if out is None:
+        out = torch.empty((M, w.N), dtype=torch.float16, device=a.codes.device)
+    if epi == VQ_EPI_GATE_RESIDUAL:
+        _need_cuda_f16(res, "res")
+        _need_cuda_f16(gate, "gate")
+    rc = _lib.lib().vq_gemm_w8a8(_ptr(a.codes), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum), a.rows, _ptr(w.codes),
+                                 _ptr(w.col), M, w.N, w.K, epi, _ptr(res), w.N, _ptr(gate), rows_per_gate, _ptr(out),
+                                 w.N, _stream())
+    _lib.check(rc, "vq_gemm_w8a8")
+    _count()
+    return out
