@@ -80,3 +80,84 @@ def w8a8_dynamic_configs(n_temporal=16, n_spatial=1024, n_prompt=120, w_bits=8, 
                   round_mode="nearest_ste", running_stat=False, dynamic=True, sym=False, n_spatial_token=n_spatial,
                   n_temporal_token=n_temporal, n_prompt=n_prompt, smooth_quant=sq)
     return wq, aq
+
+
+def install_opensora():
+    """Make `opensora.models.stdit.stdit` / `opensora.models.layers.blocks` (the reference STDiT graph) importable
+    without executing opensora's package __init__ files (they pull in diffusers / transformers / colossalai).
+    Third-party pieces are replaced by minimal stand-ins: timm's DropPath / Mlp, and xformers' block-diagonal
+    memory_efficient_attention restated with torch SDPA per (sample, prompt) segment."""
+    install()
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    t2v = os.path.join(REFERENCE_ROOT, "t2v")
+
+    def pkg(name, path):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [path]
+            sys.modules[name] = m
+
+    pkg("opensora", os.path.join(t2v, "opensora"))
+    pkg("opensora.models", os.path.join(t2v, "opensora", "models"))
+    pkg("opensora.models.layers", os.path.join(t2v, "opensora", "models", "layers"))
+    pkg("opensora.models.stdit", os.path.join(t2v, "opensora", "models", "stdit"))
+    pkg("opensora.acceleration", os.path.join(t2v, "opensora", "acceleration"))
+    pkg("opensora.utils", os.path.join(t2v, "opensora", "utils"))
+    if "opensora.registry" not in sys.modules:
+        class _Registry:
+            def register_module(self, *a, **k):
+                def deco(obj):
+                    return obj
+                if len(a) == 1 and callable(a[0]) and not k:
+                    return a[0]
+                return deco
+        _module("opensora.registry", MODELS=_Registry(), SCHEDULERS=_Registry())
+    if "opensora.utils.ckpt_utils" not in sys.modules:
+        _module("opensora.utils.ckpt_utils", load_checkpoint=lambda *a, **k: None)
+    if "timm" not in sys.modules:
+        class DropPath(nn.Identity):
+            def __init__(self, *a, **k):
+                super().__init__()
+
+        class Mlp(nn.Module):
+            def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0,
+                         **unused):
+                super().__init__()
+                self.fc1 = nn.Linear(in_features, hidden_features or in_features)
+                self.act = act_layer()
+                self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
+
+            def forward(self, x):
+                return self.fc2(self.act(self.fc1(x)))
+        _module("timm")
+        _module("timm.models")
+        _module("timm.models.layers", DropPath=DropPath)
+        _module("timm.models.vision_transformer", Mlp=Mlp)
+    if "xformers" not in sys.modules:
+        class BlockDiagonalMask:
+            def __init__(self, q_lens, kv_lens):
+                self.q_lens, self.kv_lens = list(q_lens), list(kv_lens)
+
+            @classmethod
+            def from_seqlens(cls, q_seqlen, kv_seqlen=None):
+                return cls(q_seqlen, kv_seqlen if kv_seqlen is not None else q_seqlen)
+
+        def memory_efficient_attention(q, k, v, p=0.0, attn_bias=None):
+            # q [1, sum(Nq), H, D], k/v [1, sum(Nk), H, D]
+            if attn_bias is None:
+                o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+                return o.transpose(1, 2)
+            outs, qo, ko = [], 0, 0
+            for nq, nk in zip(attn_bias.q_lens, attn_bias.kv_lens):
+                qq = q[:, qo:qo + nq].transpose(1, 2)
+                kk = k[:, ko:ko + nk].transpose(1, 2)
+                vv = v[:, ko:ko + nk].transpose(1, 2)
+                outs.append(F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2))
+                qo += nq
+                ko += nk
+            return torch.cat(outs, dim=1)
+        fmha = _module("xformers.ops.fmha", BlockDiagonalMask=BlockDiagonalMask)
+        xo = _module("xformers.ops", memory_efficient_attention=memory_efficient_attention, fmha=fmha)
+        _module("xformers", ops=xo)

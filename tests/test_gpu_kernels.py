@@ -126,9 +126,13 @@ def test_gemm_epilogues_vs_oracle(ops, epi):
     yo = O.quant_linear_int(oa["codes"], oa["delta"], oa["zp"], oa["rowsum"], wq["codes"], wd, wz, b, epi=epi,
                             res16=res, gate16=gate)
     y = y.cpu().numpy().reshape(1, M, N)
-    ulp = np.abs(y.view(np.int16).astype(np.int32) - yo.view(np.int16).astype(np.int32))
-    assert ulp.max() <= 1, ulp.max()              # gelu: __expf vs float64 tanh -> at most the last fp16 bit
-    assert (ulp > 0).mean() <= (2e-3 if epi == "gelu_tanh" else 1e-5)
+    mism = (y.view(np.uint16) != yo.view(np.uint16))
+    # identical integer accumulators; the only freedom is the last fp16 bit of y (fma vs float64 double rounding,
+    # __expf vs float64 tanh in GELU), which the gated residual can carry through a cancellation
+    assert mism.mean() <= (2e-3 if epi == "gelu_tanh" else 1e-5), mism.mean()
+    scale = np.float16(np.abs(yo.astype(np.float32)).max() if epi != "gate_residual" else
+                       max(np.abs(res.astype(np.float32)).max(), np.abs(yo.astype(np.float32)).max()))
+    assert np.abs(y.astype(np.float32) - yo.astype(np.float32)).max() <= 2 * float(np.spacing(scale))
 
 
 def test_config1_full_size_w8a8_linear(ops):

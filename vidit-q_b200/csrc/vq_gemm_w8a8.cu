@@ -43,7 +43,8 @@ constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int EPI_CHUNK = 32;                         // output columns per epilogue step (64 B of fp16 per row)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one warp's staging tile: 32 rows x 64 B, SWIZZLE_64B
 constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 2 * EPI_BUF_BYTES;  // double-buffered per warp
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + 256 + 1024;
+constexpr int COLBUF_BYTES = 2 * BN * 16;                // per-tile {c1, zw, dw, bias} records, double-buffered
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + COLBUF_BYTES + 256 + 1024;
 
 struct GemmArgs {
   int M, N, K;
@@ -76,17 +77,15 @@ constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (mea
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&v)[32], int row, int col0,
                                                int32_t zx, int32_t rs, float dx, bool row_ok, uint8_t* stage,
-                                               int lane) {
-  const int4* colp = reinterpret_cast<const int4*>(p.col);
-  const int nmax = p.N - 1;
+                                               int lane, const int4* colp) {
+  // colp: this chunk's 32 column records in shared memory (warp-uniform address -> broadcast LDS.128)
   uint32_t packed[16];
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     float f[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      int n = col0 + j + e;
-      int4 cp = __ldg(colp + (n < nmax ? n : nmax));
+      int4 cp = colp[j + e];
       int32_t t = static_cast<int32_t>(v[j + e]) - zx * cp.x - rs * cp.y;
       float s = dx * __int_as_float(cp.z);
       f[e] = fmaf(static_cast<float>(t), s, __int_as_float(cp.w));
@@ -139,7 +138,8 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* smem_epi = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGING_BYTES);
+  int4* colbuf = reinterpret_cast<int4*>(smem_epi + EPI_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGING_BYTES + COLBUF_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -231,9 +231,18 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== epilogue =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int h = (warp - 4) >> 2;   // column half
+    const int et = threadIdx.x - 128;  // 0..255 within the epilogue warps
     uint8_t* stage0 = smem_epi + (warp - 4) * 2 * EPI_BUF_BYTES;
+    const int4* colg = reinterpret_cast<const int4*>(p.col);
+    const int nmax = p.N - 1;
     int buf = 0;
     int local = 0;
+    // column records of the first tile -> colbuf[0]
+    if (blockIdx.x < num_tiles && et < BN) {
+      const int n = (blockIdx.x / num_m_tiles) * BN + et;
+      colbuf[et] = __ldg(colg + (n < nmax ? n : nmax));
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -247,28 +256,32 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const float dx = __half2float(p.a_delta[srow]);
       const int32_t zx = __float2int_rn(__half2float(p.a_zp[srow]));
       const int32_t rs = p.a_rowsum[row_c];
+      // prefetch the next tile's column record (consumed after this tile's math)
+      const int next_tile = tile + gridDim.x;
+      int4 next_col = make_int4(0, 0, 0, 0);
+      if (next_tile < num_tiles && et < BN) {
+        const int n = (next_tile / num_m_tiles) * BN + et;
+        next_col = __ldg(colg + (n < nmax ? n : nmax));
+      }
+      const int4* ctile = colbuf + acc * BN + h * (BN / 2);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * (BN / 2);
       constexpr int NCHUNK = BN / 2 / EPI_CHUNK;
-#pragma unroll 1
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(t_base, v[0]);
+      tmem_ld_wait();
+#pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_base + c * EPI_CHUNK, v);
-        tmem_ld_wait();
-        if (c == NCHUNK - 1) {
-          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp before the math
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is dequantised
+        if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_base + (c + 1) * EPI_CHUNK, v[(c + 1) & 1]);
         const int col0 = n_idx + h * (BN / 2) + c * EPI_CHUNK;
         if (EPI != VQ_EPI_DEBUG_MAINLOOP && col0 < p.N && row0 < p.M) {
           uint8_t* stage = stage0 + buf * EPI_BUF_BYTES;
           if (lane == 0) tma_store_wait_read<1>();  // the TMA store that last read this buffer has drained
           __syncwarp();
-          epilogue_chunk<EPI>(p, v, row, col0, zx, rs, dx, row_ok, stage, lane);
+          epilogue_chunk<EPI>(p, v[c & 1], row, col0, zx, rs, dx, row_ok, stage, lane, ctile + c * EPI_CHUNK);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -277,7 +290,18 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           buf ^= 1;
         }
+        if (c + 1 < NCHUNK) {
+          tmem_ld_wait();
+        } else {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
       }
+      // publish the next tile's column records; the barrier also orders this tile's reads of the other buffer
+      if (et < BN) colbuf[(acc ^ 1) * BN + et] = next_col;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (lane == 0) tma_store_wait<0>();
     __syncwarp();

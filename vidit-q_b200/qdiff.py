@@ -1,0 +1,564 @@
+"""Host-side mirror of the reference's quantised-operator API (qdiff/), backed by the sm_100a kernels.
+
+Same class names, constructor arguments, state attributes and checkpoint format as the reference so that scripts and
+PTQ-calibrated `ckpt.pth` files work unchanged:
+
+    QuantModel(model, weight_quant_params, act_quant_params, model_type)      qdiff/models/quant_model.py:38
+    QuantLayer / QuantSpatialAttnLinear / QuantTemporalAttnLinear / QuantCrossAttnLinear          (STDiT)
+    QuantAttnLinearImg / QuantCrossAttnLinearImg                                                   (PixArt)
+    load_quant_params(qnn, ckpt_path)                                          qdiff/utils.py:65
+
+What differs is what `forward` executes: when both weight and activation quantisation are enabled the layer runs
+  vq_act_quant (per-token dynamic u8 codes) -> vq_gemm_w8a8 (tcgen05 INT8 GEMM + dequant epilogue)
+on prepared u8 weight codes, instead of fake-quantising in fp16 and calling F.linear.  Layers left in floating point
+(`remain_fp.txt`) run F.linear as in the reference.  PTQ-time modes (weight-only simulation, static activation
+calibration, learned rounding, running-stat smooth-quant collection) are out of scope and raise NotImplementedError.
+Nothing here falls back to a CPU or fake-quant path.
+"""
+import logging
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+logger = logging.getLogger(__name__)
+
+
+def find_interval(timerange, timestep_id):
+    """Index of the [lo, hi] interval containing timestep_id (reference quant_layer.py:15)."""
+    for i, (lo, hi) in enumerate(timerange):
+        if lo <= timestep_id <= hi:
+            return i
+    return None
+
+
+def _cfg_get(cfg, key, default=None):
+    if cfg is None:
+        return default
+    if hasattr(cfg, "get"):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# quantiser state holders (buffers named exactly like the reference's so ckpt.pth round-trips)
+# ---------------------------------------------------------------------------------------------------------------------
+class BaseQuantizer(nn.Module):
+    """State of one uniform-affine quantiser (reference base_quantizer.py:13-72). Holds parameters; the arithmetic
+    lives in the CUDA kernels."""
+
+    def __init__(self, quant_config):
+        super().__init__()
+        self.n_bits = _cfg_get(quant_config, "n_bits")
+        self.mixed_precision = _cfg_get(quant_config, "mixed_precision")
+        self.timestep_wise = _cfg_get(quant_config, "timestep_wise")
+        self.bit_idx = self.mixed_precision.index(self.n_bits) if self.mixed_precision is not None else 0
+        self.cur_timestep_id = 0
+        self.per_group = _cfg_get(quant_config, "per_group")
+        self.channel_dim = _cfg_get(quant_config, "channel_dim", 0)
+        self.scale_method = _cfg_get(quant_config, "scale_method")
+        self.round_mode = _cfg_get(quant_config, "round_mode")
+        self.sym = _cfg_get(quant_config, "sym", False)
+        self.running_stat = _cfg_get(quant_config, "running_stat", False)
+        self.n_bitwidth = len(self.mixed_precision) if self.mixed_precision is not None else 1
+        for name in ("delta_list", "zero_point_list", "delta", "zero_point", "alpha"):
+            self.register_buffer(name, None)
+        self.init_done = False
+
+    def bitwidth_refactor(self, refactored_bit: int):
+        """Reference base_quantizer.py:319-325: changes n_bits / bit_idx only — delta and zero_point are NOT
+        re-selected once init_done (quirk Q7), so an '8-bit' layer of a 4-bit-calibrated ckpt stays on the 4-bit grid."""
+        assert 2 <= refactored_bit <= 16, "bitwidth not supported"
+        self.n_bits = refactored_bit
+        if self.mixed_precision is not None:
+            self.bit_idx = self.mixed_precision.index(self.n_bits)
+
+    def forward(self, x):
+        raise NotImplementedError("viditq_b200 quantisers hold state only; the fused kernels do the arithmetic")
+
+    def extra_repr(self):
+        return f"bit={self.n_bits}, per_group={self.per_group}, sym={self.sym}"
+
+
+class WeightQuantizer(BaseQuantizer):
+    pass
+
+
+class ActQuantizer(BaseQuantizer):
+    pass
+
+
+class DynamicActQuantizer(ActQuantizer):
+    pass
+
+
+class StraightThrough(nn.Module):
+    def forward(self, x):
+        return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# QuantLayer family
+# ---------------------------------------------------------------------------------------------------------------------
+class QuantLayer(nn.Module):
+    """Drop-in for reference QuantLayer (quant_layer.py:22): forward(input) on [B, n_token, C] fp16."""
+
+    def __init__(self, org_module: nn.Linear, weight_quant_params=None, act_quant_params=None,
+                 disable_act_quant: bool = False, act_quant_mode: str = "qdiff"):
+        super().__init__()
+        if not isinstance(org_module, nn.Linear):
+            raise NotImplementedError("viditq_b200 accelerates nn.Linear QuantLayers (all STDiT/PixArt quantised layers)")
+        self.weight_quant_params = weight_quant_params
+        self.act_quant_params = act_quant_params
+        self.in_features = org_module.in_features
+        self.out_features = org_module.out_features
+        self.weight = org_module.weight
+        self.org_weight = org_module.weight
+        self.bias = org_module.bias
+        self.org_bias = org_module.bias
+        self.org_module = org_module
+        self.weight_quant = False
+        self.act_quant = False
+        self.act_quant_mode = act_quant_mode
+        self.disable_act_quant = disable_act_quant
+        if weight_quant_params is not None:
+            self.weight_quantizer = WeightQuantizer(weight_quant_params)
+        if act_quant_params is not None:
+            dyn = _cfg_get(act_quant_params, "dynamic", False)
+            self.act_quantizer = DynamicActQuantizer(act_quant_params) if dyn else ActQuantizer(act_quant_params)
+        self.split = 0
+        self.activation_function = StraightThrough()
+        self.ignore_reconstruction = False
+        self.cur_timestep_id = 0
+        sq = _cfg_get(act_quant_params, "smooth_quant", {}) or {}
+        self.smooth_quant = bool(_cfg_get(sq, "enable", False))
+        if self.smooth_quant:
+            self.timerange = _cfg_get(sq, "timerange", [[0, 1000]])
+            prev = -1
+            for lo, hi in self.timerange:
+                assert lo == prev + 1
+                prev = hi
+            assert prev == 1000
+            self.timerange_num = len(self.timerange)
+            self.act_quantizer.register_buffer("act_scale", None)
+            self.channel_wise_scale_type = _cfg_get(sq, "channel_wise_scale_type", "dynamic")
+            self.smooth_quant_momentum = _cfg_get(sq, "momentum", 0)
+            self.smooth_quant_alpha = _cfg_get(sq, "alpha", None)
+            self.smooth_quant_running_stat = False
+        self._prepared = {}  # (n_bits, timerange_id) -> ops.PreparedWeight
+
+    # -- state -----------------------------------------------------------------------------------------------------
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.weight_quant = weight_quant
+        self.act_quant = act_quant
+
+    def get_quant_state(self):
+        return self.weight_quant, self.act_quant
+
+    def invalidate_prepared(self):
+        """Drop cached u8 weight codes (call after changing weights or weight-quantiser buffers)."""
+        self._prepared.clear()
+
+    def _apply(self, fn, *a, **k):  # .cuda()/.half() move the source tensors: prepared codes are stale
+        self._prepared = {}
+        return super()._apply(fn, *a, **k)
+
+    # -- helpers ---------------------------------------------------------------------------------------------------
+    def _timerange_id(self):
+        if not hasattr(self, "timerange"):
+            return 0
+        return find_interval(self.timerange, self.cur_timestep_id)
+
+    def channel_wise_scale(self, tr_id):
+        """quant_layer.py:137: act_scale[tr]^alpha / max_n |W|^(1-alpha), evaluated with torch half ops exactly as the
+        reference does (load-time work, cached per timerange)."""
+        if "momentum" not in self.channel_wise_scale_type:
+            raise NotImplementedError("smooth-quant channel_wise_scale_type 'dynamic' (input-dependent) is not fused")
+        if getattr(self, "smooth_quant_running_stat", False):
+            raise NotImplementedError("smooth_quant_running_stat=True is a calibration-time mode")
+        alpha = self.smooth_quant_alpha
+        if isinstance(alpha, (list, tuple)) or type(alpha).__name__ == "ListConfig":
+            alpha = alpha[tr_id]
+        act_scale = self.act_quantizer.act_scale[tr_id]
+        s = act_scale.pow(alpha) / self.weight.abs().max(dim=0)[0].pow(1 - alpha)
+        return s.reshape(-1).contiguous()
+
+    def prepared_weight(self):
+        wq = self.weight_quantizer
+        tr = self._timerange_id() if self.smooth_quant else 0
+        key = (wq.n_bits, tr)
+        pw = self._prepared.get(key)
+        if pw is None:
+            if wq.delta is None or not wq.init_done:
+                raise RuntimeError("weight quantiser has no parameters: load a PTQ ckpt (load_quant_params) or run "
+                                   "QuantModel.init_weight_quant_params() first")
+            if wq.sym or wq.per_group != "channel" or wq.n_bits > 8:
+                raise NotImplementedError("fused path supports asymmetric per-output-channel weights, <= 8 bits")
+            smooth = self.channel_wise_scale(tr) if self.smooth_quant else None
+            pw = ops.prep_weight(self.weight.data, wq.delta, wq.zero_point, n_bits=wq.n_bits, smooth=smooth,
+                                 bias=None if self.bias is None else self.bias.data)
+            pw.smooth = smooth
+            self._prepared[key] = pw
+        return pw
+
+    def _pool_view(self, input):
+        """(G, rows) of the per-token statistics pool; subclasses restate the reference's reshape tricks."""
+        return input.shape[0], input.shape[1]
+
+    def _check_act_quantizer(self):
+        aq = self.act_quantizer
+        if not isinstance(aq, DynamicActQuantizer) or aq.per_group != "token" or aq.sym or aq.n_bits > 8:
+            raise NotImplementedError("fused path supports dynamic per-token asymmetric activations, <= 8 bits "
+                                      "(the ViDiT-Q W8A8 / W4A8 configs)")
+
+    def quantize_input(self, input):
+        """Per-token dynamic activation quantisation of a [*, n, C] fp16 tensor -> ops.ActCodes."""
+        self._check_act_quantizer()
+        G, rows = self._pool_view(input)
+        x = input.reshape(G, rows, input.shape[-1])
+        if not x.is_contiguous():
+            x = x.contiguous()
+        pw = self.prepared_weight()
+        return ops.act_quant(x, n_bits=self.act_quantizer.n_bits, smooth=getattr(pw, "smooth", None))
+
+    # -- forward ---------------------------------------------------------------------------------------------------
+    def forward(self, input: torch.Tensor, scale: float = 1.0, split: int = 0, smooth_quant_enable: bool = False):
+        if split != 0 or self.split != 0:
+            raise NotImplementedError("split quantisation (UNet skip-concat) does not occur in STDiT/PixArt")
+        act_q = self.act_quant and not self.disable_act_quant
+        if self.weight_quant and act_q:
+            a = self.quantize_input(input)
+            out = ops.gemm_w8a8(a, self.prepared_weight())
+            return out.view(*input.shape[:-1], self.out_features)
+        if not self.weight_quant and not act_q:
+            if self.smooth_quant:
+                raise NotImplementedError("FP forward of a smooth-quant layer (calibration-time) is out of scope")
+            return F.linear(input, self.org_weight, self.org_bias)
+        raise NotImplementedError("weight-only / activation-only simulated quantisation is a PTQ-time mode; the B200 "
+                                  "path runs W+A quantised or full-precision layers")
+
+    def extra_repr(self):
+        return f"in={self.in_features}, out={self.out_features}, wq={self.weight_quant}, aq={self.act_quant}"
+
+
+class QuantSpatialAttnLinear(QuantLayer):
+    """stdit_quant_layer.py:10: input (B*T, S, C); statistics over the view (B, T*S, C)."""
+
+    def _pool_view(self, input):
+        T = self.act_quant_params["n_temporal_token"]
+        S = self.act_quant_params["n_spatial_token"]
+        assert input.shape[1] == S
+        return input.shape[0] // T, T * S
+
+
+class QuantTemporalAttnLinear(QuantLayer):
+    """stdit_quant_layer.py:101: input (B*S, T, C); statistics over the view (B, S*T, C)."""
+
+    def _pool_view(self, input):
+        T = self.act_quant_params["n_temporal_token"]
+        S = self.act_quant_params["n_spatial_token"]
+        assert input.shape[1] == T
+        return input.shape[0] // S, S * T
+
+
+class QuantCrossAttnLinear(QuantLayer):
+    """stdit_quant_layer.py:192: q_linear/proj see (B, T*S, C); kv_linear sees (1, sum(len), C) -> one token per row."""
+
+
+class QuantAttnLinearImg(QuantLayer):
+    """dit_quant_layer.py:9 (PixArt): plain (B, N, C), no smooth-quant path."""
+
+
+class QuantCrossAttnLinearImg(QuantLayer):
+    """dit_quant_layer.py:34 (PixArt)."""
+
+
+class BaseQuantBlock(nn.Module):
+    """Placeholder for the reference's diffusers-only quant blocks (unused for STDiT/PixArt)."""
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# QuantModel
+# ---------------------------------------------------------------------------------------------------------------------
+def pattern_in(text, pattern):
+    """Dotted-name match with '*' wildcards and '[a-b]' integer ranges (semantics of quant_model.py:14-36)."""
+    pats = pattern.split(".")
+    toks = text.split(".")
+    for start in range(len(toks)):
+        ok = True
+        for j, p in enumerate(pats):
+            if p == "*":
+                continue
+            if start + j >= len(toks):
+                raise IndexError("pattern runs past the module name")  # the reference indexes out of range here too
+            t = toks[start + j]
+            if "[" in p and "]" in p:
+                lo, hi = p[1:-1].split("-")
+                if t not in [str(v) for v in range(int(lo), int(hi) + 1)]:
+                    ok = False
+                    break
+            elif t != p:
+                ok = False
+                break
+        if ok:
+            return True
+    return False
+
+
+def _safe_pattern_in(text, pattern):
+    try:
+        return pattern_in(text, pattern)
+    except IndexError:
+        return False
+
+
+class QuantModel(nn.Module):
+    def __init__(self, model: nn.Module, weight_quant_params=None, act_quant_params=None, model_type="opensora",
+                 **kwargs):
+        super().__init__()
+        self.weight_quant = weight_quant_params is not None
+        self.act_quant = act_quant_params is not None
+        self.model_type = model_type
+        self.timestep_wise = _cfg_get(act_quant_params, "timestep_wise", False)
+        self.model = model
+        self.in_channels = model.in_channels
+        if hasattr(model, "image_size"):
+            self.image_size = model.image_size
+        self.quant_layer_refactor(self.model, weight_quant_params, act_quant_params)
+        self.quant_params_dict = {}
+
+    # replacement rules of quant_model.py:63-103
+    def quant_layer_refactor(self, module, weight_quant_params, act_quant_params, prefix=""):
+        for name, child in module.named_children():
+            full = prefix + name if prefix else name
+            if isinstance(child, nn.Linear):
+                if ".attn." in full:
+                    cls = QuantSpatialAttnLinear if self.model_type == "opensora" else QuantAttnLinearImg
+                elif "cross_attn" in full:
+                    cls = QuantCrossAttnLinear if self.model_type == "opensora" else QuantCrossAttnLinearImg
+                elif "attn_temp" in full:
+                    cls = QuantTemporalAttnLinear
+                else:
+                    cls = QuantLayer
+                setattr(module, name, cls(child, weight_quant_params, act_quant_params))
+            elif isinstance(child, (nn.Conv1d, nn.Conv2d)):
+                if self.model_type == "opensora":
+                    raise AssertionError("only linear layers are quantised in the STDiT model")
+                # PixArt's x_embedder conv stays FP via the fp list in every shipped script; leave it untouched
+            elif isinstance(child, (StraightThrough, QuantLayer)):
+                continue
+            else:
+                self.quant_layer_refactor(child, weight_quant_params, act_quant_params, prefix=full + ".")
+
+    def quant_layers(self):
+        for name, m in self.model.named_modules():
+            if isinstance(m, QuantLayer):
+                yield name, m
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.weight_quant = weight_quant
+        self.act_quant = act_quant
+        for _, m in self.quant_layers():
+            m.set_quant_state(weight_quant, act_quant)
+        if hasattr(self, "fp_layer_list"):
+            self.set_layer_quant(model=self, module_name_list=self.fp_layer_list, quant_level="per_layer",
+                                 weight_quant=False, act_quant=False, prefix="")
+
+    def get_quant_state(self):
+        return self.weight_quant, self.act_quant
+
+    def set_module_name_for_quantizer(self, module, prefix=""):
+        for name, child in module.named_children():
+            full = prefix + name if prefix else name
+            if isinstance(child, BaseQuantizer):
+                child.module_name = full
+            else:
+                self.set_module_name_for_quantizer(child, prefix=full + ".")
+
+    def set_timestep_for_quantizer(self, t, module=None):
+        for m in (self if module is None else module).modules():
+            if isinstance(m, BaseQuantizer):
+                m.cur_timestep_id = t
+
+    def set_timestep_id_for_quantlayer(self, t, module=None):
+        for m in (self if module is None else module).modules():
+            if isinstance(m, QuantLayer):
+                m.cur_timestep_id = t
+
+    def set_quant_init_done(self, quantizer_type_name, module=None):
+        kind = {"weight": WeightQuantizer, "activation": ActQuantizer}.get(quantizer_type_name)
+        if kind is None:
+            raise NotImplementedError
+        for m in (self.model if module is None else module).modules():
+            if isinstance(m, kind):
+                m.init_done = True
+
+    # ckpt format of quant_model.py:220-269: {quantizer module_name: [buffers OrderedDict, parameters OrderedDict]}
+    def get_quant_params_dict(self, module=None, prefix="", dtype=torch.float32):
+        if module is None:
+            module = self.model
+            self.quant_params_dict = {}
+        for name, child in module.named_children():
+            full = prefix + name if prefix else name
+            if isinstance(child, BaseQuantizer):
+                self.quant_params_dict[child.module_name] = [child._buffers, child._parameters]
+            else:
+                self.get_quant_params_dict(module=child, prefix=full + ".")
+        return self.quant_params_dict
+
+    def set_quant_params_dict(self, quant_params_dict, module=None, load_buffer_only=True, dtype=torch.float32):
+        if module is None:
+            module = self.model
+        for _, child in module.named_children():
+            if isinstance(child, BaseQuantizer):
+                entry = quant_params_dict[child.module_name]
+                if load_buffer_only:
+                    assert len(entry[1]) == 0
+                for bname, val in entry[0].items():
+                    setattr(child, bname, val.to(dtype) if val is not None else None)
+            else:
+                self.set_quant_params_dict(quant_params_dict, module=child, load_buffer_only=load_buffer_only,
+                                           dtype=dtype)
+        for _, m in self.quant_layers():
+            m.invalidate_prepared()
+
+    def set_smooth_quant(self, smooth_quant, smooth_quant_running_stat):
+        self.smooth_quant_stat = smooth_quant_running_stat
+        for _, m in self.quant_layers():
+            m.smooth_quant = smooth_quant
+            m.smooth_quant_running_stat = smooth_quant_running_stat
+            m.invalidate_prepared()
+
+    def set_layer_smooth_quant(self, model, module_name_list, smooth_quant, smooth_quant_running_stat, prefix=""):
+        for name, module in model.named_children():
+            full = prefix + name if prefix else name
+            if isinstance(module, QuantLayer):
+                for pat in module_name_list:
+                    if _safe_pattern_in(full, pat) or _safe_pattern_in(full, "model." + pat):
+                        module.smooth_quant_running_stat = smooth_quant_running_stat
+                        module.smooth_quant = smooth_quant
+                        module.invalidate_prepared()
+            else:
+                self.set_layer_smooth_quant(module, module_name_list, smooth_quant, smooth_quant_running_stat,
+                                            prefix=full + ".")
+
+    def set_layer_quant(self, model=None, module_name_list=(), group_list=(), group_ignore=(), quant_level="per_layer",
+                        weight_quant=True, act_quant=False, prefix=""):
+        if quant_level not in ("per_layer", "per_group"):
+            raise NotImplementedError("per_block quant levels address diffusers blocks (unused for STDiT/PixArt)")
+        for name, module in model.named_children():
+            full = prefix + name if prefix else name
+            if isinstance(module, QuantLayer):
+                if quant_level == "per_layer":
+                    for pat in module_name_list:
+                        if _safe_pattern_in(full, pat) or _safe_pattern_in(full, "model." + pat):
+                            module.set_quant_state(weight_quant=weight_quant, act_quant=act_quant)
+                else:
+                    for cls_name in group_list:
+                        hit = cls_name in full
+                        if cls_name == "attn":
+                            hit = hit and "cross_attn" not in full and "attn_temp" not in full
+                        if hit and all(e not in full for e in group_ignore):
+                            module.set_quant_state(weight_quant=weight_quant, act_quant=act_quant)
+            else:
+                self.set_layer_quant(model=module, module_name_list=module_name_list, group_list=group_list,
+                                     group_ignore=group_ignore, quant_level=quant_level, weight_quant=weight_quant,
+                                     act_quant=act_quant, prefix=full + ".")
+
+    def load_bitwidth_config(self, model, bit_config, bit_type, prefix=""):
+        """quant_model.py:562-586: per-layer bit-width table -> quantizer.bitwidth_refactor."""
+        for name, module in model.named_children():
+            full = prefix + name if prefix else name
+            if isinstance(module, QuantLayer):
+                if full in bit_config.keys():
+                    if bit_type == "weight":
+                        module.weight_quantizer.bitwidth_refactor(bit_config[full])
+                    elif bit_type == "act":
+                        module.act_quantizer.bitwidth_refactor(bit_config[full])
+            else:
+                self.load_bitwidth_config(model=module, bit_config=bit_config, bit_type=bit_type, prefix=full + ".")
+
+    @torch.no_grad()
+    def init_weight_quant_params(self):
+        """Min-max per-output-channel weight parameters for every bit-width in `mixed_precision` — what the reference's
+        PTQ weight pass (ptq.py:266-294 -> base_quantizer.py:166-228, 'channel' branch) stores into ckpt.pth.  Load-time
+        torch ops on the weight's device; provided so synthetic-weight models can be benchmarked without a PTQ run."""
+        for _, m in self.quant_layers():
+            wq = m.weight_quantizer
+            w = m.weight.data.float()
+            bits = wq.mixed_precision if wq.mixed_precision is not None else [wq.n_bits]
+            n_t = len(m.timerange) if m.smooth_quant else 1
+            dl = torch.empty(len(bits), n_t, w.shape[0], 1, device=w.device)
+            zl = torch.empty_like(dl)
+            for t in range(n_t):
+                wt = w * m.channel_wise_scale(t).float()[None, :] if m.smooth_quant else w
+                mn = wt.min(dim=-1)[0].clamp(max=0.0)
+                mx = wt.max(dim=-1)[0].clamp(min=0.0)
+                for i, b in enumerate(bits):
+                    delta = (mx - mn) / (2 ** b - 1)
+                    if delta.min() < 1e-6:
+                        delta = torch.full_like(delta, 1e-6)
+                    dl[i, t, :, 0] = delta
+                    zl[i, t, :, 0] = torch.round(-mn / delta)
+            wq.delta_list, wq.zero_point_list = dl, zl
+            wq.delta = dl[wq.bit_idx, 0].to(m.weight.dtype)
+            wq.zero_point = zl[wq.bit_idx, 0].to(m.weight.dtype)
+            wq.init_done = True
+            m.invalidate_prepared()
+
+    def forward(self, x, t, y, **kwargs):
+        """quant_model.py:337-360: broadcast the scalar timestep to every QuantLayer, then run the wrapped model."""
+        t0 = t[0].item() if isinstance(t, torch.Tensor) else float(t)
+        if self.timestep_wise:
+            self.set_timestep_for_quantizer(t0)
+        self.set_timestep_id_for_quantlayer(t0)
+        return self.model(x, t, y, **kwargs)
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(self.model, name)
+
+
+@torch.no_grad()
+def load_quant_params(qnn, ckpt_path, dtype=torch.float32):
+    """qdiff/utils.py:65-70."""
+    ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+    qnn.set_module_name_for_quantizer(module=qnn.model)
+    qnn.set_quant_params_dict(ckpt, dtype=dtype)
+
+
+def accelerate(qnn):
+    """Swap the forward of every *reference* QuantLayer inside `qnn` (an unmodified qdiff QuantModel, after
+    load_quant_params / .cuda() / .to(fp16)) for the fused kernels, in place. The reference module objects, their
+    quantiser buffers and all QuantModel methods stay as they are."""
+    mapping = {"QuantLayer": QuantLayer, "QuantSpatialAttnLinear": QuantSpatialAttnLinear,
+               "QuantTemporalAttnLinear": QuantTemporalAttnLinear, "QuantCrossAttnLinear": QuantCrossAttnLinear,
+               "QuantAttnLinearImg": QuantAttnLinearImg, "QuantCrossAttnLinearImg": QuantCrossAttnLinearImg}
+    n = 0
+    for mod in qnn.model.modules():
+        cls = mapping.get(type(mod).__name__)
+        if cls is None or isinstance(mod, QuantLayer) or not hasattr(mod, "weight_quantizer"):
+            continue
+        ours = cls(mod.org_module, mod.weight_quant_params, mod.act_quant_params)
+        for qname in ("weight_quantizer", "act_quantizer"):
+            src, dst = getattr(mod, qname), getattr(ours, qname)
+            for bname, val in src._buffers.items():
+                setattr(dst, bname, val)
+            dst.n_bits, dst.bit_idx, dst.init_done = src.n_bits, src.bit_idx, src.init_done
+        ours.weight_quant, ours.act_quant = mod.weight_quant, mod.act_quant
+        ours.smooth_quant = getattr(mod, "smooth_quant", False)
+
+        def fwd(input, scale=1.0, split=0, _ours=ours, _ref=mod, **kw):
+            _ours.cur_timestep_id = getattr(_ref, "cur_timestep_id", 0)
+            _ours.weight_quant, _ours.act_quant = _ref.weight_quant, _ref.act_quant
+            _ours.weight_quantizer.n_bits = _ref.weight_quantizer.n_bits
+            return _ours(input)
+        mod.forward = fwd
+        mod._viditq_b200 = ours
+        n += 1
+    return n

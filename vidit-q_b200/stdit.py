@@ -1,0 +1,376 @@
+"""STDiT-XL/2 (OpenSORA v1.0 video DiT) graph around the quantised linears — the caller side of the hot path.
+
+Parameter / buffer names mirror the reference (t2v/opensora/models/stdit/stdit.py:136-341, layers/blocks.py) so a
+reference state_dict and a PTQ `ckpt.pth` load unchanged, and `viditq_b200.qdiff.QuantModel` applies the same
+name-based layer replacement rules (quant_model.py:78-97).
+
+Two forward schedules over the same parameters:
+  * `forward`        — the reference's graph, one QuantLayer call per linear (13 per block, stdit.py:96-133).
+  * `forward_fused`  — the B200 schedule: one LayerNorm+modulate+quantise pass feeds a single N=3456 q|k|v GEMM
+                       (the reference quantises the same tensor three times, blocks.py:155-157), gated residuals and
+                       GELU run in the GEMM epilogues, the temporal branch reads the (T S) token layout in place.
+    Every rounding point of the reference's fp16 graph is kept, so both schedules agree to the last bit except for
+    LayerNorm statistics (fp32 here, library-dependent there).
+Attention itself is a library call for now (torch SDPA, as the reference calls flash-attn / xformers).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .qdiff import QuantLayer
+
+
+def _sincos_1d(dim, pos):
+    omega = np.arange(dim // 2, dtype=np.float64) / (dim / 2.0)
+    omega = 1.0 / 10000 ** omega
+    out = np.einsum("m,d->md", np.asarray(pos, dtype=np.float64).reshape(-1), omega)
+    return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+
+def _sincos_2d(dim, gh, gw, scale=1.0):
+    h = np.arange(gh, dtype=np.float32) / scale
+    w = np.arange(gw, dtype=np.float32) / scale
+    grid = np.stack(np.meshgrid(w, h), axis=0).reshape(2, 1, gw, gh)  # w first, as in blocks.py:565-569
+    return np.concatenate([_sincos_1d(dim // 2, grid[0]), _sincos_1d(dim // 2, grid[1])], axis=1)
+
+
+class PatchEmbed3D(nn.Module):
+    def __init__(self, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.patch_size = patch_size
+        self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)
+
+
+class TimestepEmbedder(nn.Module):
+    def __init__(self, hidden_size, frequency_embedding_size=256):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(frequency_embedding_size, hidden_size), nn.SiLU(),
+                                 nn.Linear(hidden_size, hidden_size))
+        self.frequency_embedding_size = frequency_embedding_size
+
+    def forward(self, t, dtype):
+        half = self.frequency_embedding_size // 2
+        freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+        args = t[:, None].float() * freqs[None]
+        emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1).to(dtype)
+        return self.mlp(emb)
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features, out_features=None):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU(approximate="tanh")
+        self.fc2 = nn.Linear(hidden_features, out_features or in_features)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class CaptionEmbedder(nn.Module):
+    def __init__(self, in_channels, hidden_size, token_num=120):
+        super().__init__()
+        self.y_proj = Mlp(in_channels, hidden_size, hidden_size)
+        self.register_buffer("y_embedding", torch.randn(token_num, in_channels) / in_channels ** 0.5)
+
+    def forward(self, caption):
+        return self.y_proj(caption)
+
+
+class Attention(nn.Module):
+    """Self-attention with separate q/k/v linears (blocks.py:113-195, separate_qkv=True)."""
+
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads, self.head_dim = num_heads, dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.q = nn.Linear(dim, dim)
+        self.k = nn.Linear(dim, dim)
+        self.v = nn.Linear(dim, dim)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        shp = (B, N, self.num_heads, self.head_dim)
+        q, k, v = (t.view(shp).transpose(1, 2) for t in (self.q(x), self.k(x), self.v(x)))
+        o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)
+        return self.proj(o.transpose(1, 2).reshape(B, N, C))
+
+
+class MultiHeadCrossAttention(nn.Module):
+    """blocks.py:277-310: block-diagonal attention of image tokens over each sample's (mask-selected) prompt tokens."""
+
+    def __init__(self, d_model, num_heads):
+        super().__init__()
+        self.num_heads, self.head_dim = num_heads, d_model // num_heads
+        self.q_linear = nn.Linear(d_model, d_model)
+        self.kv_linear = nn.Linear(d_model, d_model * 2)
+        self.proj = nn.Linear(d_model, d_model)
+
+    @staticmethod
+    def attend(q, kv, B, N, y_lens, H, D):
+        """q [B*N, C]; kv [sum(y_lens), 2C] -> [B*N, C]."""
+        q = q.view(B, N, H, D)
+        kv = kv.view(-1, 2, H, D)
+        outs, off = [], 0
+        for b in range(B):
+            L = y_lens[b]
+            k = kv[off:off + L, 0].transpose(0, 1).unsqueeze(0)
+            v = kv[off:off + L, 1].transpose(0, 1).unsqueeze(0)
+            o = F.scaled_dot_product_attention(q[b].transpose(0, 1).unsqueeze(0), k, v)
+            outs.append(o.squeeze(0).transpose(0, 1))
+            off += L
+        return torch.stack(outs, 0).reshape(B * N, H * D)
+
+    def forward(self, x, cond, y_lens):
+        B, N, C = x.shape
+        q = self.q_linear(x).reshape(B * N, C)
+        kv = self.kv_linear(cond).reshape(-1, 2 * C)
+        o = self.attend(q, kv, B, N, y_lens, self.num_heads, self.head_dim)
+        return self.proj(o.view(B, N, C))
+
+
+class T2IFinalLayer(nn.Module):
+    def __init__(self, hidden_size, num_patch, out_channels):
+        super().__init__()
+        self.norm_final = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.linear = nn.Linear(hidden_size, num_patch * out_channels)
+        self.scale_shift_table = nn.Parameter(torch.randn(2, hidden_size) / hidden_size ** 0.5)
+        self.out_channels = out_channels
+
+    def forward(self, x, t):
+        shift, scale = (self.scale_shift_table[None] + t[:, None]).chunk(2, dim=1)
+        return self.linear(self.norm_final(x) * (1 + scale) + shift)
+
+
+class STDiTBlock(nn.Module):
+    def __init__(self, hidden_size, num_heads, d_s, d_t, mlp_ratio=4.0):
+        super().__init__()
+        self.hidden_size, self.d_s, self.d_t = hidden_size, d_s, d_t
+        self.norm1 = nn.LayerNorm(hidden_size, eps=1e-6, elementwise_affine=False)
+        self.attn = Attention(hidden_size, num_heads)
+        self.cross_attn = MultiHeadCrossAttention(hidden_size, num_heads)
+        self.norm2 = nn.LayerNorm(hidden_size, eps=1e-6, elementwise_affine=False)
+        self.mlp = Mlp(hidden_size, int(hidden_size * mlp_ratio))
+        self.scale_shift_table = nn.Parameter(torch.randn(6, hidden_size) / hidden_size ** 0.5)
+        self.attn_temp = Attention(hidden_size, num_heads)
+
+    def modulation(self, t):
+        B = t.shape[0]
+        return (self.scale_shift_table[None] + t.reshape(B, 6, -1)).chunk(6, dim=1)
+
+    def forward(self, x, y, t, y_lens, tpe=None):
+        """Reference schedule (stdit.py:96-133)."""
+        B, N, C = x.shape
+        T, S = self.d_t, self.d_s
+        shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = self.modulation(t)
+        x_m = self.norm1(x) * (1 + scale_msa) + shift_msa
+        x_s = self.attn(x_m.view(B * T, S, C)).view(B, N, C)
+        x = x + gate_msa * x_s
+        x_t = x.view(B, T, S, C).transpose(1, 2).reshape(B * S, T, C)
+        if tpe is not None:
+            x_t = x_t + tpe
+        x_t = self.attn_temp(x_t).view(B, S, T, C).transpose(1, 2).reshape(B, N, C)
+        x = x + gate_msa * x_t
+        x = x + self.cross_attn(x, y, y_lens)
+        x = x + gate_mlp * self.mlp(self.norm2(x) * (1 + scale_mlp) + shift_mlp)
+        return x
+
+
+class STDiT(nn.Module):
+    def __init__(self, input_size=(16, 64, 64), in_channels=4, patch_size=(1, 2, 2), hidden_size=1152, depth=28,
+                 num_heads=16, mlp_ratio=4.0, pred_sigma=True, caption_channels=4096, model_max_length=120,
+                 dtype=torch.float32, space_scale=1.0, time_scale=1.0, **unused):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = in_channels * 2 if pred_sigma else in_channels
+        self.hidden_size, self.patch_size, self.input_size = hidden_size, patch_size, input_size
+        self.num_temporal = input_size[0] // patch_size[0]
+        self.num_patches = int(np.prod([input_size[i] // patch_size[i] for i in range(3)]))
+        self.num_spatial = self.num_patches // self.num_temporal
+        self.num_heads, self.depth, self.dtype = num_heads, depth, dtype
+        gh, gw = input_size[1] // patch_size[1], input_size[2] // patch_size[2]
+        self.register_buffer("pos_embed", torch.from_numpy(_sincos_2d(hidden_size, gh, gw, space_scale)).float()[None])
+        tp = _sincos_1d(hidden_size, np.arange(self.num_temporal)[..., None] / time_scale)
+        self.register_buffer("pos_embed_temporal", torch.from_numpy(tp).float()[None])
+        self.x_embedder = PatchEmbed3D(patch_size, in_channels, hidden_size)
+        self.t_embedder = TimestepEmbedder(hidden_size)
+        self.t_block = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size))
+        self.y_embedder = CaptionEmbedder(caption_channels, hidden_size, model_max_length)
+        self.blocks = nn.ModuleList([STDiTBlock(hidden_size, num_heads, self.num_spatial, self.num_temporal, mlp_ratio)
+                                     for _ in range(depth)])
+        self.final_layer = T2IFinalLayer(hidden_size, int(np.prod(patch_size)), self.out_channels)
+        self.init_synthetic()
+
+    @torch.no_grad()
+    def init_synthetic(self, seed=0):
+        """Seeded synthetic weights (no checkpoints in this environment): xavier linears, and — unlike the reference's
+        zero-init of cross_attn.proj / attn_temp.proj / final_layer.linear (stdit.py:409-452) — non-zero everywhere so
+        that every branch contributes to the output in parity tests."""
+        g = torch.Generator().manual_seed(seed)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                bound = math.sqrt(6.0 / (m.in_features + m.out_features))
+                m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) * bound)
+                if m.bias is not None:
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.02)
+        w = self.x_embedder.proj.weight
+        bound = math.sqrt(6.0 / (w[0].numel() + w.shape[0]))
+        w.copy_((torch.rand(w.shape, generator=g) * 2 - 1) * bound)
+        for b in self.blocks:
+            b.scale_shift_table.copy_(torch.randn(b.scale_shift_table.shape, generator=g) / self.hidden_size ** 0.5)
+        fl = self.final_layer.scale_shift_table
+        fl.copy_(torch.randn(fl.shape, generator=g) / self.hidden_size ** 0.5)
+        ye = self.y_embedder.y_embedding
+        ye.copy_(torch.randn(ye.shape, generator=g) / ye.shape[1] ** 0.5)
+        self.x_embedder.proj.bias.copy_(torch.randn(self.x_embedder.proj.bias.shape, generator=g) * 0.02)
+
+    # ---- shared pre/post --------------------------------------------------------------------------------------------
+    @staticmethod
+    def mask_select_plan(mask):
+        """Host-side plan of the MASK_SELECT gather (stdit.py:280-286) for a fixed prompt mask [B, L]: flat indices of
+        the kept tokens and the per-sample lengths. Computed once per prompt so the forward itself is sync-free
+        (CUDA-graph capturable)."""
+        m = mask.reshape(mask.shape[0], -1).cpu()
+        idx = torch.nonzero(m.reshape(-1) != 0).reshape(-1)
+        return idx.to(mask.device), [int(v) for v in m.sum(dim=1).tolist()]
+
+    def embed(self, x, timestep, y, mask, plan=None):
+        x = x.to(self.dtype)
+        timestep = timestep.to(self.dtype)
+        y = y.to(self.dtype)
+        B = x.shape[0]
+        T, S, C = self.num_temporal, self.num_spatial, self.hidden_size
+        x = self.x_embedder(x).view(B, T, S, C) + self.pos_embed
+        x = x.view(B, T * S, C)
+        t = self.t_embedder(timestep, dtype=x.dtype)
+        t0 = self.t_block(t)
+        y = self.y_embedder(y)
+        if plan is not None:
+            y_index, y_lens = plan
+            y = y.squeeze(1).reshape(-1, C).index_select(0, y_index).view(1, -1, C)
+        elif mask is not None:  # MASK_SELECT branch of stdit.py:280-286 (dynamic activation quantiser)
+            aq = getattr(self.final_layer.linear, "act_quantizer", None)
+            if aq is not None and type(aq).__name__ != "DynamicActQuantizer" and aq.per_group == "token":
+                raise NotImplementedError("static per-token activation quantisation (MASK_SELECT=False, quirk Q14)")
+            if mask.shape[0] != y.shape[0]:
+                mask = mask.repeat(y.shape[0] // mask.shape[0], 1)
+            mask = mask.squeeze(1).squeeze(1)
+            y = y.squeeze(1).masked_select(mask.unsqueeze(-1) != 0).view(1, -1, C)
+            y_lens = mask.sum(dim=1).tolist()
+        else:
+            y_lens = [y.shape[2]] * y.shape[0]
+            y = y.squeeze(1).reshape(1, -1, C)
+        return x, t, t0, y, y_lens
+
+    def unpatchify(self, x):
+        B = x.shape[0]
+        Nt, Nh, Nw = [self.input_size[i] // self.patch_size[i] for i in range(3)]
+        Tp, Hp, Wp = self.patch_size
+        x = x.view(B, Nt, Nh, Nw, Tp, Hp, Wp, self.out_channels)
+        return x.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(B, self.out_channels, Nt * Tp, Nh * Hp, Nw * Wp)
+
+    def forward(self, x, timestep, y, mask=None):
+        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask)
+        tpe = self.pos_embed_temporal.to(x.dtype)
+        for i, block in enumerate(self.blocks):
+            x = block(x, y, t0, y_lens, tpe if i == 0 else None)
+        x = self.final_layer(x, t)
+        return self.unpatchify(x).to(torch.float32)
+
+    # ---- fused B200 schedule ----------------------------------------------------------------------------------------
+    def forward_fused(self, x, timestep, y, mask=None, plan=None):
+        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan)
+        eng = getattr(self, "_engine", None)
+        if eng is None:
+            eng = self._engine = FusedBlocks(self)
+        x = eng.run(x, y, t0, y_lens)
+        x = self.final_layer(x, t)
+        return self.unpatchify(x).to(torch.float32)
+
+
+def STDiT_XL_2(**kwargs):
+    return STDiT(depth=28, hidden_size=1152, patch_size=(1, 2, 2), num_heads=16, **kwargs)
+
+
+class FusedBlocks:
+    """Block-level schedule on the fused kernels. Reads the QuantLayers' prepared weights; q|k|v weights of each
+    attention are concatenated once into one [3C, K] operand (identical per-channel parameters, one GEMM)."""
+
+    def __init__(self, model: STDiT):
+        self.m = model
+        self._qkv = {}
+
+    @staticmethod
+    def _cat_prepared(layers):
+        pws = [l.prepared_weight() for l in layers]
+        codes = torch.cat([p.codes for p in pws], 0).contiguous()
+        col = torch.cat([p.col for p in pws], 0).contiguous()
+        return ops.PreparedWeight(codes, col, codes.shape[0], pws[0].K, pws[0].n_bits)
+
+    def _qkv_weight(self, attn, tag):
+        layers = (attn.q, attn.k, attn.v)
+        key = (tag,) + tuple((l.weight_quantizer.n_bits, l._timerange_id() if l.smooth_quant else 0) for l in layers)
+        pw = self._qkv.get(key)
+        if pw is None:
+            for l in layers:
+                if not (isinstance(l, QuantLayer) and l.weight_quant and l.act_quant):
+                    raise NotImplementedError("forward_fused needs every block linear in W+A quantised state")
+            pw = self._qkv[key] = self._cat_prepared(layers)
+            pw.smooth = getattr(layers[0].prepared_weight(), "smooth", None)
+            if any(getattr(l.prepared_weight(), "smooth", None) is not None for l in layers):
+                raise NotImplementedError("fused q|k|v with smooth-quant needs a shared channel scale; use forward()")
+        return pw
+
+    def run(self, x, y, t0, y_lens):
+        m = self.m
+        B, N, C = x.shape
+        T, S, H = m.num_temporal, m.num_spatial, m.num_heads
+        D = C // H
+        M = B * N
+        x = x.contiguous()
+        ones = torch.ones(1, C, dtype=x.dtype, device=x.device)
+        tpe = m.pos_embed_temporal.to(x.dtype)
+        for i, blk in enumerate(m.blocks):
+            shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = (
+                v.reshape(B, C).contiguous() for v in blk.modulation(t0))
+            # ---- spatial attention: LN + modulate + quantise once, one q|k|v GEMM
+            a, _ = ops.ln_modulate_act_quant(x, shift_msa, scale_msa, n_bits=blk.attn.q.act_quantizer.n_bits)
+            qkv = ops.gemm_w8a8(a, self._qkv_weight(blk.attn, (i, "s"))).view(B * T, S, 3, H, D)
+            o = F.scaled_dot_product_attention(qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2),
+                                               qkv[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
+            o = o.transpose(1, 2).reshape(B, N, C)
+            a = blk.attn.proj.quantize_input(o.view(B * T, S, C))
+            x = ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=x.view(M, C),
+                              gate=gate_msa, rows_per_gate=N).view(B, N, C)
+            # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
+            xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
+            a = ops.act_quant(xt, n_bits=blk.attn_temp.q.act_quantizer.n_bits)
+            qkv = ops.gemm_w8a8(a, self._qkv_weight(blk.attn_temp, (i, "t"))).view(B, T, S, 3, H, D)
+            qt, kt, vt = (qkv[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
+            o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)   # [B*S, H, T, D]
+            o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
+            a = ops.act_quant(o, n_bits=blk.attn_temp.proj.act_quantizer.n_bits)
+            x = ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=x.view(M, C),
+                              gate=gate_msa, rows_per_gate=N).view(B, N, C)
+            # ---- cross attention
+            ca = blk.cross_attn
+            q = ops.gemm_w8a8(ca.q_linear.quantize_input(x), ca.q_linear.prepared_weight())
+            kv = ops.gemm_w8a8(ca.kv_linear.quantize_input(y), ca.kv_linear.prepared_weight())
+            o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
+            x = ops.gemm_w8a8(ca.proj.quantize_input(o), ca.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
+                              res=x.view(M, C), gate=ones, rows_per_gate=M).view(B, N, C)
+            # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
+            a, _ = ops.ln_modulate_act_quant(x, shift_mlp, scale_mlp, n_bits=blk.mlp.fc1.act_quantizer.n_bits)
+            h = ops.gemm_w8a8(a, blk.mlp.fc1.prepared_weight(), epi=ops.VQ_EPI_GELU_TANH).view(B, N, -1)
+            a = blk.mlp.fc2.quantize_input(h)
+            x = ops.gemm_w8a8(a, blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=x.view(M, C),
+                              gate=gate_mlp, rows_per_gate=N).view(B, N, C)
+        return x
