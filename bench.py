@@ -203,6 +203,7 @@ def main():
     d_z, d_yc, d_yu = h_z.to(dev), h_yc.to(dev), h_yu.to(dev)
     d_t, d_coef = torch.zeros(1, device=dev), torch.zeros(4, device=dev)
     plan = model.mask_select_plan(mask.to(dev))
+    segments = model.kv_segments(plan[1], dev)
     sched = [(ddim.model_timestep(i), ddim.coefficients(i, "cpu")) for i in range(ddim.num_timesteps)]
 
     def set_step(i):
@@ -213,8 +214,8 @@ def main():
 
     def step_device():
         """The denoise step on device-resident inputs (iddpm forward_with_cfg + ddim_sample, cfg_split)."""
-        out_c = model.forward_fused(d_z, d_t, d_yc, plan=plan)
-        out_u = model.forward_fused(d_z, d_t, d_yu, plan=plan)
+        out_c = model.forward_fused(d_z, d_t, d_yc, plan=plan, segments=segments)
+        out_u = model.forward_fused(d_z, d_t, d_yu, plan=plan, segments=segments)
         out = SpacedDDIM.cfg_combine(out_c, out_u, ddim.cfg_scale)
         return SpacedDDIM.ddim_update(d_z, out, d_coef)
 

@@ -79,6 +79,16 @@ int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const void* a_zp, 
                  int a_rows_period, const uint8_t* w_codes, const VqColParam* col, int M, int N, int K, int epi, const void* res,
                  int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* stream);
 
+/* (a9) temporal self-attention of STDiT (stdit.py:112-118, blocks.py:151-195 on "(B S) T C"), reading q|k|v in place
+ * from the fused GEMM output qkv fp16 [B*T*S, 3*H*head_dim] in the (T S) token layout; out fp16 [B*T*S, H*head_dim].
+ * head_dim must be 72, T <= 16. scale = head_dim^-0.5.                                                             */
+int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S, int H, int head_dim, float scale, void* stream);
+
+/* (a9) cross attention (blocks.py:292-310, xformers BlockDiagonalMask.from_seqlens([N]*B, y_lens)): q fp16
+ * [B*N, H*head_dim]; kv fp16 [sum(len), 2*H*head_dim] (k | v); kv_start / kv_len: device int32 [B]; max_len <= 128. */
+int vq_attn_cross(const void* q, const void* kv, void* out, const int32_t* kv_start, const int32_t* kv_len, int B,
+                  int N, int H, int head_dim, int max_len, float scale, void* stream);
+
 /* status word helpers (host side; the only calls here that synchronise) */
 int vq_status_read(const uint32_t* status_dev, uint32_t* host_out, void* stream);
 

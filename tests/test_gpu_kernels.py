@@ -196,8 +196,10 @@ def test_ln_modulate_act_quant(ops, G, rows, K):
     a, y = ops.ln_modulate_act_quant(dev(x), dev(shift), dev(scale), want_y=True)
     y = y.cpu().numpy()
     yo = O.ln_modulate(x, shift, scale)
-    ulp = np.abs(y.view(np.int16).astype(np.int32) - yo.view(np.int16).astype(np.int32))
-    assert ulp.max() <= 1 and (ulp > 0).mean() < 5e-3   # fp32 vs fp64 LayerNorm statistics: last-bit only
+    # fp32 vs fp64 LayerNorm statistics move h(LN) by at most one fp16 ulp; |LN * (1+scale)| <~ 8 bounds that ulp, and
+    # the final add can cancel, so compare absolutely rather than in ulps of the (possibly tiny) result
+    diff = np.abs(y.astype(np.float32) - yo.astype(np.float32))
+    assert diff.max() <= 2 * 2.0 ** -8 and (diff > 0).mean() < 2e-2, (diff.max(), (diff > 0).mean())
     # given the kernel's own modulated tensor, the quantiser part must be bit-exact
     oa = O.dynamic_act_quant(y)
     np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(G, rows, K), oa["codes"])
@@ -219,3 +221,45 @@ def test_eps_degenerate_row_sets_status_and_raises(ops):
 def test_cpu_tensor_is_rejected_no_fallback(ops):
     with pytest.raises(Exception, match="no CPU path"):
         ops.act_quant(torch.zeros(1, 8, 64, dtype=torch.float16))
+
+
+# ---------------------------------------------------------------------------------------------------- attention (fp16)
+def _sdpa_ref(q, k, v, scale):
+    """Plain fp32 softmax attention: q [n, Lq, H, D], k/v [n, Lk, H, D]."""
+    qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+    p = torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1)
+    return (p @ vf).transpose(1, 2)
+
+
+@pytest.mark.parametrize("B,T,S", [(1, 16, 64), (2, 4, 33), (1, 7, 40)])
+def test_temporal_attention_matches_fp32_reference(ops, B, T, S):
+    H, D = 16, 72
+    C = H * D
+    torch.manual_seed(0)
+    qkv = (torch.randn(B * T * S, 3 * C, device="cuda") * 1.5).half()
+    out = ops.attn_temporal(qkv, B, T, S, H, D, D ** -0.5)
+    v5 = qkv.view(B, T, S, 3, H, D)
+    q, k, v = (v5[:, :, :, j].permute(0, 2, 1, 3, 4).reshape(B * S, T, H, D) for j in range(3))
+    ref = _sdpa_ref(q, k, v, D ** -0.5).reshape(B, S, T, C).permute(0, 2, 1, 3).reshape(B * T * S, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-3 * ref.abs().max().item() + 1e-3, err      # fp16 P and fp16 output rounding
+
+
+@pytest.mark.parametrize("B,N,lens", [(1, 256, [109]), (2, 200, [77, 120]), (1, 130, [1]), (3, 48, [128, 5, 64])])
+def test_cross_attention_matches_fp32_reference(ops, B, N, lens):
+    H, D = 16, 72
+    C = H * D
+    torch.manual_seed(1)
+    q = torch.randn(B * N, C, device="cuda").half()
+    kv = torch.randn(sum(lens), 2 * C, device="cuda").half()
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    out = ops.attn_cross(q, kv, torch.from_numpy(starts).cuda(), torch.tensor(lens, dtype=torch.int32, device="cuda"),
+                         B, N, H, D, max(lens), D ** -0.5)
+    refs, off = [], 0
+    for b in range(B):
+        kk = kv[off:off + lens[b]].view(1, lens[b], 2, H, D)
+        refs.append(_sdpa_ref(q[b * N:(b + 1) * N].view(1, N, H, D), kk[:, :, 0], kk[:, :, 1], D ** -0.5).reshape(N, C))
+        off += lens[b]
+    ref = torch.cat(refs, 0)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-3 * ref.abs().max().item() + 1e-3, err

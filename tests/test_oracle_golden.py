@@ -116,3 +116,20 @@ def test_div_by_levels_matches_reciprocal_multiply():
         b = (allh * (np.float32(1.0) / np.float32(qmax))).astype(np.float16)
         mism = int((a != b).sum())
         assert mism == 0, (qmax, mism)
+
+
+@pytest.mark.parametrize("name", sorted(LAYER_VIEWS))
+def test_torch_fake_quant_restatement_is_bit_exact_on_cpu(golden, name):
+    """oracle/torch_fake_quant.py (used on the GPU by the model-level tests) reproduces the reference layer outputs
+    exactly when run on the reference's own back end (CPU, fp16)."""
+    import torch
+    from oracle import torch_fake_quant as TF
+    c = golden[name]
+    x, smooth = _layer_inputs(c)
+    B, n = LAYER_VIEWS[name](x.shape)
+    xv = torch.from_numpy(x.reshape(B, n, x.shape[-1]))
+    sm = None if smooth is None else torch.from_numpy(smooth)
+    bias = torch.from_numpy(c["bias"]) if "bias" in c else None
+    out = TF.quant_linear_fake(xv, torch.from_numpy(c["weight"]), bias, torch.from_numpy(c["wdelta"]),
+                               torch.from_numpy(c["wzp"]), int(c["w_bits"]), 8, sm)
+    np.testing.assert_array_equal(out.numpy().reshape(c["out"].shape), c["out"])

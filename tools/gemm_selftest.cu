@@ -45,7 +45,7 @@ __global__ void ref_gemm(const uint8_t* a, const __half* ad, const __half* az, c
   if (epi == VQ_EPI_GELU_TANH) y = __float2half_rn(ref_gelu(__half2float(y)));
   if (epi == VQ_EPI_GATE_RESIDUAL) {
     __half g = gate[(size_t)(m / rpg) * N + n];
-    y = __hadd(res[(size_t)m * N + n], __hmul(g, y));
+    y = __hadd_rn(res[(size_t)m * N + n], __hmul_rn(g, y));
   }
   out[(size_t)m * N + n] = y;
 }

@@ -1,0 +1,252 @@
+// Small-sequence attention kernels (head_dim 72, fp16 in/out, fp32 softmax) for the two STDiT attentions whose key
+// length is tiny and which are therefore HBM-bound:
+//   * temporal self-attention (reference stdit.py:112-118 -> blocks.py:151-195 on "(B S) T C"): T <= 16 keys per
+//     (batch, spatial position, head). Reads q/k/v straight out of the fused q|k|v GEMM output in the (T S) token
+//     layout through strides — the reference's rearrange copies do not exist here.
+//   * cross attention (blocks.py:292-310, xformers BlockDiagonalMask): every image token of sample b attends to that
+//     sample's (mask-selected) prompt tokens, L <= 128.
+// One warp owns 16 query rows: S = Q K^T and O = P V run on mma.sync.m16n8k16 (f16 x f16 -> f32) with ldmatrix
+// fragments from padded shared-memory tiles (pitch 88 halves: conflict-free); softmax in registers; the C fragments of
+// S are reused as the A fragments of P. Single key chunk, so no online-softmax rescaling is needed.
+// (The long spatial attention, S = 1024, stays on the library flash kernel for now; a tcgen05 version is a later row.)
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "vq_internal.h"
+
+namespace vq {
+
+constexpr int HD = 72;        // head dim
+constexpr int HDP = 80;       // padded to a multiple of the MMA K (16)
+constexpr int PITCH = 88;     // smem row pitch in halves (176 B: 8 consecutive rows hit 8 distinct 16B bank groups)
+constexpr int ND = HD / 8;    // 9 output n-tiles
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __half* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __half* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], const __half* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Copy `rows` rows of 72 halves (global row stride gstride elements) into a [*, PITCH] smem tile, zero-filling rows
+// >= rows up to tile_rows and the pad columns 72..79. `nthr` threads starting at `tid` cooperate.
+__device__ __forceinline__ void load_tile(__half* dst, const __half* src, long long gstride, int rows, int tile_rows,
+                                          int tid, int nthr) {
+  const int chunks = tile_rows * 10;  // 10 x 16 B per row: 9 data + 1 pad
+  for (int c = tid; c < chunks; c += nthr) {
+    const int r = c / 10, cc = c % 10;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (cc < 9 && r < rows) v = __ldg(reinterpret_cast<const uint4*>(src + r * gstride) + cc);
+    *reinterpret_cast<uint4*>(dst + r * PITCH + cc * 8) = v;
+  }
+}
+
+// One warp: 16 query rows in sQ (rows >= nq are zero), keys/values in sK/sV (KT*16 rows, rows >= lk zero).
+// Result rows [0, nq) written to global through sQ as staging.
+template <int KT>
+__device__ __forceinline__ void warp_attend(__half* sQ, const __half* sK, const __half* sV, int lk, float scale_log2e,
+                                            __half* out, long long ostride, int nq, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  // ---- S = Q K^T : 2*KT n-tiles of 8 keys, 5 k-steps of 16 dims
+  float s[2 * KT][4];
+#pragma unroll
+  for (int n = 0; n < 2 * KT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < HDP / 16; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(a, sQ + ((lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + ks * 16 + 8 * (lane >> 4));
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t b[4];  // keys kt*16 + [0,8) / [8,16), dims ks*16 + [0,8) / [8,16)
+      ldsm_x4(b, sK + (kt * 16 + (lane & 7) + 8 * (lane >> 4)) * PITCH + ks * 16 + 8 * ((lane >> 3) & 1));
+      mma16816(s[2 * kt], a, b[0], b[1]);
+      mma16816(s[2 * kt + 1], a, b[2], b[3]);
+    }
+  }
+  // ---- softmax over keys (rows g and g+8 of this quad), fp32
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 2 * KT; ++n) {
+    const int col = n * 8 + 2 * t;
+    if (col >= lk) s[n][0] = s[n][2] = -INFINITY;
+    if (col + 1 >= lk) s[n][1] = s[n][3] = -INFINITY;
+    m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+    m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t p[KT][4];
+#pragma unroll
+  for (int n = 0; n < 2 * KT; ++n) {
+    float e0 = exp2f((s[n][0] - m0) * scale_log2e), e1 = exp2f((s[n][1] - m0) * scale_log2e);
+    float e2 = exp2f((s[n][2] - m1) * scale_log2e), e3 = exp2f((s[n][3] - m1) * scale_log2e);
+    l0 += e0 + e1;
+    l1 += e2 + e3;
+    // C fragments of key tiles (2kt, 2kt+1) are the A fragment of P for k-step kt
+    p[n >> 1][(n & 1) * 2 + 0] = pack_h2(e0, e1);
+    p[n >> 1][(n & 1) * 2 + 1] = pack_h2(e2, e3);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // ---- O = P V : 9 n-tiles of 8 dims, KT k-steps of 16 keys
+  float o[ND][4];
+#pragma unroll
+  for (int n = 0; n < ND; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < KT; ++kt) {
+#pragma unroll
+    for (int n = 0; n < ND - 1; n += 2) {
+      uint32_t b[4];  // V^T fragments: keys kt*16 + [0,8)/[8,16), dims n*8 + [0,8) / (n+1)*8 + [0,8)
+      ldsm_x4_t(b, sV + (kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + n * 8 + 8 * (lane >> 4));
+      mma16816(o[n], p[kt], b[0], b[1]);
+      mma16816(o[n + 1], p[kt], b[2], b[3]);
+    }
+    uint32_t b2[2];
+    ldsm_x2_t(b2, sV + (kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + (ND - 1) * 8);
+    mma16816(o[ND - 1], p[kt], b2[0], b2[1]);
+  }
+  // ---- normalise, stage through sQ, coalesced 16-byte stores
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < ND; ++n) {
+    *reinterpret_cast<uint32_t*>(sQ + g * PITCH + n * 8 + 2 * t) = pack_h2(o[n][0] * i0, o[n][1] * i0);
+    *reinterpret_cast<uint32_t*>(sQ + (g + 8) * PITCH + n * 8 + 2 * t) = pack_h2(o[n][2] * i1, o[n][3] * i1);
+  }
+  __syncwarp();
+  for (int c = lane; c < 16 * 9; c += 32) {
+    const int r = c / 9, cc = c % 9;
+    if (r < nq) *(reinterpret_cast<uint4*>(out + r * ostride) + cc) = *reinterpret_cast<const uint4*>(sQ + r * PITCH + cc * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- temporal
+struct TemporalArgs {
+  const __half* qkv;   // [B, T, S, 3, H, 72] == fused q|k|v GEMM output [B*T*S, 3*H*72]
+  __half* out;         // [B, T, S, H*72]
+  int B, T, S, H;
+  float scale_log2e;
+};
+
+constexpr int TEMPORAL_WARPS = 8;
+
+__global__ void __launch_bounds__(TEMPORAL_WARPS * 32) vq_attn_temporal_kernel(const TemporalArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* sQ = reinterpret_cast<__half*>(smem_attn) + warp * 3 * 16 * PITCH;
+  __half* sK = sQ + 16 * PITCH;
+  __half* sV = sK + 16 * PITCH;
+  const long long unit = static_cast<long long>(blockIdx.x) * TEMPORAL_WARPS + warp;  // (b, s, h), h fastest
+  const long long total = static_cast<long long>(a.B) * a.S * a.H;
+  if (unit >= total) return;
+  const int h = static_cast<int>(unit % a.H);
+  const long long bs = unit / a.H;
+  const int sidx = static_cast<int>(bs % a.S);
+  const int b = static_cast<int>(bs / a.S);
+  const int C = a.H * HD;
+  const long long tok0 = static_cast<long long>(b) * a.T * a.S + sidx;   // token (b, t=0, s)
+  const long long rstride = static_cast<long long>(a.S) * 3 * C;         // next frame, same spatial position
+  const __half* q = a.qkv + tok0 * 3 * C + h * HD;
+  load_tile(sQ, q, rstride, a.T, 16, lane, 32);
+  load_tile(sK, q + C, rstride, a.T, 16, lane, 32);
+  load_tile(sV, q + 2 * C, rstride, a.T, 16, lane, 32);
+  __syncwarp();
+  warp_attend<1>(sQ, sK, sV, a.T, a.scale_log2e, a.out + tok0 * C + h * HD, static_cast<long long>(a.S) * C, a.T, lane);
+}
+
+// ------------------------------------------------------------------------------------------------- cross
+struct CrossArgs {
+  const __half* q;     // [B*N, H*72]
+  const __half* kv;    // [sum(len), 2, H, 72]
+  __half* out;         // [B*N, H*72]
+  const int* kv_start; // [B] first prompt row of each sample
+  const int* kv_len;   // [B] prompt length (<= 128)
+  int B, N, H;
+  float scale_log2e;
+};
+
+constexpr int CROSS_WARPS = 8;
+constexpr int CROSS_KT = 8;   // 128 keys
+
+__global__ void __launch_bounds__(CROSS_WARPS * 32) vq_attn_cross_kernel(const CrossArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* sK = reinterpret_cast<__half*>(smem_attn);
+  __half* sV = sK + CROSS_KT * 16 * PITCH;
+  __half* sQ = sV + CROSS_KT * 16 * PITCH + warp * 16 * PITCH;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int C = a.H * HD;
+  const int lk = a.kv_len[b];
+  const __half* kbase = a.kv + static_cast<long long>(a.kv_start[b]) * 2 * C + h * HD;
+  load_tile(sK, kbase, 2LL * C, lk, CROSS_KT * 16, threadIdx.x, CROSS_WARPS * 32);
+  load_tile(sV, kbase + C, 2LL * C, lk, CROSS_KT * 16, threadIdx.x, CROSS_WARPS * 32);
+  const int row0 = (blockIdx.x * CROSS_WARPS + warp) * 16;
+  const int nq = min(16, a.N - row0);
+  const long long tok0 = static_cast<long long>(b) * a.N + row0;
+  if (nq > 0) load_tile(sQ, a.q + tok0 * C + h * HD, C, nq, 16, lane, 32);
+  __syncthreads();
+  if (nq > 0) warp_attend<CROSS_KT>(sQ, sK, sV, lk, a.scale_log2e, a.out + tok0 * C + h * HD, C, nq, lane);
+}
+
+}  // namespace vq
+
+extern "C" int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S, int H, int head_dim, float scale,
+                                void* stream) {
+  using namespace vq;
+  if (!qkv || !out || B <= 0 || S <= 0 || H <= 0) return VQ_ERR_ARG;
+  if (head_dim != HD || T <= 0 || T > 16) return VQ_ERR_UNSUPPORTED;
+  TemporalArgs a{static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, S, H, scale * 1.4426950408889634f};
+  const long long units = static_cast<long long>(B) * S * H;
+  const int smem = TEMPORAL_WARPS * 3 * 16 * PITCH * 2;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(vq_attn_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return VQ_ERR_LAUNCH;
+    attr = true;
+  }
+  const unsigned grid = static_cast<unsigned>((units + TEMPORAL_WARPS - 1) / TEMPORAL_WARPS);
+  vq_attn_temporal_kernel<<<grid, TEMPORAL_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+extern "C" int vq_attn_cross(const void* q, const void* kv, void* out, const int32_t* kv_start, const int32_t* kv_len,
+                             int B, int N, int H, int head_dim, int max_len, float scale, void* stream) {
+  using namespace vq;
+  if (!q || !kv || !out || !kv_start || !kv_len || B <= 0 || N <= 0 || H <= 0) return VQ_ERR_ARG;
+  if (head_dim != HD || max_len <= 0 || max_len > CROSS_KT * 16) return VQ_ERR_UNSUPPORTED;
+  CrossArgs a{static_cast<const __half*>(q), static_cast<const __half*>(kv), static_cast<__half*>(out), kv_start,
+              kv_len, B, N, H, scale * 1.4426950408889634f};
+  const int smem = (2 * CROSS_KT * 16 + CROSS_WARPS * 16) * PITCH * 2;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(vq_attn_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return VQ_ERR_LAUNCH;
+    attr = true;
+  }
+  dim3 grid((N + CROSS_WARPS * 16 - 1) / (CROSS_WARPS * 16), H, B);
+  vq_attn_cross_kernel<<<grid, CROSS_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}

@@ -113,7 +113,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
-            __half2 o = __hadd2(r2[e], __hmul2(g2[e], y));
+            __half2 o = __hadd2_rn(r2[e], __hmul2_rn(g2[e], y));  // _rn: two roundings, never contracted to an fp16 FMA
             packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
           }
         }

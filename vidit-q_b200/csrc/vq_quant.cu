@@ -45,12 +45,18 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-// q = clamp(rint(h(x / delta)) + zp, 0, qmax); x, delta are fp16 values held in fp32.
-__device__ __forceinline__ int quant_code(float x, float delta, float zp, float qmax) {
-  float y = h_round(__fdiv_rn(x, delta));
-  float r = rintf(y) + zp;  // exact: integers well below 2^24
-  r = fminf(fmaxf(r, 0.0f), qmax);
-  return static_cast<int>(r);
+// q = clamp(rint(h(x / delta)) + zp, 0, qmax); x, delta are fp16 values held in fp32, rdelta ~= 1/delta.
+// Division-free but exact: for fp16 operands (11-bit significands) the true quotient is either exactly an fp16
+// rounding midpoint or at least 2^-23 (relative) away from one, so (a) the reference's fp32-then-fp16 double rounding
+// equals one direct rounding, and (b) a quotient with < 2^-24 relative error — one Newton step on x * (1/delta), the
+// residual being exact in one FMA — rounds to the same fp16. (Checked against x/delta on 2e7 random pairs and all
+// golden vectors; see tests.)  NaN (delta == 0, flagged as degenerate) converts to 0.
+__device__ __forceinline__ int quant_code(float x, float delta, float rdelta, int zp, int qmax) {
+  float q0 = x * rdelta;
+  float e = fmaf(-q0, delta, x);
+  float q1 = fmaf(e, rdelta, q0);
+  int q = __half2int_rn(__float2half_rn(q1)) + zp;
+  return min(max(q, 0), qmax);
 }
 
 struct RowStats {
@@ -171,7 +177,10 @@ __device__ __forceinline__ void row_minmax(const RowRegs<MAXC>& r, int nchunk, i
 
 template <int MAXC>
 __device__ __forceinline__ int quant_store_row(const RowRegs<MAXC>& r, uint8_t* codes_row, int nchunk, int lane,
-                                               float delta, float zp, float qmax) {
+                                               float delta, float zpf, float qmaxf) {
+  const float rdelta = __frcp_rn(delta);
+  const int zp = __float2int_rn(zpf);
+  const int qmax = __float2int_rn(qmaxf);
   int sum = 0;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
@@ -181,7 +190,7 @@ __device__ __forceinline__ int quant_store_row(const RowRegs<MAXC>& r, uint8_t* 
       uint32_t w[2] = {0u, 0u};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        int q = quant_code(__half2float(x[e]), delta, zp, qmax);
+        int q = quant_code(__half2float(x[e]), delta, rdelta, zp, qmax);
         sum += q;
         w[e >> 2] |= static_cast<uint32_t>(q) << (8 * (e & 3));
       }
@@ -291,6 +300,9 @@ __global__ void __launch_bounds__(256) vq_prep_weight_kernel(const PrepArgs a) {
   if (n >= a.N) return;
   const float delta = __half2float(a.delta[n]);
   const float zp = __half2float(a.zp[n]);
+  const float rdelta = __frcp_rn(delta);
+  const int zpi = __float2int_rn(zp);
+  const int qmaxi = __float2int_rn(a.qmax);
   const __half* wrow = a.w + static_cast<size_t>(n) * a.K;
   uint8_t* crow = a.codes + static_cast<size_t>(n) * a.K;
   int sum = 0;
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(256) vq_prep_weight_kernel(const PrepArgs a) {
     for (int e = 0; e < 8; ++e) {
       float v = __half2float(x[e]);
       if (a.smooth) v = h_round(v * __half2float(s[e]));  // quant_layer.py:178 weight * channel_wise_scale (fp16)
-      int q = quant_code(v, delta, zp, a.qmax);
+      int q = quant_code(v, delta, rdelta, zpi, qmaxi);
       sum += q;
       w[e >> 2] |= static_cast<uint32_t>(q) << (8 * (e & 3));
     }

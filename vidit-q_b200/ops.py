@@ -150,3 +150,31 @@ def gemm_w8a8(a: ActCodes, w: PreparedWeight, epi=VQ_EPI_BIAS, res=None, gate=No
     _lib.check(rc, "vq_gemm_w8a8")
     _count()
     return out
+
+
+def attn_temporal(qkv, B, T, S, H, head_dim, scale, out=None):
+    """qkv: fp16 [B*T*S, 3*H*head_dim] (fused q|k|v GEMM output, (T S) token order) -> fp16 [B*T*S, H*head_dim]."""
+    _need_cuda_f16(qkv, "qkv")
+    C = H * head_dim
+    if qkv.shape != (B * T * S, 3 * C):
+        raise _lib.VqError(f"attn_temporal: qkv shape {tuple(qkv.shape)} != {(B * T * S, 3 * C)}")
+    if out is None:
+        out = torch.empty((B * T * S, C), dtype=torch.float16, device=qkv.device)
+    rc = _lib.lib().vq_attn_temporal(_ptr(qkv), _ptr(out), B, T, S, H, head_dim, float(scale), _stream())
+    _lib.check(rc, "vq_attn_temporal")
+    _count()
+    return out
+
+
+def attn_cross(q, kv, kv_start, kv_len, B, N, H, head_dim, max_len, scale, out=None):
+    """q: fp16 [B*N, C]; kv: fp16 [sum(len), 2C]; kv_start/kv_len: int32 device tensors [B] -> fp16 [B*N, C]."""
+    _need_cuda_f16(q, "q")
+    _need_cuda_f16(kv, "kv")
+    C = H * head_dim
+    if out is None:
+        out = torch.empty((B * N, C), dtype=torch.float16, device=q.device)
+    rc = _lib.lib().vq_attn_cross(_ptr(q), _ptr(kv), _ptr(out), _ptr(kv_start), _ptr(kv_len), B, N, H, head_dim,
+                                  int(max_len), float(scale), _stream())
+    _lib.check(rc, "vq_attn_cross")
+    _count()
+    return out

@@ -242,6 +242,15 @@ class STDiT(nn.Module):
         idx = torch.nonzero(m.reshape(-1) != 0).reshape(-1)
         return idx.to(mask.device), [int(v) for v in m.sum(dim=1).tolist()]
 
+    @staticmethod
+    def kv_segments(y_lens, device):
+        """Device int32 (start, length) of every sample's prompt rows in the packed kv tensor."""
+        starts = [0]
+        for v in y_lens[:-1]:
+            starts.append(starts[-1] + v)
+        return (torch.tensor(starts, dtype=torch.int32, device=device),
+                torch.tensor(list(y_lens), dtype=torch.int32, device=device))
+
     def embed(self, x, timestep, y, mask, plan=None):
         x = x.to(self.dtype)
         timestep = timestep.to(self.dtype)
@@ -286,12 +295,15 @@ class STDiT(nn.Module):
         return self.unpatchify(x).to(torch.float32)
 
     # ---- fused B200 schedule ----------------------------------------------------------------------------------------
-    def forward_fused(self, x, timestep, y, mask=None, plan=None):
+    def forward_fused(self, x, timestep, y, mask=None, plan=None, segments=None):
+        """plan / segments: host-precomputed mask_select_plan(mask) and kv_segments(y_lens) make the call sync-free."""
         x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan)
         eng = getattr(self, "_engine", None)
         if eng is None:
             eng = self._engine = FusedBlocks(self)
-        x = eng.run(x, y, t0, y_lens)
+        if segments is None:
+            segments = self.kv_segments(y_lens, x.device)
+        x = eng.run(x, y, t0, y_lens, segments)
         x = self.final_layer(x, t)
         return self.unpatchify(x).to(torch.float32)
 
@@ -329,7 +341,7 @@ class FusedBlocks:
                 raise NotImplementedError("fused q|k|v with smooth-quant needs a shared channel scale; use forward()")
         return pw
 
-    def run(self, x, y, t0, y_lens):
+    def run(self, x, y, t0, y_lens, segments):
         m = self.m
         B, N, C = x.shape
         T, S, H = m.num_temporal, m.num_spatial, m.num_heads
@@ -353,10 +365,14 @@ class FusedBlocks:
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
             xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
             a = ops.act_quant(xt, n_bits=blk.attn_temp.q.act_quantizer.n_bits)
-            qkv = ops.gemm_w8a8(a, self._qkv_weight(blk.attn_temp, (i, "t"))).view(B, T, S, 3, H, D)
-            qt, kt, vt = (qkv[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
-            o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)   # [B*S, H, T, D]
-            o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
+            qkv = ops.gemm_w8a8(a, self._qkv_weight(blk.attn_temp, (i, "t")))
+            if T <= 16 and D == 72:      # own kernel: reads the (T S) layout in place, no permute copies
+                o = ops.attn_temporal(qkv, B, T, S, H, D, blk.attn_temp.scale).view(B, N, C)
+            else:                        # library path for shapes the kernel does not cover
+                q5 = qkv.view(B, T, S, 3, H, D)
+                qt, kt, vt = (q5[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
+                o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)
+                o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
             a = ops.act_quant(o, n_bits=blk.attn_temp.proj.act_quantizer.n_bits)
             x = ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=x.view(M, C),
                               gate=gate_msa, rows_per_gate=N).view(B, N, C)
@@ -364,7 +380,10 @@ class FusedBlocks:
             ca = blk.cross_attn
             q = ops.gemm_w8a8(ca.q_linear.quantize_input(x), ca.q_linear.prepared_weight())
             kv = ops.gemm_w8a8(ca.kv_linear.quantize_input(y), ca.kv_linear.prepared_weight())
-            o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
+            if D == 72 and max(y_lens) <= 128:
+                o = ops.attn_cross(q, kv, segments[0], segments[1], B, N, H, D, max(y_lens), D ** -0.5).view(B, N, C)
+            else:
+                o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
             x = ops.gemm_w8a8(ca.proj.quantize_input(o), ca.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
                               res=x.view(M, C), gate=ones, rows_per_gate=M).view(B, N, C)
             # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
