@@ -67,9 +67,10 @@ int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, in
                  int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream);
 
 /* LayerNorm(eps=1e-6, no affine) + t2i_modulate (blocks.py:51: x*(1+scale)+shift) + (a1), one pass.
- * x: fp16 [G*rows, K]; shift, scale: fp16 [G, K] (per sample); y_out (optional, may be NULL): fp16 modulated x.   */
-int vq_ln_modulate_act_quant(const void* x, const void* shift, const void* scale, int G, int rows, int K,
-                             int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp, int32_t* rowsum,
+ * x: fp16 [G*rows, K]; shift, scale: fp16 [G, K] (per sample); smooth: fp16 [K] or NULL (divides the modulated
+ * tensor, quant_layer.py:140); y_out (optional, may be NULL): fp16 tensor the quantiser saw.                        */
+int vq_ln_modulate_act_quant(const void* x, const void* shift, const void* scale, const void* smooth, int G, int rows,
+                             int K, int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp, int32_t* rowsum,
                              uint32_t* status, void* stream);
 
 /* (a3-a7) integer GEMM + dequant epilogue on prepared operands. a_codes u8 [M,K]; a_delta/a_zp fp16 [rows] indexed

@@ -56,7 +56,7 @@ static uint32_t rnd() {
   return rng_state >> 8;
 }
 
-static int run_case(int M, int N, int K, int epi, int period, bool timeit) {
+static int run_case(int M, int N, int K, int epi, int period, bool timeit, bool inplace = false) {
   std::vector<uint8_t> ha((size_t)M * K), hw((size_t)N * K);
   for (auto& v : ha) v = rnd() & 255;
   for (auto& v : hw) v = rnd() & 255;
@@ -110,7 +110,9 @@ static int run_case(int M, int N, int K, int epi, int period, bool timeit) {
   CK(cudaMemcpy(dgate, hgate.data(), hgate.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0xFF, (size_t)M * N * 2));
 
-  int rc = vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, epi, dres, N, dgate, rpg, dout, N, 0);
+  if (inplace) CK(cudaMemcpy(dout, dres, (size_t)M * N * 2, cudaMemcpyDeviceToDevice));  // out aliases the residual
+  int rc = vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, epi, inplace ? dout : dres, N, dgate, rpg, dout,
+                        N, 0);
   if (rc != VQ_OK) {
     printf("vq_gemm_w8a8 rc=%d\n", rc);
     return 1;
@@ -128,7 +130,8 @@ static int run_case(int M, int N, int K, int epi, int period, bool timeit) {
       if (bad == 0) first = i;
       ++bad;
     }
-  printf("case M=%d N=%d K=%d epi=%d period=%d : mismatches %zu / %zu", M, N, K, epi, period, bad, ho.size());
+  printf("case M=%d N=%d K=%d epi=%d%s period=%d : mismatches %zu / %zu", M, N, K, epi, inplace ? " (in-place)" : "",
+         period, bad, ho.size());
   if (bad) {
     __half a, b;
     memcpy(&a, &ho[first], 2);
@@ -190,12 +193,15 @@ int main(int argc, char** argv) {
   fails += run_case(120, 2304, 1152, VQ_EPI_BIAS, 120, false);  // kv_linear shape: ragged M
   fails += run_case(200, 32, 1152, VQ_EPI_BIAS, 100, false);    // PixArt final_layer: N tail, pooled period
   fails += run_case(2048, 1152, 1152, VQ_EPI_GATE_RESIDUAL, 1024, false);
+  fails += run_case(2048, 1152, 1152, VQ_EPI_GATE_RESIDUAL, 1024, false, true);   // TMA reduce-add path
+  fails += run_case(300, 200, 1152, VQ_EPI_GATE_RESIDUAL, 300, false, true);      // ragged M / N, in place
   fails += run_case(2048, 4608, 1152, VQ_EPI_GELU_TANH, 2048, false);
   fails += run_case(2048, 1152, 4608, VQ_EPI_BIAS, 2048, false);
   fails += run_case(16384, 1152, 1152, VQ_EPI_BIAS, 16384, timeit);  // > 148 tiles: persistent loop, TMEM double buffer
   if (timeit) {
     fails += run_case(16384, 4608, 1152, VQ_EPI_GELU_TANH, 16384, true);
     fails += run_case(16384, 1152, 4608, VQ_EPI_GATE_RESIDUAL, 16384, true);
+    fails += run_case(16384, 1152, 1152, VQ_EPI_GATE_RESIDUAL, 16384, true, true);
     fails += run_case(16384, 3456, 1152, VQ_EPI_BIAS, 16384, true);
   }
   printf(fails ? "SELFTEST FAILED (%d cases)\n" : "SELFTEST PASSED\n", fails);

@@ -37,7 +37,7 @@ def lib():
     L.vq_num_sms.restype = i32
     L.vq_prep_weight.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
     L.vq_act_quant.argtypes = [vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp]
-    L.vq_ln_modulate_act_quant.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.vq_ln_modulate_act_quant.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.vq_gemm_w8a8.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
     f32 = ctypes.c_float
     L.vq_attn_temporal.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp]

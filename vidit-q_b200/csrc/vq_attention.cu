@@ -7,7 +7,7 @@
 //     sample's (mask-selected) prompt tokens, L <= 128.
 // One warp owns 16 query rows: S = Q K^T and O = P V run on mma.sync.m16n8k16 (f16 x f16 -> f32) with ldmatrix
 // fragments from padded shared-memory tiles (pitch 88 halves: conflict-free); softmax in registers; the C fragments of
-// S are reused as the A fragments of P. Single key chunk, so no online-softmax rescaling is needed.
+// S are reused as the A fragments of P. Keys are processed in 64-key chunks with online softmax.
 // (The long spatial attention, S = 1024, stays on the library flash kernel for now; a tcgen05 version is a later row.)
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -46,88 +46,114 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Copy `rows` rows of 72 halves (global row stride gstride elements) into a [*, PITCH] smem tile, zero-filling rows
-// >= rows up to tile_rows and the pad columns 72..79. `nthr` threads starting at `tid` cooperate.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Asynchronously copy `rows` rows of 72 halves (global row stride gstride elements) into a [tile_rows, PITCH] smem
+// tile; rows >= rows and the pad columns 72..79 are zero-filled (cp.async with src-size 0). `nthr` threads cooperate.
+// All copies of a thread are in flight together; the caller waits with cp_async_wait_all().
 __device__ __forceinline__ void load_tile(__half* dst, const __half* src, long long gstride, int rows, int tile_rows,
                                           int tid, int nthr) {
   const int chunks = tile_rows * 10;  // 10 x 16 B per row: 9 data + 1 pad
   for (int c = tid; c < chunks; c += nthr) {
     const int r = c / 10, cc = c % 10;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (cc < 9 && r < rows) v = __ldg(reinterpret_cast<const uint4*>(src + r * gstride) + cc);
-    *reinterpret_cast<uint4*>(dst + r * PITCH + cc * 8) = v;
+    const bool real = cc < 9 && r < rows;
+    const __half* g = real ? src + r * gstride + cc * 8 : src;
+    cp_async16(dst + r * PITCH + cc * 8, g, real ? 16 : 0);
   }
 }
 
-// One warp: 16 query rows in sQ (rows >= nq are zero), keys/values in sK/sV (KT*16 rows, rows >= lk zero).
-// Result rows [0, nq) written to global through sQ as staging.
-template <int KT>
+// One warp: 16 query rows in sQ (rows >= nq are zero), keys/values in sK/sV (rows >= lk zero), processed in chunks of
+// CK*16 keys with online softmax (running max / sum, accumulator rescale). Result rows [0, nq) are written to global
+// through sQ as staging.
+template <int CK>
 __device__ __forceinline__ void warp_attend(__half* sQ, const __half* sK, const __half* sV, int lk, float scale_log2e,
                                             __half* out, long long ostride, int nq, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  // ---- S = Q K^T : 2*KT n-tiles of 8 keys, 5 k-steps of 16 dims
-  float s[2 * KT][4];
+  float o[ND][4];
 #pragma unroll
-  for (int n = 0; n < 2 * KT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+  for (int n = 0; n < ND; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int ntiles = (lk + 15) >> 4;
+  for (int kt0 = 0; kt0 < ntiles; kt0 += CK) {
+    // ---- S = Q K^T for this chunk: 2*CK n-tiles of 8 keys, 5 k-steps of 16 dims
+    float s[2 * CK][4];
 #pragma unroll
-  for (int ks = 0; ks < HDP / 16; ++ks) {
-    uint32_t a[4];
-    ldsm_x4(a, sQ + ((lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + ks * 16 + 8 * (lane >> 4));
+    for (int n = 0; n < 2 * CK; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      uint32_t b[4];  // keys kt*16 + [0,8) / [8,16), dims ks*16 + [0,8) / [8,16)
-      ldsm_x4(b, sK + (kt * 16 + (lane & 7) + 8 * (lane >> 4)) * PITCH + ks * 16 + 8 * ((lane >> 3) & 1));
-      mma16816(s[2 * kt], a, b[0], b[1]);
-      mma16816(s[2 * kt + 1], a, b[2], b[3]);
+    for (int ks = 0; ks < HDP / 16; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(a, sQ + ((lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + ks * 16 + 8 * (lane >> 4));
+#pragma unroll
+      for (int kt = 0; kt < CK; ++kt) {
+        if (kt0 + kt < ntiles) {   // warp-uniform
+          uint32_t b[4];  // keys (kt0+kt)*16 + [0,8) / [8,16), dims ks*16 + [0,8) / [8,16)
+          ldsm_x4(b, sK + ((kt0 + kt) * 16 + (lane & 7) + 8 * (lane >> 4)) * PITCH + ks * 16 + 8 * ((lane >> 3) & 1));
+          mma16816(s[2 * kt], a, b[0], b[1]);
+          mma16816(s[2 * kt + 1], a, b[2], b[3]);
+        }
+      }
     }
-  }
-  // ---- softmax over keys (rows g and g+8 of this quad), fp32
-  float m0 = -INFINITY, m1 = -INFINITY;
+    // ---- online softmax (rows g and g+8 of this quad), fp32
+    float c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
-  for (int n = 0; n < 2 * KT; ++n) {
-    const int col = n * 8 + 2 * t;
-    if (col >= lk) s[n][0] = s[n][2] = -INFINITY;
-    if (col + 1 >= lk) s[n][1] = s[n][3] = -INFINITY;
-    m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
-    m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float l0 = 0.f, l1 = 0.f;
-  uint32_t p[KT][4];
+    for (int n = 0; n < 2 * CK; ++n) {
+      const int col = kt0 * 16 + n * 8 + 2 * t;
+      if (col >= lk) s[n][0] = s[n][2] = -INFINITY;
+      if (col + 1 >= lk) s[n][1] = s[n][3] = -INFINITY;
+      c0 = fmaxf(c0, fmaxf(s[n][0], s[n][1]));
+      c1 = fmaxf(c1, fmaxf(s[n][2], s[n][3]));
+    }
+    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1));
+    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1));
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
+    const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);   // finite: every chunk holds at least one real key
+    const float r0 = exp2f((m0 - n0) * scale_log2e), r1 = exp2f((m1 - n1) * scale_log2e);
+    m0 = n0;
+    m1 = n1;
+    l0 *= r0;
+    l1 *= r1;
 #pragma unroll
-  for (int n = 0; n < 2 * KT; ++n) {
-    float e0 = exp2f((s[n][0] - m0) * scale_log2e), e1 = exp2f((s[n][1] - m0) * scale_log2e);
-    float e2 = exp2f((s[n][2] - m1) * scale_log2e), e3 = exp2f((s[n][3] - m1) * scale_log2e);
-    l0 += e0 + e1;
-    l1 += e2 + e3;
-    // C fragments of key tiles (2kt, 2kt+1) are the A fragment of P for k-step kt
-    p[n >> 1][(n & 1) * 2 + 0] = pack_h2(e0, e1);
-    p[n >> 1][(n & 1) * 2 + 1] = pack_h2(e2, e3);
+    for (int n = 0; n < ND; ++n) {
+      o[n][0] *= r0; o[n][1] *= r0; o[n][2] *= r1; o[n][3] *= r1;
+    }
+    uint32_t p[CK][4];
+#pragma unroll
+    for (int n = 0; n < 2 * CK; ++n) {
+      float e0 = exp2f((s[n][0] - m0) * scale_log2e), e1 = exp2f((s[n][1] - m0) * scale_log2e);
+      float e2 = exp2f((s[n][2] - m1) * scale_log2e), e3 = exp2f((s[n][3] - m1) * scale_log2e);
+      l0 += e0 + e1;
+      l1 += e2 + e3;
+      // C fragments of key tiles (2kt, 2kt+1) are the A fragment of P for k-step kt
+      p[n >> 1][(n & 1) * 2 + 0] = pack_h2(e0, e1);
+      p[n >> 1][(n & 1) * 2 + 1] = pack_h2(e2, e3);
+    }
+    // ---- O += P V : 9 n-tiles of 8 dims, CK k-steps of 16 keys
+#pragma unroll
+    for (int kt = 0; kt < CK; ++kt) {
+      if (kt0 + kt < ntiles) {
+        const __half* vrow = sV + ((kt0 + kt) * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH;
+#pragma unroll
+        for (int n = 0; n < ND - 1; n += 2) {
+          uint32_t b[4];  // V^T fragments: keys [0,8)/[8,16) of the tile, dims n*8 + [0,8) / (n+1)*8 + [0,8)
+          ldsm_x4_t(b, vrow + n * 8 + 8 * (lane >> 4));
+          mma16816(o[n], p[kt], b[0], b[1]);
+          mma16816(o[n + 1], p[kt], b[2], b[3]);
+        }
+        uint32_t b2[2];
+        ldsm_x2_t(b2, vrow + (ND - 1) * 8);
+        mma16816(o[ND - 1], p[kt], b2[0], b2[1]);
+      }
+    }
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  // ---- O = P V : 9 n-tiles of 8 dims, KT k-steps of 16 keys
-  float o[ND][4];
-#pragma unroll
-  for (int n = 0; n < ND; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-  for (int kt = 0; kt < KT; ++kt) {
-#pragma unroll
-    for (int n = 0; n < ND - 1; n += 2) {
-      uint32_t b[4];  // V^T fragments: keys kt*16 + [0,8)/[8,16), dims n*8 + [0,8) / (n+1)*8 + [0,8)
-      ldsm_x4_t(b, sV + (kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + n * 8 + 8 * (lane >> 4));
-      mma16816(o[n], p[kt], b[0], b[1]);
-      mma16816(o[n + 1], p[kt], b[2], b[3]);
-    }
-    uint32_t b2[2];
-    ldsm_x2_t(b2, sV + (kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + (ND - 1) * 8);
-    mma16816(o[ND - 1], p[kt], b2[0], b2[1]);
-  }
   // ---- normalise, stage through sQ, coalesced 16-byte stores
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
   __syncwarp();
@@ -173,6 +199,7 @@ __global__ void __launch_bounds__(TEMPORAL_WARPS * 32) vq_attn_temporal_kernel(c
   load_tile(sQ, q, rstride, a.T, 16, lane, 32);
   load_tile(sK, q + C, rstride, a.T, 16, lane, 32);
   load_tile(sV, q + 2 * C, rstride, a.T, 16, lane, 32);
+  cp_async_wait_all();
   __syncwarp();
   warp_attend<1>(sQ, sK, sV, a.T, a.scale_log2e, a.out + tok0 * C + h * HD, static_cast<long long>(a.S) * C, a.T, lane);
 }
@@ -191,7 +218,7 @@ struct CrossArgs {
 constexpr int CROSS_WARPS = 8;
 constexpr int CROSS_KT = 8;   // 128 keys
 
-__global__ void __launch_bounds__(CROSS_WARPS * 32) vq_attn_cross_kernel(const CrossArgs a) {
+__global__ void __launch_bounds__(CROSS_WARPS * 32, 2) vq_attn_cross_kernel(const CrossArgs a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __half* sK = reinterpret_cast<__half*>(smem_attn);
@@ -207,8 +234,9 @@ __global__ void __launch_bounds__(CROSS_WARPS * 32) vq_attn_cross_kernel(const C
   const int nq = min(16, a.N - row0);
   const long long tok0 = static_cast<long long>(b) * a.N + row0;
   if (nq > 0) load_tile(sQ, a.q + tok0 * C + h * HD, C, nq, 16, lane, 32);
+  cp_async_wait_all();
   __syncthreads();
-  if (nq > 0) warp_attend<CROSS_KT>(sQ, sK, sV, lk, a.scale_log2e, a.out + tok0 * C + h * HD, C, nq, lane);
+  if (nq > 0) warp_attend<4>(sQ, sK, sV, lk, a.scale_log2e, a.out + tok0 * C + h * HD, C, nq, lane);
 }
 
 }  // namespace vq

@@ -71,6 +71,7 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 
 constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (measures the TMA->MMA pipeline alone)
+constexpr int VQ_EPI_GATE_ACCUM = 4;      // internal: out += gate * y, the add done by a TMA reduction (res aliases out)
 
 // Dequantise 32 consecutive output columns of one row, apply the epilogue op and write the fp16 results into this
 // warp's staging tile (row-major 64 B rows, 16-byte chunk index XOR ((row >> 1) & 3) == CU_TENSOR_MAP_SWIZZLE_64B).
@@ -85,7 +86,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
     float f[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      int4 cp = colp[j + e];
+      const int4 cp = lds_v4(colp + j + e);
       int32_t t = static_cast<int32_t>(v[j + e]) - zx * cp.x - rs * cp.y;
       float s = dx * __int_as_float(cp.z);
       f[e] = fmaf(static_cast<float>(t), s, __int_as_float(cp.w));
@@ -97,8 +98,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
     }
     packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
   }
-  if (EPI == VQ_EPI_GATE_RESIDUAL) {
-    // x_new = res + gate * y, each op rounded to fp16 like the reference's half tensors (stdit.py:109,118,123,127)
+  if (EPI == VQ_EPI_GATE_RESIDUAL || EPI == VQ_EPI_GATE_ACCUM) {
+    // x_new = res + gate * y, each op rounded to fp16 like the reference's half tensors (stdit.py:109,118,123,127).
+    // GATE_ACCUM: only gate * y is staged; the "+ res" is a fp16 add by the TMA reduction into out (== res).
     if (row_ok) {
       const __half* gate_row = p.gate + static_cast<size_t>(row / p.rows_per_gate) * p.N;
       const __half* res_row = p.res + static_cast<size_t>(row) * p.ldr;
@@ -107,13 +109,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
         int n = col0 + g * 8;
         if (n < p.N) {
           uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
-          uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
           const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+          uint4 rv = make_uint4(0, 0, 0, 0);
+          if (EPI == VQ_EPI_GATE_RESIDUAL) rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
           const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
-            __half2 o = __hadd2_rn(r2[e], __hmul2_rn(g2[e], y));  // _rn: two roundings, never contracted to an fp16 FMA
+            __half2 o = __hmul2_rn(g2[e], y);   // _rn: never contracted with the add into an fp16 FMA
+            if (EPI == VQ_EPI_GATE_RESIDUAL) o = __hadd2_rn(r2[e], o);
             packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
           }
         }
@@ -243,6 +247,19 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       colbuf[et] = __ldg(colg + (n < nmax ? n : nmax));
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    // per-row dequant parameters {delta, zero point, row sum}, fetched one tile ahead
+    struct RowP { float dx; int32_t zx, rs; };
+    auto load_rowp = [&](int tile_) {
+      RowP r;
+      const int row_ = (tile_ % num_m_tiles) * BM + q * 32 + lane;
+      const int rc = row_ < p.M ? row_ : p.M - 1;
+      const int sr = p.a_period >= p.M ? rc : rc % p.a_period;
+      r.dx = __half2float(p.a_delta[sr]);
+      r.zx = __float2int_rn(__half2float(p.a_zp[sr]));
+      r.rs = p.a_rowsum[rc];
+      return r;
+    };
+    RowP rp_next = load_rowp(blockIdx.x < num_tiles ? blockIdx.x : 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -251,11 +268,11 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int row0 = m_idx + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const int row_c = row_ok ? row : p.M - 1;
-      const int srow = row_c % p.a_period;
-      const float dx = __half2float(p.a_delta[srow]);
-      const int32_t zx = __float2int_rn(__half2float(p.a_zp[srow]));
-      const int32_t rs = p.a_rowsum[row_c];
+      const RowP rp = rp_next;
+      const float dx = rp.dx;
+      const int32_t zx = rp.zx;
+      const int32_t rs = rp.rs;
+      if (tile + static_cast<int>(gridDim.x) < num_tiles) rp_next = load_rowp(tile + gridDim.x);
       // prefetch the next tile's column record (consumed after this tile's math)
       const int next_tile = tile + gridDim.x;
       int4 next_col = make_int4(0, 0, 0, 0);
@@ -285,7 +302,8 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_out, stage, col0, row0);
+            if (EPI == VQ_EPI_GATE_ACCUM) tma_reduce_add_2d(&tmap_out, stage, col0, row0);
+            else tma_store_2d(&tmap_out, stage, col0, row0);
             tma_store_commit();
           }
           buf ^= 1;
@@ -395,6 +413,7 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0 || !out) return VQ_ERR_ARG;
   if (epi == VQ_EPI_GATE_RESIDUAL && (!res || !gate || rows_per_gate <= 0 || (ldr % 8) != 0)) return VQ_ERR_ARG;
   if (epi < 0 || epi > VQ_EPI_DEBUG_MAINLOOP) return VQ_ERR_ARG;
+  if (epi == VQ_EPI_GATE_RESIDUAL && res == out && ldr == ldo) epi = VQ_EPI_GATE_ACCUM;  // in-place residual update
   CUtensorMap ta, tb, to;
   int rc = make_u8_kmajor_tmap(&ta, a_codes, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM);
   if (rc != VQ_OK) return rc;
@@ -423,6 +442,7 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
     case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, args, grid, st);
     case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, args, grid, st);
     case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, args, grid, st);
+    case VQ_EPI_GATE_ACCUM: return launch_gemm<VQ_EPI_GATE_ACCUM>(ta, tb, to, args, grid, st);
     default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, args, grid, st);
   }
 }

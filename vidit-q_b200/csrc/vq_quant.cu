@@ -45,18 +45,66 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-// q = clamp(rint(h(x / delta)) + zp, 0, qmax); x, delta are fp16 values held in fp32, rdelta ~= 1/delta.
-// Division-free but exact: for fp16 operands (11-bit significands) the true quotient is either exactly an fp16
-// rounding midpoint or at least 2^-23 (relative) away from one, so (a) the reference's fp32-then-fp16 double rounding
-// equals one direct rounding, and (b) a quotient with < 2^-24 relative error — one Newton step on x * (1/delta), the
-// residual being exact in one FMA — rounds to the same fp16. (Checked against x/delta on 2e7 random pairs and all
-// golden vectors; see tests.)  NaN (delta == 0, flagged as degenerate) converts to 0.
-__device__ __forceinline__ int quant_code(float x, float delta, float rdelta, int zp, int qmax) {
-  float q0 = x * rdelta;
-  float e = fmaf(-q0, delta, x);
-  float q1 = fmaf(e, rdelta, q0);
-  int q = __half2int_rn(__float2half_rn(q1)) + zp;
-  return min(max(q, 0), qmax);
+// ---------------------------------------------------------------------------------------------------------------
+// Exact, division-free quantisation on packed pairs.
+//   q = clamp(rint(h(x / delta)) + zp, 0, qmax)          (x, delta fp16 values)
+// (1) For fp16 operands (11-bit significands) the true quotient is either exactly an fp16 rounding midpoint or at
+//     least 2^-23 (relative) away from one, so the reference's fp32-then-fp16 double rounding equals one direct
+//     rounding, and a quotient with < 2^-24 relative error — one Newton step on x * (1/delta), the residual being exact
+//     in one FMA — rounds to the same fp16 (validated against x/delta on 2e7 random pairs and every golden vector).
+// (2) rint + zero-point + clamp run in fp16 with the 1.5*2^10 trick: h + 1536 rounds to an integer (RNE, ulp = 1 on
+//     [1024, 2048)), adding (zp - 512) gives 1024 + rint + zp exactly, clamping to [1024, 1024 + qmax] leaves the code
+//     in the low byte of each fp16 lane.  No F2I, two elements per instruction (FFMA2 / HADD2 / HMNMX2).
+// ---------------------------------------------------------------------------------------------------------------
+struct QuantConsts {
+  float2 delta2, rdelta2;   // delta and ~1/delta broadcast to both lanes
+  __half2 zpm;              // zp - 512
+  __half2 hi;               // 1024 + qmax
+};
+
+__device__ __forceinline__ QuantConsts make_consts(float delta, float zp, float qmax) {
+  QuantConsts c;
+  const float r = __frcp_rn(delta);
+  c.delta2 = make_float2(delta, delta);
+  c.rdelta2 = make_float2(r, r);
+  c.zpm = __float2half2_rn(zp - 512.0f);
+  c.hi = __float2half2_rn(1024.0f + qmax);
+  return c;
+}
+
+// two fp16 inputs -> 32-bit word whose 16-bit lanes hold 0x6400 + code
+__device__ __forceinline__ uint32_t quant_pair(__half2 x, const QuantConsts& c) {
+  const float2 xf = __half22float2(x);
+  const float2 q0 = __fmul2_rn(xf, c.rdelta2);
+  const float2 e = __ffma2_rn(make_float2(-q0.x, -q0.y), c.delta2, xf);
+  const float2 q1 = __ffma2_rn(e, c.rdelta2, q0);
+  __half2 y = __floats2half2_rn(q1.x, q1.y);
+  y = __hadd2_rn(y, __float2half2_rn(1536.0f));
+  y = __hadd2_rn(y, c.zpm);
+  y = __hmin2(__hmax2(y, __float2half2_rn(1024.0f)), c.hi);
+  return *reinterpret_cast<uint32_t*>(&y);
+}
+
+// 8 halves (one 16-byte chunk) -> 8 codes (two words); accumulates their sum via dp4a
+__device__ __forceinline__ uint2 quant_chunk(const uint4& v, const QuantConsts& c, int& sum) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const uint32_t a = quant_pair(h[0], c), b = quant_pair(h[1], c), d = quant_pair(h[2], c), f = quant_pair(h[3], c);
+  uint2 out;
+  out.x = __byte_perm(a, b, 0x6420);
+  out.y = __byte_perm(d, f, 0x6420);
+  sum = static_cast<int>(__dp4a(out.x, 0x01010101u, static_cast<unsigned>(sum)));
+  sum = static_cast<int>(__dp4a(out.y, 0x01010101u, static_cast<unsigned>(sum)));
+  return out;
+}
+
+// h(x / s) for fp16 x, s: the same exact Newton-corrected reciprocal
+__device__ __forceinline__ __half2 div_pair(__half2 x, __half2 s) {
+  const float2 xf = __half22float2(x), sf = __half22float2(s);
+  const float2 r = make_float2(__frcp_rn(sf.x), __frcp_rn(sf.y));
+  const float2 q0 = __fmul2_rn(xf, r);
+  const float2 e = __ffma2_rn(make_float2(-q0.x, -q0.y), sf, xf);
+  const float2 q1 = __ffma2_rn(e, r, q0);
+  return __floats2half2_rn(q1.x, q1.y);
 }
 
 struct RowStats {
@@ -100,10 +148,10 @@ __device__ __forceinline__ void apply_smooth(RowRegs<MAXC>& r, const __half* smo
     int ci = lane + 32 * i;
     if (ci < nchunk) {
       uint4 sv = __ldg(reinterpret_cast<const uint4*>(smooth) + ci);
-      __half* x = reinterpret_cast<__half*>(&r.c[i]);
-      const __half* s = reinterpret_cast<const __half*>(&sv);
+      __half2* x = reinterpret_cast<__half2*>(&r.c[i]);
+      const __half2* s = reinterpret_cast<const __half2*>(&sv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = __float2half_rn(__fdiv_rn(__half2float(x[e]), __half2float(s[e])));
+      for (int e = 0; e < 4; ++e) x[e] = div_pair(x[e], s[e]);
     }
   }
 }
@@ -112,64 +160,66 @@ __device__ __forceinline__ void apply_smooth(RowRegs<MAXC>& r, const __half* smo
 template <int MAXC>
 __device__ __forceinline__ void apply_ln_modulate(RowRegs<MAXC>& r, const __half* shift, const __half* scale, int K,
                                                   int nchunk, int lane) {
-  float sum = 0.f;
+  float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     int ci = lane + 32 * i;
     if (ci < nchunk) {
-      const __half* x = reinterpret_cast<const __half*>(&r.c[i]);
+      const __half2* x = reinterpret_cast<const __half2*>(&r.c[i]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sum += __half2float(x[e]);
+      for (int e = 0; e < 4; ++e) sum2 = __fadd2_rn(sum2, __half22float2(x[e]));
     }
   }
-  const float mean = warp_sum(sum) / static_cast<float>(K);
-  float sq = 0.f;
+  const float mean = warp_sum(sum2.x + sum2.y) / static_cast<float>(K);
+  const float2 nmean2 = make_float2(-mean, -mean);
+  float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     int ci = lane + 32 * i;
     if (ci < nchunk) {
-      const __half* x = reinterpret_cast<const __half*>(&r.c[i]);
+      const __half2* x = reinterpret_cast<const __half2*>(&r.c[i]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float d = __half2float(x[e]) - mean;
-        sq = fmaf(d, d, sq);
+      for (int e = 0; e < 4; ++e) {
+        const float2 d = __fadd2_rn(__half22float2(x[e]), nmean2);
+        sq2 = __ffma2_rn(d, d, sq2);
       }
     }
   }
-  const float var = warp_sum(sq) / static_cast<float>(K);
+  const float var = warp_sum(sq2.x + sq2.y) / static_cast<float>(K);
   const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  const float2 rstd2 = make_float2(rstd, rstd);
+  const __half2 one = __float2half2_rn(1.0f);
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     int ci = lane + 32 * i;
     if (ci < nchunk) {
       uint4 shv = __ldg(reinterpret_cast<const uint4*>(shift) + ci);
       uint4 scv = __ldg(reinterpret_cast<const uint4*>(scale) + ci);
-      __half* x = reinterpret_cast<__half*>(&r.c[i]);
-      const __half* sh = reinterpret_cast<const __half*>(&shv);
-      const __half* sc = reinterpret_cast<const __half*>(&scv);
+      __half2* x = reinterpret_cast<__half2*>(&r.c[i]);
+      const __half2* sh = reinterpret_cast<const __half2*>(&shv);
+      const __half2* sc = reinterpret_cast<const __half2*>(&scv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float ln = h_round((__half2float(x[e]) - mean) * rstd);
-        float one_plus = h_round(1.0f + __half2float(sc[e]));
-        float prod = h_round(ln * one_plus);
-        x[e] = __float2half_rn(prod + __half2float(sh[e]));
+      for (int e = 0; e < 4; ++e) {
+        const float2 ln = __fmul2_rn(__fadd2_rn(__half22float2(x[e]), nmean2), rstd2);
+        const __half2 lnh = __floats2half2_rn(ln.x, ln.y);
+        // each op rounded to fp16 separately, like the reference's half tensors (never contracted to an FMA)
+        x[e] = __hadd2_rn(__hmul2_rn(lnh, __hadd2_rn(one, sc[e])), sh[e]);
       }
     }
   }
 }
 
 template <int MAXC>
-__device__ __forceinline__ void row_minmax(const RowRegs<MAXC>& r, int nchunk, int lane, float& mn, float& mx) {
+__device__ __forceinline__ void row_minmax(const RowRegs<MAXC>& r, int nchunk, int lane, __half2& mn2, __half2& mx2) {
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     int ci = lane + 32 * i;
     if (ci < nchunk) {
-      const __half* x = reinterpret_cast<const __half*>(&r.c[i]);
+      const __half2* x = reinterpret_cast<const __half2*>(&r.c[i]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float v = __half2float(x[e]);
-        mn = fminf(mn, v);
-        mx = fmaxf(mx, v);
+      for (int e = 0; e < 4; ++e) {
+        mn2 = __hmin2(mn2, x[e]);
+        mx2 = __hmax2(mx2, x[e]);
       }
     }
   }
@@ -177,25 +227,12 @@ __device__ __forceinline__ void row_minmax(const RowRegs<MAXC>& r, int nchunk, i
 
 template <int MAXC>
 __device__ __forceinline__ int quant_store_row(const RowRegs<MAXC>& r, uint8_t* codes_row, int nchunk, int lane,
-                                               float delta, float zpf, float qmaxf) {
-  const float rdelta = __frcp_rn(delta);
-  const int zp = __float2int_rn(zpf);
-  const int qmax = __float2int_rn(qmaxf);
+                                               const QuantConsts& qc) {
   int sum = 0;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     int ci = lane + 32 * i;
-    if (ci < nchunk) {
-      const __half* x = reinterpret_cast<const __half*>(&r.c[i]);
-      uint32_t w[2] = {0u, 0u};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        int q = quant_code(__half2float(x[e]), delta, rdelta, zp, qmax);
-        sum += q;
-        w[e >> 2] |= static_cast<uint32_t>(q) << (8 * (e & 3));
-      }
-      reinterpret_cast<uint2*>(codes_row)[ci] = make_uint2(w[0], w[1]);
-    }
+    if (ci < nchunk) reinterpret_cast<uint2*>(codes_row)[ci] = quant_chunk(r.c[i], qc, sum);
   }
   return sum;
 }
@@ -223,12 +260,13 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
   if (r >= a.rows) return;
   const int nchunk = a.K >> 3;
   RowRegs<MAXC> regs;
-  float mn = 0.f, mx = 0.f;  // the range always contains zero
+  __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
   for (int g = 0; g < a.G; ++g) {
     load_row<MAXC>(regs, a.x + g * a.group_stride + r * a.ld, nchunk, lane);
     if (LN) {
       apply_ln_modulate<MAXC>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K,
                               a.K, nchunk, lane);
+      if (a.smooth) apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
       if (a.y_out) {
         __half* yrow = a.y_out + (static_cast<size_t>(g) * a.rows + r) * a.K;
 #pragma unroll
@@ -240,11 +278,12 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
     } else if (a.smooth) {
       apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
     }
-    row_minmax<MAXC>(regs, nchunk, lane, mn, mx);
+    row_minmax<MAXC>(regs, nchunk, lane, mn2, mx2);
   }
-  mn = warp_min(mn);
-  mx = warp_max(mx);
+  const float mn = warp_min(fminf(__low2float(mn2), __high2float(mn2)));
+  const float mx = warp_max(fmaxf(__low2float(mx2), __high2float(mx2)));
   const RowStats st = make_stats(mn, mx, a.qmax);
+  const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
   if (lane == 0) {
     a.delta[r] = __float2half_rn(st.delta);
     a.zp[r] = __float2half_rn(st.zp);
@@ -256,12 +295,13 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
       if (LN) {
         apply_ln_modulate<MAXC>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K,
                                 a.K, nchunk, lane);
+        if (a.smooth) apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
       } else if (a.smooth) {
         apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
       }
     }
     const size_t orow = static_cast<size_t>(g) * a.rows + r;
-    int s = quant_store_row<MAXC>(regs, a.codes + orow * a.K, nchunk, lane, st.delta, st.zp, a.qmax);
+    int s = quant_store_row<MAXC>(regs, a.codes + orow * a.K, nchunk, lane, qc);
     s = warp_sum_i(s);
     if (lane == 0) a.rowsum[orow] = s;
   }
@@ -300,28 +340,25 @@ __global__ void __launch_bounds__(256) vq_prep_weight_kernel(const PrepArgs a) {
   if (n >= a.N) return;
   const float delta = __half2float(a.delta[n]);
   const float zp = __half2float(a.zp[n]);
-  const float rdelta = __frcp_rn(delta);
-  const int zpi = __float2int_rn(zp);
-  const int qmaxi = __float2int_rn(a.qmax);
+  const QuantConsts qc = make_consts(delta, zp, a.qmax);
   const __half* wrow = a.w + static_cast<size_t>(n) * a.K;
   uint8_t* crow = a.codes + static_cast<size_t>(n) * a.K;
+  // static (checkpoint) step sizes do not bound |w / delta|: pre-clamp the weight so that |w / delta| <= 511 keeps the
+  // fp16 rounding trick exact; beyond that the code saturates to 0 / qmax either way
+  const __half2 wl = __float2half2_rn(fminf(511.0f * delta, 65504.0f));
   int sum = 0;
   for (int ci = lane; ci < (a.K >> 3); ci += 32) {
     uint4 wv = __ldg(reinterpret_cast<const uint4*>(wrow) + ci);
-    const __half* x = reinterpret_cast<const __half*>(&wv);
-    uint4 sv = make_uint4(0, 0, 0, 0);
-    if (a.smooth) sv = __ldg(reinterpret_cast<const uint4*>(a.smooth) + ci);
-    const __half* s = reinterpret_cast<const __half*>(&sv);
-    uint32_t w[2] = {0u, 0u};
+    __half2* x = reinterpret_cast<__half2*>(&wv);
+    if (a.smooth) {  // quant_layer.py:178 weight * channel_wise_scale (fp16 product)
+      uint4 sv = __ldg(reinterpret_cast<const uint4*>(a.smooth) + ci);
+      const __half2* sm = reinterpret_cast<const __half2*>(&sv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = __half2float(x[e]);
-      if (a.smooth) v = h_round(v * __half2float(s[e]));  // quant_layer.py:178 weight * channel_wise_scale (fp16)
-      int q = quant_code(v, delta, rdelta, zpi, qmaxi);
-      sum += q;
-      w[e >> 2] |= static_cast<uint32_t>(q) << (8 * (e & 3));
+      for (int e = 0; e < 4; ++e) x[e] = __hmul2_rn(x[e], sm[e]);
     }
-    reinterpret_cast<uint2*>(crow)[ci] = make_uint2(w[0], w[1]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = __hmin2(__hmax2(x[e], __hneg2(wl)), wl);
+    reinterpret_cast<uint2*>(crow)[ci] = quant_chunk(wv, qc, sum);
   }
   sum = warp_sum_i(sum);
   if (lane == 0) {
@@ -357,8 +394,8 @@ extern "C" int vq_act_quant(const void* x, int G, int rows, int K, int64_t group
   return launch_act_quant<false>(a, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int vq_ln_modulate_act_quant(const void* x, const void* shift, const void* scale, int G, int rows, int K,
-                                        int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp,
+extern "C" int vq_ln_modulate_act_quant(const void* x, const void* shift, const void* scale, const void* smooth, int G,
+                                        int rows, int K, int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp,
                                         int32_t* rowsum, uint32_t* status, void* stream) {
   using namespace vq;
   if (!x || !shift || !scale || !codes || !delta || !zp || !rowsum || G <= 0 || rows <= 0 || K <= 0)
@@ -370,6 +407,7 @@ extern "C" int vq_ln_modulate_act_quant(const void* x, const void* shift, const 
   a.group_stride = static_cast<long long>(rows) * K; a.ld = K;
   a.shift = static_cast<const __half*>(shift);
   a.scale = static_cast<const __half*>(scale);
+  a.smooth = static_cast<const __half*>(smooth);
   a.y_out = static_cast<__half*>(y_out);
   a.qmax = static_cast<float>((1 << n_bits) - 1);
   a.codes = codes;

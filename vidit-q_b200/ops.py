@@ -118,15 +118,17 @@ def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None) -> ActCo
     return a
 
 
-def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional[ActCodes] = None):
-    """x: fp16 [G, rows, K]; shift/scale: fp16 [G, K]. Returns (ActCodes, y or None)."""
+def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional[ActCodes] = None, smooth=None):
+    """x: fp16 [G, rows, K]; shift/scale: fp16 [G, K]; smooth: fp16 [K] or None. Returns (ActCodes, y or None)."""
     _need_cuda_f16(x, "x")
     _need_cuda_f16(shift, "shift")
     _need_cuda_f16(scale, "scale")
     G, rows, K = x.shape
     a = out if out is not None else _alloc_act(G, rows, K, x.device)
     y = torch.empty_like(x) if want_y else None
-    rc = _lib.lib().vq_ln_modulate_act_quant(_ptr(x), _ptr(shift), _ptr(scale), G, rows, K, n_bits, _ptr(y),
+    if smooth is not None:
+        _need_cuda_f16(smooth, "smooth")
+    rc = _lib.lib().vq_ln_modulate_act_quant(_ptr(x), _ptr(shift), _ptr(scale), _ptr(smooth), G, rows, K, n_bits, _ptr(y),
                                              _ptr(a.codes), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum),
                                              _ptr(status_word(x.device)), _stream())
     _lib.check(rc, "vq_ln_modulate_act_quant")
@@ -134,8 +136,9 @@ def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional
     return a, y
 
 
-def gemm_w8a8(a: ActCodes, w: PreparedWeight, epi=VQ_EPI_BIAS, res=None, gate=None, rows_per_gate=0, out=None):
-    """out[M,N] fp16 = epilogue(dequant(a.codes @ w.codes^T)); M = G*rows."""
+def gemm_w8a8(a: ActCodes, w: PreparedWeight, epi=VQ_EPI_BIAS, res=None, gate=None, rows_per_gate=0, out=None, ldo=None):
+    """out[M,N] fp16 = epilogue(dequant(a.codes @ w.codes^T)); M = G*rows. `out` may be a column slice of a wider
+    row-major tensor (pass its row pitch as ldo)."""
     M = a.G * a.rows
     if a.K != w.K:
         raise _lib.VqError(f"gemm_w8a8: K mismatch {a.K} vs {w.K}")
@@ -146,7 +149,7 @@ def gemm_w8a8(a: ActCodes, w: PreparedWeight, epi=VQ_EPI_BIAS, res=None, gate=No
         _need_cuda_f16(gate, "gate")
     rc = _lib.lib().vq_gemm_w8a8(_ptr(a.codes), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum), a.rows, _ptr(w.codes),
                                  _ptr(w.col), M, w.N, w.K, epi, _ptr(res), w.N, _ptr(gate), rows_per_gate, _ptr(out),
-                                 w.N, _stream())
+                                 w.N if ldo is None else ldo, _stream())
     _lib.check(rc, "vq_gemm_w8a8")
     _count()
     return out

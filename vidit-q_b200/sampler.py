@@ -48,9 +48,13 @@ class SpacedDDIM:
         return float(self.timestep_map[i])
 
     def coefficients(self, i, device):
-        c = [self.sqrt_recip_alphas_cumprod[i], self.sqrt_recipm1_alphas_cumprod[i],
-             np.sqrt(self.alphas_cumprod_prev[i]), np.sqrt(1 - self.alphas_cumprod_prev[i])]
-        return torch.tensor(c, dtype=torch.float32, device=device)
+        # the reference extracts float64 tables to fp32 tensors and takes the square roots in fp32
+        # (gaussian_diffusion.py:543-549 with sigma = 0)
+        ab_prev = torch.tensor(self.alphas_cumprod_prev[i], dtype=torch.float64).float()
+        c = torch.stack([torch.tensor(self.sqrt_recip_alphas_cumprod[i], dtype=torch.float64).float(),
+                         torch.tensor(self.sqrt_recipm1_alphas_cumprod[i], dtype=torch.float64).float(),
+                         torch.sqrt(ab_prev), torch.sqrt(1 - ab_prev)])
+        return c.to(device)
 
     @staticmethod
     def cfg_combine(out_cond, out_uncond, cfg_scale, ptqd_k=0.0):
@@ -77,3 +81,58 @@ class SpacedDDIM:
         out_u = model_forward(x, t, y_uncond, mask=mask)
         out = self.cfg_combine(out_c, out_u, self.cfg_scale)
         return self.ddim_update(x, out, self.coefficients(i, x.device))
+
+
+def get_key_for_value(dict_ranges, value):
+    """gaussian_diffusion.py:24-29: the "hi-lo" range key containing step index `value` (non-range keys skipped)."""
+    for key in dict_ranges:
+        parts = str(key).split("-")
+        if len(parts) != 2 or not all(p.isdigit() for p in parts):
+            continue
+        if int(parts[0]) >= value >= int(parts[1]):
+            return key
+    return None
+
+
+class TimestepMixedPrecision:
+    """Per-timestep bit-width switching of config 4 (quant_txt2video_mp.py:533-540 + gaussian_diffusion.py:739-759):
+    whenever the DDIM step index enters a new range key, re-open the previous FP list, apply the range's FP list and
+    load the per-layer weight / activation bit tables (QuantModel.load_bitwidth_config; delta stays, quirk Q7)."""
+
+    def __init__(self, qnn):
+        self.qnn = qnn
+        self.key, self.fp_prev = None, None
+
+    def before_step(self, i):
+        qnn = self.qnn
+        if not getattr(qnn, "timestep_wise_mp", False):
+            return False
+        key = get_key_for_value(qnn.time_mp_config_weight, i)
+        if key is None:
+            raise RuntimeError(f"this timestep {i} is not included by the config")
+        if key == self.key:
+            return False
+        if self.fp_prev is not None:
+            qnn.set_layer_quant(model=qnn, module_name_list=self.fp_prev, quant_level="per_layer", weight_quant=True,
+                                act_quant=True, prefix="")
+        fp_layers = qnn.time_mp_config_weight["fp_layers"][key]
+        qnn.set_layer_quant(model=qnn, module_name_list=fp_layers, quant_level="per_layer", weight_quant=False,
+                            act_quant=False, prefix="")
+        qnn.load_bitwidth_config(model=qnn, bit_config=qnn.time_mp_config_weight[key], bit_type="weight")
+        qnn.load_bitwidth_config(model=qnn, bit_config=qnn.time_mp_config_act[key], bit_type="act")
+        self.key, self.fp_prev = key, fp_layers
+        return True
+
+
+def ddim_sample_loop(ddim: SpacedDDIM, model_forward, z, y_cond, y_uncond, mask, qnn=None, on_step=None):
+    """iddpm IDDPM.sample(..., 'ddim') for cfg_split models: all steps from num_timesteps-1 down to 0."""
+    mp = TimestepMixedPrecision(qnn) if qnn is not None else None
+    for i in range(ddim.num_timesteps - 1, -1, -1):
+        if mp is not None:
+            mp.before_step(i)
+        if qnn is not None:
+            qnn.set_timestep_id_for_quantlayer(ddim.model_timestep(i))
+        z = ddim.step(model_forward, z, i, y_cond, y_uncond, mask)
+        if on_step is not None:
+            on_step(i, z)
+    return z

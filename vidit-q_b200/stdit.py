@@ -335,11 +335,31 @@ class FusedBlocks:
             for l in layers:
                 if not (isinstance(l, QuantLayer) and l.weight_quant and l.act_quant):
                     raise NotImplementedError("forward_fused needs every block linear in W+A quantised state")
+            if any(l.smooth_quant for l in layers):
+                return None   # per-layer channel scales (quant_layer.py:137 depends on each weight): no shared input codes
             pw = self._qkv[key] = self._cat_prepared(layers)
-            pw.smooth = getattr(layers[0].prepared_weight(), "smooth", None)
-            if any(getattr(l.prepared_weight(), "smooth", None) is not None for l in layers):
-                raise NotImplementedError("fused q|k|v with smooth-quant needs a shared channel scale; use forward()")
         return pw
+
+    def _qkv_project(self, attn, tag, x, ln=None):
+        """q|k|v of one attention as one [M, 3C] tensor. ln = (shift, scale) fuses LayerNorm+modulate in front.
+        Without smooth-quant: one quantise pass + one N=3C GEMM. With it (w4a8_timestep_aware_cb.yaml): each layer has
+        its own channel scale, hence its own codes; the three GEMMs write column slices of the same output."""
+        pw = self._qkv_weight(attn, tag)
+        nb = attn.q.act_quantizer.n_bits
+        if pw is not None:
+            a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb)[0] if ln is not None else ops.act_quant(x, n_bits=nb)
+            return ops.gemm_w8a8(a, pw)
+        B, N, C = x.shape
+        out = torch.empty(B * N, 3 * C, dtype=x.dtype, device=x.device)
+        for j, layer in enumerate((attn.q, attn.k, attn.v)):
+            lw = layer.prepared_weight()
+            sm = getattr(lw, "smooth", None)
+            if ln is not None:
+                a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, smooth=sm)[0]
+            else:
+                a = ops.act_quant(x, n_bits=nb, smooth=sm)
+            ops.gemm_w8a8(a, lw, out=out[:, j * C:(j + 1) * C], ldo=3 * C)
+        return out
 
     def run(self, x, y, t0, y_lens, segments):
         m = self.m
@@ -347,25 +367,24 @@ class FusedBlocks:
         T, S, H = m.num_temporal, m.num_spatial, m.num_heads
         D = C // H
         M = B * N
-        x = x.contiguous()
+        x = x.contiguous()   # fresh tensor from embed(): the residual stream is updated in place below
         ones = torch.ones(1, C, dtype=x.dtype, device=x.device)
         tpe = m.pos_embed_temporal.to(x.dtype)
         for i, blk in enumerate(m.blocks):
             shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = (
                 v.reshape(B, C).contiguous() for v in blk.modulation(t0))
             # ---- spatial attention: LN + modulate + quantise once, one q|k|v GEMM
-            a, _ = ops.ln_modulate_act_quant(x, shift_msa, scale_msa, n_bits=blk.attn.q.act_quantizer.n_bits)
-            qkv = ops.gemm_w8a8(a, self._qkv_weight(blk.attn, (i, "s"))).view(B * T, S, 3, H, D)
+            qkv = self._qkv_project(blk.attn, (i, "s"), x, ln=(shift_msa, scale_msa)).view(B * T, S, 3, H, D)
             o = F.scaled_dot_product_attention(qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2),
                                                qkv[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
             o = o.transpose(1, 2).reshape(B, N, C)
             a = blk.attn.proj.quantize_input(o.view(B * T, S, C))
-            x = ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=x.view(M, C),
-                              gate=gate_msa, rows_per_gate=N).view(B, N, C)
+            xr = x.view(M, C)   # residual stream, updated in place: out aliases res -> TMA reduce-add epilogue
+            ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
+                          rows_per_gate=N, out=xr)
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
             xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
-            a = ops.act_quant(xt, n_bits=blk.attn_temp.q.act_quantizer.n_bits)
-            qkv = ops.gemm_w8a8(a, self._qkv_weight(blk.attn_temp, (i, "t")))
+            qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt)
             if T <= 16 and D == 72:      # own kernel: reads the (T S) layout in place, no permute copies
                 o = ops.attn_temporal(qkv, B, T, S, H, D, blk.attn_temp.scale).view(B, N, C)
             else:                        # library path for shapes the kernel does not cover
@@ -373,9 +392,9 @@ class FusedBlocks:
                 qt, kt, vt = (q5[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
                 o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)
                 o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
-            a = ops.act_quant(o, n_bits=blk.attn_temp.proj.act_quantizer.n_bits)
-            x = ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=x.view(M, C),
-                              gate=gate_msa, rows_per_gate=N).view(B, N, C)
+            a = blk.attn_temp.proj.quantize_input(o.view(B, S * T, C))   # per-token statistics: row order irrelevant
+            ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
+                          rows_per_gate=N, out=xr)
             # ---- cross attention
             ca = blk.cross_attn
             q = ops.gemm_w8a8(ca.q_linear.quantize_input(x), ca.q_linear.prepared_weight())
@@ -384,12 +403,14 @@ class FusedBlocks:
                 o = ops.attn_cross(q, kv, segments[0], segments[1], B, N, H, D, max(y_lens), D ** -0.5).view(B, N, C)
             else:
                 o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
-            x = ops.gemm_w8a8(ca.proj.quantize_input(o), ca.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
-                              res=x.view(M, C), gate=ones, rows_per_gate=M).view(B, N, C)
+            ops.gemm_w8a8(ca.proj.quantize_input(o), ca.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
+                          res=xr, gate=ones, rows_per_gate=M, out=xr)
             # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
-            a, _ = ops.ln_modulate_act_quant(x, shift_mlp, scale_mlp, n_bits=blk.mlp.fc1.act_quantizer.n_bits)
-            h = ops.gemm_w8a8(a, blk.mlp.fc1.prepared_weight(), epi=ops.VQ_EPI_GELU_TANH).view(B, N, -1)
+            fc1w = blk.mlp.fc1.prepared_weight()
+            a, _ = ops.ln_modulate_act_quant(x, shift_mlp, scale_mlp, n_bits=blk.mlp.fc1.act_quantizer.n_bits,
+                                             smooth=getattr(fc1w, "smooth", None))
+            h = ops.gemm_w8a8(a, fc1w, epi=ops.VQ_EPI_GELU_TANH).view(B, N, -1)
             a = blk.mlp.fc2.quantize_input(h)
-            x = ops.gemm_w8a8(a, blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=x.view(M, C),
-                              gate=gate_mlp, rows_per_gate=N).view(B, N, C)
+            ops.gemm_w8a8(a, blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp,
+                          rows_per_gate=N, out=xr)
         return x
