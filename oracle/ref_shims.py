@@ -161,3 +161,64 @@ def install_opensora():
         fmha = _module("xformers.ops.fmha", BlockDiagonalMask=BlockDiagonalMask)
         xo = _module("xformers.ops", memory_efficient_attention=memory_efficient_attention, fmha=fmha)
         _module("xformers", ops=xo)
+
+
+def install_pixart():
+    """Make `diffusion.model.nets.PixArtMS` (reference t2i graph) importable: path-only packages (no __init__
+    execution), a no-op mmcv-style registry, and constructor-only restatements of the timm pieces it subclasses."""
+    install_opensora()   # omegaconf / diffusers / xformers / qdiff stubs (shared)
+    import torch
+    import torch.nn as nn
+    t2i = os.path.join(REFERENCE_ROOT, "t2i")
+
+    def pkg(name, path):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [path]
+            sys.modules[name] = m
+
+    pkg("diffusion", os.path.join(t2i, "diffusion"))
+    pkg("diffusion.model", os.path.join(t2i, "diffusion", "model"))
+    pkg("diffusion.model.nets", os.path.join(t2i, "diffusion", "model", "nets"))
+    pkg("diffusion.utils", os.path.join(t2i, "diffusion", "utils"))
+    if "diffusion.model.builder" not in sys.modules:
+        class _Registry:
+            def register_module(self, *a, **k):
+                if len(a) == 1 and callable(a[0]) and not k:
+                    return a[0]
+                return lambda obj: obj
+        _module("diffusion.model.builder", MODELS=_Registry())
+    if "diffusion.model.utils" not in sys.modules:
+        def auto_grad_checkpoint(module, *args, **kwargs):
+            return module(*args, **kwargs)
+
+        def to_2tuple(x):
+            return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+        _module("diffusion.model.utils", auto_grad_checkpoint=auto_grad_checkpoint, to_2tuple=to_2tuple,
+                set_grad_checkpoint=lambda *a, **k: None)
+    if "diffusion.utils.logger" not in sys.modules:
+        import logging
+        _module("diffusion.utils.logger", get_root_logger=lambda *a, **k: logging.getLogger("pixart"))
+    vt = sys.modules["timm.models.vision_transformer"]
+    if not hasattr(vt, "Attention"):
+        class Attention(nn.Module):
+            def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, **unused):
+                super().__init__()
+                self.num_heads = num_heads
+                self.scale = (dim // num_heads) ** -0.5
+                self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+                self.attn_drop = nn.Dropout(attn_drop)
+                self.proj = nn.Linear(dim, dim)
+                self.proj_drop = nn.Dropout(proj_drop)
+
+        class PatchEmbed(nn.Module):
+            def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, bias=True, **unused):
+                super().__init__()
+                self.patch_size = (patch_size, patch_size)
+                self.num_patches = (img_size // patch_size) ** 2
+                self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
+
+            def forward(self, x):
+                return self.proj(x).flatten(2).transpose(1, 2)
+        vt.Attention = Attention
+        vt.PatchEmbed = PatchEmbed

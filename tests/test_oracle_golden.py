@@ -133,3 +133,26 @@ def test_torch_fake_quant_restatement_is_bit_exact_on_cpu(golden, name):
     out = TF.quant_linear_fake(xv, torch.from_numpy(c["weight"]), bias, torch.from_numpy(c["wdelta"]),
                                torch.from_numpy(c["wzp"]), int(c["w_bits"]), 8, sm)
     np.testing.assert_array_equal(out.numpy().reshape(c["out"].shape), c["out"])
+
+
+@pytest.mark.parametrize("name", ["layer/mlp_fc1", "layer/spatial_attn_b2", "layer/w4_smooth_t900", "layer/cross_kv"])
+def test_torch_exact_operand_simulation_equals_integer_decomposition(golden, name):
+    """oracle.torch_fake_quant(exact=True) — the simulation with un-rounded dequantised operands — is the same number
+    as the integer decomposition the kernels evaluate (up to fp32 summation order)."""
+    import torch
+    from oracle import torch_fake_quant as TF
+    c = golden[name]
+    x, smooth = _layer_inputs(c)
+    B, n = LAYER_VIEWS[name](x.shape)
+    xv = x.reshape(B, n, x.shape[-1])
+    sm = None if smooth is None else torch.from_numpy(smooth)
+    bias = c["bias"] if "bias" in c else None
+    ex = TF.quant_linear_fake(torch.from_numpy(xv), torch.from_numpy(c["weight"]),
+                              None if bias is None else torch.from_numpy(bias), torch.from_numpy(c["wdelta"]),
+                              torch.from_numpy(c["wzp"]), int(c["w_bits"]), 8, sm, exact=True).numpy()
+    a = O.dynamic_act_quant(xv, 8, smooth)
+    wq = O.weight_quant(c["weight"], c["wdelta"], c["wzp"], int(c["w_bits"]), smooth)
+    y = O.quant_linear_int(a["codes"], a["delta"], a["zp"], a["rowsum"], wq["codes"], c["wdelta"], c["wzp"], bias)
+    d = np.abs(ex.astype(np.float32) - y.astype(np.float32))
+    assert d.max() <= 2 * float(np.spacing(np.float16(np.abs(y.astype(np.float32)).max())))
+    assert (d > 0).mean() < 0.02

@@ -1,0 +1,106 @@
+"""PixArt-alpha/MS (BASELINE config 2 family): host graph pinned on CPU against the reference's
+fp32 output, and — on the GPU — the W8A8 integer kernels against the simulated quantisation (same back end) and the
+reference's own fp16 W8A8 output (tests/golden/pixart_small_golden.npz, generator make_golden_pixart.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_stdit_graph_cpu import Cfg, ckpt_from_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FP_LAYERS = ["x_embedder", "t_embedder", "t_block", "y_embedder", "csize_embedder", "ar_embedder"]
+
+
+@pytest.fixture(scope="module")
+def pix():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pixart_small_golden.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def build(pix):
+    from viditq_b200.pixart import PixArtMS
+    from viditq_b200.qdiff import QuantModel
+    model = PixArtMS(input_size=16, depth=2)
+    model.init_synthetic(seed=0)
+    model.eval()
+    sq = Cfg(enable=False, channel_wise_scale_type="momentum_act_max", momentum=0.95, alpha=0.625)
+    wq = Cfg(n_bits=8, per_group="channel", channel_dim=0, scale_method="min_max", round_mode="nearest",
+             mixed_precision=[4, 6, 8])
+    aq = Cfg(n_bits=8, per_group="token", scale_method="min_max", round_mode="nearest_ste", running_stat=False,
+             dynamic=True, sym=False, n_spatial_token=64, n_temporal_token=1, n_prompt=120, smooth_quant=sq)
+    qnn = QuantModel(model, wq, aq, model_type="pixart")
+    qnn.set_module_name_for_quantizer(module=qnn.model)
+    qnn.set_quant_params_dict(ckpt_from_golden(pix))
+    qnn.set_quant_init_done("weight")
+    qnn.set_quant_init_done("activation")
+    return qnn, model
+
+
+def _rel(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return np.abs(a - b).max() / np.abs(b).max(), np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_pixart_layer_types_and_fp_graph(pix):
+    from viditq_b200 import qdiff
+    qnn, model = build(pix)
+    b = model.blocks[0]
+    assert type(b.attn.qkv) is qdiff.QuantAttnLinearImg and type(b.attn.proj) is qdiff.QuantAttnLinearImg
+    assert type(b.cross_attn.kv_linear) is qdiff.QuantCrossAttnLinearImg
+    assert type(b.mlp.fc2) is qdiff.QuantLayer and type(model.final_layer.linear) is qdiff.QuantLayer
+    assert sum(1 for n, _ in qnn.quant_layers() if n.startswith("blocks.")) == 7 * 2   # 7 quantised linears per block
+    qnn.set_quant_state(False, False)
+    with torch.no_grad():
+        out = qnn(torch.from_numpy(pix["x"]), torch.from_numpy(pix["t"]), torch.from_numpy(pix["y"]).float(),
+                  mask=torch.from_numpy(pix["mask"])).numpy()
+    inf, _ = _rel(out, pix["out_fp32"])
+    assert inf < 2e-5, inf
+
+
+@pytest.mark.gpu
+def test_pixart_w8a8_on_gpu(pix):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import torch_fake_quant as TF
+    from viditq_b200 import ops
+    qnn, model = build(pix)
+    qnn.cuda()
+    qnn.half()
+    model.dtype = torch.float16
+    qnn.set_quant_state(True, True)
+    qnn.set_layer_quant(model=qnn, module_name_list=FP_LAYERS, quant_level="per_layer", weight_quant=False,
+                        act_quant=False, prefix="")
+    assert model.final_layer.linear.get_quant_state() == (True, True)      # quantised in PixArt (unlike STDiT)
+    x, t = torch.from_numpy(pix["x"]).cuda(), torch.from_numpy(pix["t"]).cuda()
+    y, mask = torch.from_numpy(pix["y"]).cuda(), torch.from_numpy(pix["mask"]).cuda()
+
+    saved = {}
+
+    def make(layer):
+        def fwd(inp, *a, **k):
+            if not (layer.weight_quant and layer.act_quant):
+                return saved[layer](inp)
+            wq = layer.weight_quantizer
+            return TF.quant_linear_fake(inp, layer.weight, layer.bias, wq.delta, wq.zero_point, wq.n_bits, 8,
+                                        exact=True)
+        return fwd
+    for _, layer in qnn.quant_layers():
+        saved[layer] = layer.forward
+        layer.forward = make(layer)
+    with torch.no_grad():
+        sim = qnn(x, t, y, mask=mask).float().cpu().numpy()
+    for layer in saved:
+        del layer.forward
+    n0 = ops.launch_count()
+    with torch.no_grad():
+        out = qnn(x, t, y, mask=mask).float().cpu().numpy()
+        fused = model.forward_fused(x, t, y, mask=mask).float().cpu().numpy()
+    assert ops.launch_count() - n0 >= 2 * 2 * 15 and ops.check_status() == 0
+    a, b = _rel(out, sim), _rel(fused, sim)
+    c, d = _rel(out, pix["out_w8a8"]), _rel(fused, pix["out_w8a8"])
+    print("pixart int vs exact-operand sim: layerwise %.3e %.3e | fused %.3e %.3e" % (a + b))
+    print("pixart vs reference (CPU fp16) W8A8: layerwise %.3e %.3e | fused %.3e %.3e" % (c + d))
+    assert a[1] <= 1e-3 and b[1] <= 1.5e-3, (a, b)
+    assert c[1] <= 5e-3 and d[1] <= 5e-3, (c, d)      # cross-back-end; quantisation noise itself is 1.0e-2 here
