@@ -33,18 +33,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: build a tuning variant next to the product library (e.g. -DVQ_EPI_WARPS=8 for A/B timing)."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    target = LIB if out is None else os.path.join(HERE, out)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", target]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libviditq_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -41,6 +41,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -112,7 +117,7 @@ __device__ __forceinline__ void warp_attend(__half* sQ, const __half* sK, const 
     c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1));
     c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
     const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);   // finite: every chunk holds at least one real key
-    const float r0 = exp2f((m0 - n0) * scale_log2e), r1 = exp2f((m1 - n1) * scale_log2e);
+    const float r0 = fast_exp2((m0 - n0) * scale_log2e), r1 = fast_exp2((m1 - n1) * scale_log2e);
     m0 = n0;
     m1 = n1;
     l0 *= r0;
@@ -124,8 +129,8 @@ __device__ __forceinline__ void warp_attend(__half* sQ, const __half* sK, const 
     uint32_t p[CK][4];
 #pragma unroll
     for (int n = 0; n < 2 * CK; ++n) {
-      float e0 = exp2f((s[n][0] - m0) * scale_log2e), e1 = exp2f((s[n][1] - m0) * scale_log2e);
-      float e2 = exp2f((s[n][2] - m1) * scale_log2e), e3 = exp2f((s[n][3] - m1) * scale_log2e);
+      float e0 = fast_exp2((s[n][0] - m0) * scale_log2e), e1 = fast_exp2((s[n][1] - m0) * scale_log2e);
+      float e2 = fast_exp2((s[n][2] - m1) * scale_log2e), e3 = fast_exp2((s[n][3] - m1) * scale_log2e);
       l0 += e0 + e1;
       l1 += e2 + e3;
       // C fragments of key tiles (2kt, 2kt+1) are the A fragment of P for k-step kt
@@ -155,7 +160,7 @@ __device__ __forceinline__ void warp_attend(__half* sQ, const __half* sK, const 
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   // ---- normalise, stage through sQ, coalesced 16-byte stores
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const float i0 = __fdividef(1.0f, l0), i1 = __fdividef(1.0f, l1);
   __syncwarp();
 #pragma unroll
   for (int n = 0; n < ND; ++n) {
@@ -196,9 +201,19 @@ __global__ void __launch_bounds__(TEMPORAL_WARPS * 32) vq_attn_temporal_kernel(c
   const long long tok0 = static_cast<long long>(b) * a.T * a.S + sidx;   // token (b, t=0, s)
   const long long rstride = static_cast<long long>(a.S) * 3 * C;         // next frame, same spatial position
   const __half* q = a.qkv + tok0 * 3 * C + h * HD;
-  load_tile(sQ, q, rstride, a.T, 16, lane, 32);
-  load_tile(sK, q + C, rstride, a.T, 16, lane, 32);
-  load_tile(sV, q + 2 * C, rstride, a.T, 16, lane, 32);
+  // 16 rows x 10 sixteen-byte chunks (9 data + 1 zero pad) = 5 per lane; one (row, chunk) pattern serves q, k and v
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int c = lane + 32 * i;
+    const int r = c / 10, cc = c - r * 10;
+    const bool real = cc < 9 && r < a.T;
+    const long long goff = real ? r * rstride + cc * 8 : 0;
+    const int soff = r * PITCH + cc * 8;
+    const int nbytes = real ? 16 : 0;
+    cp_async16(sQ + soff, q + goff, nbytes);
+    cp_async16(sK + soff, q + C + goff, nbytes);
+    cp_async16(sV + soff, q + 2 * C + goff, nbytes);
+  }
   cp_async_wait_all();
   __syncwarp();
   warp_attend<1>(sQ, sK, sV, a.T, a.scale_log2e, a.out + tok0 * C + h * HD, static_cast<long long>(a.S) * C, a.T, lane);

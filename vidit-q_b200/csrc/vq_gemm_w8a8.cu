@@ -13,10 +13,12 @@
 //   warp 0      : TMA producer   (one elected lane; A box 128 rows x 128 B, B box 192 rows x 128 B, SWIZZLE_128B)
 //   warp 1      : MMA issuer     (one elected lane; 4 x tcgen05.mma 128x192x32 per 128-byte K block)
 //   warp 2      : TMEM allocator (512 columns = 2 accumulator stages x 256)
-//   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half)
+//   warps 4..19 : epilogue       (tcgen05.ld 32x32b; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column group)
 // Pipelines: smem full/empty ring (4 stages x 40 KB) and TMEM full/empty (2 stages), all mbarrier based.
 // Epilogue output path: registers -> per-warp 32x32 fp16 staging tile in smem (64B swizzle, bank-conflict free)
-// -> TMA store (cp.async.bulk.tensor, coalesced, clipped at the M/N edges by the tensor map).
+// -> TMA store (cp.async.bulk.tensor, coalesced, clipped at the M/N edges by the tensor map). For the gated-residual
+// epilogue the residual tile is TMA-loaded into the same staging tile one chunk ahead (per-warp mbarriers), so the
+// SM never issues row-scattered global loads; out may alias res (in-place residual stream).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -38,13 +40,22 @@ constexpr int B_STAGE_BYTES = BN * BK;  // 24 KB
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;  // TMEM column stride between accumulator stages
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_EPI_WARPS = 8;
+#ifndef VQ_EPI_WARPS
+#define VQ_EPI_WARPS 16
+#endif
+constexpr int NUM_EPI_WARPS = VQ_EPI_WARPS;           // 8: two per scheduler, 32-column chunks; 16: four, 16-column chunks
+static_assert(NUM_EPI_WARPS == 8 || NUM_EPI_WARPS == 16, "8 or 16 epilogue warps");
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
-constexpr int EPI_CHUNK = 32;                         // output columns per epilogue step (64 B of fp16 per row)
-constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one warp's staging tile: 32 rows x 64 B, SWIZZLE_64B
-constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 2 * EPI_BUF_BYTES;  // double-buffered per warp
+constexpr int EPI_COL_GROUPS = NUM_EPI_WARPS / 4;     // column groups (each warp: one TMEM lane quarter x one group)
+constexpr int EPI_COLS = BN / EPI_COL_GROUPS;         // columns per warp per tile (96 | 48)
+constexpr int EPI_CHUNK = NUM_EPI_WARPS == 8 ? 32 : 16;   // output columns per epilogue step
+constexpr int EPI_NCHUNK = EPI_COLS / EPI_CHUNK;      // 3
+constexpr int EPI_V4 = EPI_CHUNK / 8;                 // 16-byte pieces per staged row (4 | 2)
+constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one warp's staging tile: 32 rows x (64 | 32) B, 64B / 32B swizzle
+constexpr int EPI_NBUF = 3;                           // staging tiles per warp (residual load / math / store in flight)
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_NBUF * EPI_BUF_BYTES;
 constexpr int COLBUF_BYTES = 2 * BN * 16;                // per-tile {c1, zw, dw, bias} records, double-buffered
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + COLBUF_BYTES + 256 + 1024;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
 
 struct GemmArgs {
   int M, N, K;
@@ -71,18 +82,17 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 
 constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (measures the TMA->MMA pipeline alone)
-constexpr int VQ_EPI_GATE_ACCUM = 4;      // internal: out += gate * y, the add done by a TMA reduction (res aliases out)
 
 // Dequantise 32 consecutive output columns of one row, apply the epilogue op and write the fp16 results into this
 // warp's staging tile (row-major 64 B rows, 16-byte chunk index XOR ((row >> 1) & 3) == CU_TENSOR_MAP_SWIZZLE_64B).
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&v)[32], int row, int col0,
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&v)[EPI_CHUNK], int row, int col0,
                                                int32_t zx, int32_t rs, float dx, bool row_ok, uint8_t* stage,
                                                int lane, const int4* colp) {
-  // colp: this chunk's 32 column records in shared memory (warp-uniform address -> broadcast LDS.128)
-  uint32_t packed[16];
+  // colp: this chunk's column records in shared memory (warp-uniform address -> broadcast LDS.128)
+  uint32_t packed[EPI_CHUNK / 2];
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
+  for (int j = 0; j < EPI_CHUNK; j += 2) {
     float f[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -98,44 +108,46 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
     }
     packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
   }
-  if (EPI == VQ_EPI_GATE_RESIDUAL || EPI == VQ_EPI_GATE_ACCUM) {
+  // staging tile: row-major (64 | 32)-byte rows; 16-byte piece index XOR-swizzled exactly like the TMA tensor map
+  // (SWIZZLE_64B: ^ ((row >> 1) & 3); SWIZZLE_32B: ^ ((row >> 2) & 1)) -> conflict-free 16-byte accesses
+  const uint32_t sw = EPI_V4 == 4 ? ((static_cast<uint32_t>(lane) >> 1) & 3u) : ((static_cast<uint32_t>(lane) >> 2) & 1u);
+  uint4* srow = reinterpret_cast<uint4*>(stage + lane * (EPI_CHUNK * 2));
+  if (EPI == VQ_EPI_GATE_RESIDUAL) {
     // x_new = res + gate * y, each op rounded to fp16 like the reference's half tensors (stdit.py:109,118,123,127).
-    // GATE_ACCUM: only gate * y is staged; the "+ res" is a fp16 add by the TMA reduction into out (== res).
-    if (row_ok) {
-      const __half* gate_row = p.gate + static_cast<size_t>(row / p.rows_per_gate) * p.N;
-      const __half* res_row = p.res + static_cast<size_t>(row) * p.ldr;
+    // The residual chunk already sits in the staging tile (TMA load, same swizzle); it is overwritten in place.
+    const __half* gate_row = p.gate + static_cast<size_t>((row_ok ? row : 0) / p.rows_per_gate) * p.N;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        int n = col0 + g * 8;
-        if (n < p.N) {
-          uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
-          const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
-          uint4 rv = make_uint4(0, 0, 0, 0);
-          if (EPI == VQ_EPI_GATE_RESIDUAL) rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
-          const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+    for (int g = 0; g < EPI_V4; ++g) {
+      const int n = col0 + g * 8;
+      uint4 gv = make_uint4(0, 0, 0, 0);
+      if (n < p.N) gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+      const uint4 rv = srow[g ^ sw];
+      const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+      const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
-            __half2 o = __hmul2_rn(g2[e], y);   // _rn: never contracted with the add into an fp16 FMA
-            if (EPI == VQ_EPI_GATE_RESIDUAL) o = __hadd2_rn(r2[e], o);
-            packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
-          }
-        }
+      for (int e = 0; e < 4; ++e) {
+        __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
+        __half2 o = __hadd2_rn(r2[e], __hmul2_rn(g2[e], y));   // _rn: two roundings, never one fp16 FMA
+        packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
       }
     }
   }
-  const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
-  uint4* srow = reinterpret_cast<uint4*>(stage + lane * (EPI_CHUNK * 2));
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < EPI_V4; ++g) {
     srow[g ^ sw] = make_uint4(packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
   }
+}
+
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[EPI_CHUNK]) {
+  if constexpr (EPI_CHUNK == 32) tmem_ld_32x32b_x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
+  else tmem_ld_32x32b_x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                    const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -148,7 +160,8 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint64_t* res_bar = bars + 2 * STAGES + 2 * ACC_STAGES;   // [NUM_EPI_WARPS][EPI_NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NUM_EPI_WARPS * EPI_NBUF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,6 +175,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
+    if (EPI == VQ_EPI_GATE_RESIDUAL) tma_prefetch_desc(&tmap_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -172,6 +186,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
     }
+    for (int i = 0; i < NUM_EPI_WARPS * EPI_NBUF; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -234,19 +249,20 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int h = (warp - 4) >> 2;   // column half
-    const int et = threadIdx.x - 128;  // 0..255 within the epilogue warps
-    uint8_t* stage0 = smem_epi + (warp - 4) * 2 * EPI_BUF_BYTES;
+    const int h = (warp - 4) >> 2;   // column group
+    const int et = threadIdx.x - 128;  // index within the epilogue warps
+    uint8_t* stage0 = smem_epi + (warp - 4) * EPI_NBUF * EPI_BUF_BYTES;
+    uint64_t* my_res_bar = res_bar + (warp - 4) * EPI_NBUF;
+    uint32_t n_issued = 0, n_done = 0;   // residual loads issued / chunks written (same order)
     const int4* colg = reinterpret_cast<const int4*>(p.col);
     const int nmax = p.N - 1;
-    int buf = 0;
     int local = 0;
     // column records of the first tile -> colbuf[0]
     if (blockIdx.x < num_tiles && et < BN) {
       const int n = (blockIdx.x / num_m_tiles) * BN + et;
       colbuf[et] = __ldg(colg + (n < nmax ? n : nmax));
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
     // per-row dequant parameters {delta, zero point, row sum}, fetched one tile ahead
     struct RowP { float dx; int32_t zx, rs; };
     auto load_rowp = [&](int tile_) {
@@ -280,33 +296,54 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n = (next_tile / num_m_tiles) * BN + et;
         next_col = __ldg(colg + (n < nmax ? n : nmax));
       }
-      const int4* ctile = colbuf + acc * BN + h * (BN / 2);
+      const int4* ctile = colbuf + acc * BN + h * EPI_COLS;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * (BN / 2);
-      constexpr int NCHUNK = BN / 2 / EPI_CHUNK;
-      uint32_t v[2][32];
-      tmem_ld_32x32b_x32(t_base, v[0]);
+      const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * EPI_COLS;
+      constexpr int NCHUNK = EPI_NCHUNK;
+      // residual tile of chunk c -> staging buffer (n_issued % 3); the store that last read that buffer is >= 2 back
+      auto issue_res = [&](int c) {
+        const int col0_ = n_idx + h * EPI_COLS + c * EPI_CHUNK;
+        if (EPI == VQ_EPI_GATE_RESIDUAL && col0_ < p.N && row0 < p.M) {
+          if (lane == 0) {
+            const uint32_t b = n_issued % EPI_NBUF;
+            tma_store_wait_read<1>();
+            mbar_arrive_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
+            tma_load_2d(stage0 + b * EPI_BUF_BYTES, &tmap_res, &my_res_bar[b], col0_, row0);
+          }
+          ++n_issued;
+        }
+      };
+      issue_res(0);
+      uint32_t v[2][EPI_CHUNK];
+      tmem_ld_chunk(t_base, v[0]);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
-        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is dequantised
-        if (c + 1 < NCHUNK) tmem_ld_32x32b_x32(t_base + (c + 1) * EPI_CHUNK, v[(c + 1) & 1]);
-        const int col0 = n_idx + h * (BN / 2) + c * EPI_CHUNK;
+        // software pipeline: the TMEM load (and residual TMA load) of chunk c+1 fly while chunk c is dequantised
+        if (c + 1 < NCHUNK) {
+          tmem_ld_chunk(t_base + (c + 1) * EPI_CHUNK, v[(c + 1) & 1]);
+          issue_res(c + 1);
+        }
+        const int col0 = n_idx + h * EPI_COLS + c * EPI_CHUNK;
         if (EPI != VQ_EPI_DEBUG_MAINLOOP && col0 < p.N && row0 < p.M) {
-          uint8_t* stage = stage0 + buf * EPI_BUF_BYTES;
-          if (lane == 0) tma_store_wait_read<1>();  // the TMA store that last read this buffer has drained
-          __syncwarp();
+          const uint32_t b = n_done % EPI_NBUF;
+          uint8_t* stage = stage0 + b * EPI_BUF_BYTES;
+          if (EPI == VQ_EPI_GATE_RESIDUAL) {
+            mbar_wait(&my_res_bar[b], (n_done / EPI_NBUF) & 1);   // residual chunk has landed
+          } else {
+            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();   // the store that last read this buffer has drained
+            __syncwarp();
+          }
           epilogue_chunk<EPI>(p, v[c & 1], row, col0, zx, rs, dx, row_ok, stage, lane, ctile + c * EPI_CHUNK);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (EPI == VQ_EPI_GATE_ACCUM) tma_reduce_add_2d(&tmap_out, stage, col0, row0);
-            else tma_store_2d(&tmap_out, stage, col0, row0);
+            tma_store_2d(&tmap_out, stage, col0, row0);
             tma_store_commit();
           }
-          buf ^= 1;
+          ++n_done;
         }
         if (c + 1 < NCHUNK) {
           tmem_ld_wait();
@@ -319,7 +356,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       // publish the next tile's column records; the barrier also orders this tile's reads of the other buffer
       if (et < BN) colbuf[(acc ^ 1) * BN + et] = next_col;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
     }
     if (lane == 0) tma_store_wait<0>();
     __syncwarp();
@@ -364,16 +401,17 @@ int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
 }
 
-// rows x cols fp16 matrix (row pitch ld elements); box = 32 rows x 32 cols (64 B), 64B swizzle: the epilogue staging tile.
+// rows x cols fp16 matrix (row pitch ld elements); box = 32 rows x EPI_CHUNK cols, matching swizzle: the epilogue staging tile.
 int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return VQ_ERR_DRIVER;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(EPI_CHUNK), 32u};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, EPI_CHUNK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
 }
@@ -389,8 +427,8 @@ int num_sms() {
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& args,
-                       int grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                       const GemmArgs& args, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -398,7 +436,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     if (e != cudaSuccess) return VQ_ERR_LAUNCH;
     attr_set = true;
   }
-  vq_gemm_w8a8_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, args);
+  vq_gemm_w8a8_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, args);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
@@ -413,7 +451,6 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0 || !out) return VQ_ERR_ARG;
   if (epi == VQ_EPI_GATE_RESIDUAL && (!res || !gate || rows_per_gate <= 0 || (ldr % 8) != 0)) return VQ_ERR_ARG;
   if (epi < 0 || epi > VQ_EPI_DEBUG_MAINLOOP) return VQ_ERR_ARG;
-  if (epi == VQ_EPI_GATE_RESIDUAL && res == out && ldr == ldo) epi = VQ_EPI_GATE_ACCUM;  // in-place residual update
   CUtensorMap ta, tb, to;
   int rc = make_u8_kmajor_tmap(&ta, a_codes, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM);
   if (rc != VQ_OK) return rc;
@@ -421,6 +458,11 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   if (rc != VQ_OK) return rc;
   rc = make_f16_out_tmap(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo);
   if (rc != VQ_OK) return rc;
+  CUtensorMap tr = to;
+  if (epi == VQ_EPI_GATE_RESIDUAL) {
+    rc = make_f16_out_tmap(&tr, res, (uint64_t)M, (uint64_t)N, (uint64_t)ldr);
+    if (rc != VQ_OK) return rc;
+  }
   GemmArgs args;
   args.M = M; args.N = N; args.K = K;
   args.a_delta = static_cast<const __half*>(a_delta);
@@ -439,10 +481,9 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   const int grid = tiles < num_sms() ? tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, args, grid, st);
-    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, args, grid, st);
-    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, args, grid, st);
-    case VQ_EPI_GATE_ACCUM: return launch_gemm<VQ_EPI_GATE_ACCUM>(ta, tb, to, args, grid, st);
-    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, args, grid, st);
+    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, tr, args, grid, st);
+    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, tr, args, grid, st);
+    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, tr, args, grid, st);
+    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, tr, args, grid, st);
   }
 }

@@ -237,6 +237,99 @@ __device__ __forceinline__ int quant_store_row(const RowRegs<MAXC>& r, uint8_t* 
   return sum;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Branch-free row mapping for K = U * 128: the row is U x 32 units of 8 bytes (4 halves); lane l owns units
+// l, l+32, ... — every lane does identical, fully unrolled work (K = 1152 -> U = 9, K = 4608 -> U = 36).
+// ---------------------------------------------------------------------------------------------------------------
+template <int U>
+struct UnitRegs {
+  uint2 u[U];
+};
+
+template <int U>
+__device__ __forceinline__ void uload_row(UnitRegs<U>& r, const __half* row, int lane) {
+#pragma unroll
+  for (int i = 0; i < U; ++i) r.u[i] = __ldg(reinterpret_cast<const uint2*>(row) + lane + 32 * i);
+}
+
+template <int U>
+__device__ __forceinline__ void uapply_smooth(UnitRegs<U>& r, const __half* smooth, int lane) {
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const uint2 sv = __ldg(reinterpret_cast<const uint2*>(smooth) + lane + 32 * i);
+    __half2* x = reinterpret_cast<__half2*>(&r.u[i]);
+    const __half2* sm = reinterpret_cast<const __half2*>(&sv);
+    x[0] = div_pair(x[0], sm[0]);
+    x[1] = div_pair(x[1], sm[1]);
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void uapply_ln_modulate(UnitRegs<U>& r, const __half* shift, const __half* scale, int K,
+                                                   int lane) {
+  float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const __half2* x = reinterpret_cast<const __half2*>(&r.u[i]);
+    sum2 = __fadd2_rn(sum2, __half22float2(x[0]));
+    sum2 = __fadd2_rn(sum2, __half22float2(x[1]));
+  }
+  const float mean = warp_sum(sum2.x + sum2.y) / static_cast<float>(K);
+  const float2 nmean2 = make_float2(-mean, -mean);
+  float2 sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const __half2* x = reinterpret_cast<const __half2*>(&r.u[i]);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float2 d = __fadd2_rn(__half22float2(x[e]), nmean2);
+      sq2 = __ffma2_rn(d, d, sq2);
+    }
+  }
+  const float var = warp_sum(sq2.x + sq2.y) / static_cast<float>(K);
+  const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  const float2 rstd2 = make_float2(rstd, rstd);
+  const __half2 one = __float2half2_rn(1.0f);
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const uint2 shv = __ldg(reinterpret_cast<const uint2*>(shift) + lane + 32 * i);
+    const uint2 scv = __ldg(reinterpret_cast<const uint2*>(scale) + lane + 32 * i);
+    __half2* x = reinterpret_cast<__half2*>(&r.u[i]);
+    const __half2* sh = reinterpret_cast<const __half2*>(&shv);
+    const __half2* sc = reinterpret_cast<const __half2*>(&scv);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float2 ln = __fmul2_rn(__fadd2_rn(__half22float2(x[e]), nmean2), rstd2);
+      const __half2 lnh = __floats2half2_rn(ln.x, ln.y);
+      x[e] = __hadd2_rn(__hmul2_rn(lnh, __hadd2_rn(one, sc[e])), sh[e]);   // three separate fp16 roundings
+    }
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void urow_minmax(const UnitRegs<U>& r, __half2& mn2, __half2& mx2) {
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const __half2* x = reinterpret_cast<const __half2*>(&r.u[i]);
+    mn2 = __hmin2(mn2, __hmin2(x[0], x[1]));
+    mx2 = __hmax2(mx2, __hmax2(x[0], x[1]));
+  }
+}
+
+template <int U>
+__device__ __forceinline__ int uquant_store_row(const UnitRegs<U>& r, uint8_t* codes_row, int lane,
+                                                const QuantConsts& qc) {
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const __half2* x = reinterpret_cast<const __half2*>(&r.u[i]);
+    const uint32_t w = __byte_perm(quant_pair(x[0], qc), quant_pair(x[1], qc), 0x6420);
+    sum = __dp4a(w, 0x01010101u, sum);
+    reinterpret_cast<uint32_t*>(codes_row)[lane + 32 * i] = w;
+  }
+  return static_cast<int>(sum);
+}
+
 struct ActQuantArgs {
   const __half* x;
   int G, rows, K;
@@ -307,13 +400,66 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
   }
 }
 
+template <int U, bool LN>
+__global__ void __launch_bounds__(256) vq_act_quant_unit_kernel(const ActQuantArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a.rows) return;
+  UnitRegs<U> regs;
+  __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
+  for (int g = 0; g < a.G; ++g) {
+    uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
+    if (LN) {
+      uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K,
+                            lane);
+      if (a.smooth) uapply_smooth<U>(regs, a.smooth, lane);
+      if (a.y_out) {
+        uint2* yrow = reinterpret_cast<uint2*>(a.y_out + (static_cast<size_t>(g) * a.rows + r) * a.K);
+#pragma unroll
+        for (int i = 0; i < U; ++i) yrow[lane + 32 * i] = regs.u[i];
+      }
+    } else if (a.smooth) {
+      uapply_smooth<U>(regs, a.smooth, lane);
+    }
+    urow_minmax<U>(regs, mn2, mx2);
+  }
+  const float mn = warp_min(fminf(__low2float(mn2), __high2float(mn2)));
+  const float mx = warp_max(fmaxf(__low2float(mx2), __high2float(mx2)));
+  const RowStats st = make_stats(mn, mx, a.qmax);
+  const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
+  if (lane == 0) {
+    a.delta[r] = __float2half_rn(st.delta);
+    a.zp[r] = __float2half_rn(st.zp);
+    if (st.degenerate && a.status) atomicOr(a.status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
+  }
+  for (int g = 0; g < a.G; ++g) {
+    if (a.G > 1) {  // G == 1: the transformed row is still in registers
+      uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
+      if (LN) {
+        uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K,
+                              a.K, lane);
+        if (a.smooth) uapply_smooth<U>(regs, a.smooth, lane);
+      } else if (a.smooth) {
+        uapply_smooth<U>(regs, a.smooth, lane);
+      }
+    }
+    const size_t orow = static_cast<size_t>(g) * a.rows + r;
+    int s = uquant_store_row<U>(regs, a.codes + orow * a.K, lane, qc);
+    s = warp_sum_i(s);
+    if (lane == 0) a.rowsum[orow] = s;
+  }
+}
+
 template <bool LN>
 static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
   const int nchunk = a.K >> 3;
   const int maxc = (nchunk + 31) / 32;
   const int warps = 8;
   dim3 grid((a.rows + warps - 1) / warps), block(warps * 32);
-  if (maxc <= 5) vq_act_quant_kernel<5, LN><<<grid, block, 0, st>>>(a);
+  // K = 1152 is 4.5 sixteen-byte chunks per lane (divergent in the chunk mapping) but exactly 9 eight-byte units;
+  // K = 4608 is 18 full chunk rounds, where the chunk mapping is already branch-free and lighter on registers.
+  if (a.K == 9 * 128) vq_act_quant_unit_kernel<9, LN><<<grid, block, 0, st>>>(a);
+  else if (maxc <= 5) vq_act_quant_kernel<5, LN><<<grid, block, 0, st>>>(a);
   else if (maxc <= 9) vq_act_quant_kernel<9, LN><<<grid, block, 0, st>>>(a);
   else if (maxc <= 18) vq_act_quant_kernel<18, LN><<<grid, block, 0, st>>>(a);
   else if (maxc <= 36) vq_act_quant_kernel<36, LN><<<grid, block, 0, st>>>(a);

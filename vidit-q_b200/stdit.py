@@ -392,7 +392,7 @@ class FusedBlocks:
                 qt, kt, vt = (q5[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
                 o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)
                 o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
-            a = blk.attn_temp.proj.quantize_input(o.view(B, S * T, C))   # per-token statistics: row order irrelevant
+            a = blk.attn_temp.proj.quantize_input(o.view(B * S, T, C))   # per-token statistics: row order irrelevant
             ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                           rows_per_gate=N, out=xr)
             # ---- cross attention
