@@ -13,7 +13,8 @@
 //   warp 0      : TMA producer   (one elected lane; A box 128 rows x 128 B, B box 192 rows x 128 B, SWIZZLE_128B)
 //   warp 1      : MMA issuer     (one elected lane; 4 x tcgen05.mma 128x192x32 per 128-byte K block)
 //   warp 2      : TMEM allocator (512 columns = 2 accumulator stages x 256)
-//   warps 4..19 : epilogue       (tcgen05.ld 32x32b; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column group)
+//   warp 3      : stages each tile's per-column dequant records in smem one tile ahead (mbarrier hand-off)
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half)
 // Pipelines: smem full/empty ring (4 stages x 40 KB) and TMEM full/empty (2 stages), all mbarrier based.
 // Epilogue output path: registers -> per-warp 32x32 fp16 staging tile in smem (64B swizzle, bank-conflict free)
 // -> TMA store (cp.async.bulk.tensor, coalesced, clipped at the M/N edges by the tensor map). For the gated-residual
@@ -40,20 +41,13 @@ constexpr int B_STAGE_BYTES = BN * BK;  // 24 KB
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;  // TMEM column stride between accumulator stages
 constexpr int TMEM_COLS = 512;
-#ifndef VQ_EPI_WARPS
-#define VQ_EPI_WARPS 16
-#endif
-constexpr int NUM_EPI_WARPS = VQ_EPI_WARPS;           // 8: two per scheduler, 32-column chunks; 16: four, 16-column chunks
-static_assert(NUM_EPI_WARPS == 8 || NUM_EPI_WARPS == 16, "8 or 16 epilogue warps");
+constexpr int NUM_EPI_WARPS = 8;                      // warp%4 = TMEM lane quarter, (warp-4)/4 = column half
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
-constexpr int EPI_COL_GROUPS = NUM_EPI_WARPS / 4;     // column groups (each warp: one TMEM lane quarter x one group)
-constexpr int EPI_COLS = BN / EPI_COL_GROUPS;         // columns per warp per tile (96 | 48)
-constexpr int EPI_CHUNK = NUM_EPI_WARPS == 8 ? 32 : 16;   // output columns per epilogue step
+constexpr int EPI_COLS = BN / 2;                      // 96 output columns per epilogue warp per tile
+constexpr int EPI_CHUNK = 32;                         // columns per TMEM load / staging sub-tile (64 B of fp16 per row)
 constexpr int EPI_NCHUNK = EPI_COLS / EPI_CHUNK;      // 3
-constexpr int EPI_V4 = EPI_CHUNK / 8;                 // 16-byte pieces per staged row (4 | 2)
-constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one warp's staging tile: 32 rows x (64 | 32) B, 64B / 32B swizzle
-constexpr int EPI_NBUF = 3;                           // staging tiles per warp (residual load / math / store in flight)
-constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_NBUF * EPI_BUF_BYTES;
+constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one sub-tile: 32 rows x 64 B, SWIZZLE_64B
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_NCHUNK * EPI_BUF_BYTES;   // one 32 x 96 strip per warp
 constexpr int COLBUF_BYTES = 2 * BN * 16;                // per-tile {c1, zw, dw, bias} records, double-buffered
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
 
@@ -83,16 +77,14 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 
 constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (measures the TMA->MMA pipeline alone)
 
-// Dequantise 32 consecutive output columns of one row, apply the epilogue op and write the fp16 results into this
-// warp's staging tile (row-major 64 B rows, 16-byte chunk index XOR ((row >> 1) & 3) == CU_TENSOR_MAP_SWIZZLE_64B).
+// Dequantise 32 consecutive output columns of one row (thread = row): int32 zero-point correction, one fp32 FMA with
+// dx * dw and the bias, one rounding to fp16, optional GELU. Results stay in registers (16 packed half2).
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&v)[EPI_CHUNK], int row, int col0,
-                                               int32_t zx, int32_t rs, float dx, bool row_ok, uint8_t* stage,
-                                               int lane, const int4* colp) {
-  // colp: this chunk's column records in shared memory (warp-uniform address -> broadcast LDS.128)
-  uint32_t packed[EPI_CHUNK / 2];
+__device__ __forceinline__ void dequant_chunk(const uint32_t (&v)[32], int32_t zx, int32_t rs, float dx,
+                                              const int4* colp, uint32_t (&packed)[16]) {
+  // colp: this chunk's 32 column records in shared memory (warp-uniform address -> broadcast LDS.128)
 #pragma unroll
-  for (int j = 0; j < EPI_CHUNK; j += 2) {
+  for (int j = 0; j < 32; j += 2) {
     float f[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -108,20 +100,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
     }
     packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
   }
-  // staging tile: row-major (64 | 32)-byte rows; 16-byte piece index XOR-swizzled exactly like the TMA tensor map
-  // (SWIZZLE_64B: ^ ((row >> 1) & 3); SWIZZLE_32B: ^ ((row >> 2) & 1)) -> conflict-free 16-byte accesses
-  const uint32_t sw = EPI_V4 == 4 ? ((static_cast<uint32_t>(lane) >> 1) & 3u) : ((static_cast<uint32_t>(lane) >> 2) & 1u);
-  uint4* srow = reinterpret_cast<uint4*>(stage + lane * (EPI_CHUNK * 2));
+}
+
+// Write one chunk (32 columns of this thread's row) into its staging sub-tile: row-major 64-byte rows, 16-byte piece
+// index XOR ((row >> 1) & 3) == CU_TENSOR_MAP_SWIZZLE_64B (conflict-free). For the gated residual the sub-tile already
+// holds the residual (TMA load, same swizzle): x_new = res + gate * y with the reference's two fp16 roundings.
+template <int EPI>
+__device__ __forceinline__ void stage_chunk(const GemmArgs& p, uint32_t (&packed)[16], int row, bool row_ok, int col0,
+                                            uint8_t* sub, int lane) {
+  const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+  const uint32_t base = smem_u32(sub) + lane * (EPI_CHUNK * 2);
   if (EPI == VQ_EPI_GATE_RESIDUAL) {
-    // x_new = res + gate * y, each op rounded to fp16 like the reference's half tensors (stdit.py:109,118,123,127).
-    // The residual chunk already sits in the staging tile (TMA load, same swizzle); it is overwritten in place.
     const __half* gate_row = p.gate + static_cast<size_t>((row_ok ? row : 0) / p.rows_per_gate) * p.N;
 #pragma unroll
-    for (int g = 0; g < EPI_V4; ++g) {
+    for (int g = 0; g < 4; ++g) {
       const int n = col0 + g * 8;
       uint4 gv = make_uint4(0, 0, 0, 0);
       if (n < p.N) gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
-      const uint4 rv = srow[g ^ sw];
+      const int4 rv = lds_v4_addr(base + ((g ^ sw) << 4));
       const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
       const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
@@ -133,14 +129,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
     }
   }
 #pragma unroll
-  for (int g = 0; g < EPI_V4; ++g) {
-    srow[g ^ sw] = make_uint4(packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
-  }
-}
-
-__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[EPI_CHUNK]) {
-  if constexpr (EPI_CHUNK == 32) tmem_ld_32x32b_x32(taddr, reinterpret_cast<uint32_t(&)[32]>(v));
-  else tmem_ld_32x32b_x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
+  for (int g = 0; g < 4; ++g)
+    sts_v4_addr(base + ((g ^ sw) << 4), packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
 }
 
 template <int EPI>
@@ -154,14 +144,16 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* smem_epi = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-  int4* colbuf = reinterpret_cast<int4*>(smem_epi + EPI_STAGING_BYTES);
+  int4* colbuf = reinterpret_cast<int4*>(smem_epi + EPI_STAGING_BYTES);   // [2][BN] records
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGING_BYTES + COLBUF_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
-  uint64_t* res_bar = bars + 2 * STAGES + 2 * ACC_STAGES;   // [NUM_EPI_WARPS][EPI_NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NUM_EPI_WARPS * EPI_NBUF);
+  uint64_t* res_bar = bars + 2 * STAGES + 2 * ACC_STAGES;   // [NUM_EPI_WARPS] residual strip landed
+  uint64_t* colfull_bar = res_bar + NUM_EPI_WARPS;           // [2] column records of a tile are in colbuf[b]
+  uint64_t* colempty_bar = colfull_bar + 2;                  // [2] all epilogue warps are done with colbuf[b]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(colempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -186,7 +178,11 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
     }
-    for (int i = 0; i < NUM_EPI_WARPS * EPI_NBUF; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&colfull_bar[b], 1);
+      mbar_init(&colempty_bar[b], NUM_EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -246,23 +242,34 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int h = (warp - 4) >> 2;   // column group
-    const int et = threadIdx.x - 128;  // index within the epilogue warps
-    uint8_t* stage0 = smem_epi + (warp - 4) * EPI_NBUF * EPI_BUF_BYTES;
-    uint64_t* my_res_bar = res_bar + (warp - 4) * EPI_NBUF;
-    uint32_t n_issued = 0, n_done = 0;   // residual loads issued / chunks written (same order)
+  } else if (warp == 3) {
+    // ===================== column-record producer =====================
+    // stages each tile's 192 {c1, zw, dw, bias} records in shared memory one tile ahead of the epilogue warps
     const int4* colg = reinterpret_cast<const int4*>(p.col);
     const int nmax = p.N - 1;
     int local = 0;
-    // column records of the first tile -> colbuf[0]
-    if (blockIdx.x < num_tiles && et < BN) {
-      const int n = (blockIdx.x / num_m_tiles) * BN + et;
-      colbuf[et] = __ldg(colg + (n < nmax ? n : nmax));
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int b = local & 1;
+      mbar_wait(&colempty_bar[b], ((local >> 1) & 1) ^ 1);
+      const int n0 = (tile / num_m_tiles) * BN;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int n = n0 + lane + 32 * i;
+        colbuf[b * BN + lane + 32 * i] = __ldg(colg + (n < nmax ? n : nmax));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&colfull_bar[b]);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    // Per tile and warp: 32 rows x 96 columns. The strip is dequantised into registers chunk by chunk (TMEM loads
+    // software-pipelined), then staged and handed to the TMA with ONE proxy fence and three bulk stores per tile.
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int h = (warp - 4) >> 2;   // column half
+    uint8_t* stage0 = smem_epi + (warp - 4) * EPI_NCHUNK * EPI_BUF_BYTES;
+    uint64_t* my_res_bar = res_bar + (warp - 4);
+    uint32_t res_uses = 0;
+    int local = 0;
     // per-row dequant parameters {delta, zero point, row sum}, fetched one tile ahead
     struct RowP { float dx; int32_t zx, rs; };
     auto load_rowp = [&](int tile_) {
@@ -285,78 +292,67 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const RowP rp = rp_next;
-      const float dx = rp.dx;
-      const int32_t zx = rp.zx;
-      const int32_t rs = rp.rs;
       if (tile + static_cast<int>(gridDim.x) < num_tiles) rp_next = load_rowp(tile + gridDim.x);
-      // prefetch the next tile's column record (consumed after this tile's math)
-      const int next_tile = tile + gridDim.x;
-      int4 next_col = make_int4(0, 0, 0, 0);
-      if (next_tile < num_tiles && et < BN) {
-        const int n = (next_tile / num_m_tiles) * BN + et;
-        next_col = __ldg(colg + (n < nmax ? n : nmax));
+      const int cbase = n_idx + h * EPI_COLS;
+      // active sub-tiles of this warp: rows in range and first column in range (N is a multiple of 8)
+      int nact = 0;
+      if (EPI != VQ_EPI_DEBUG_MAINLOOP && row0 < p.M) {
+#pragma unroll
+        for (int c = 0; c < EPI_NCHUNK; ++c) nact += (cbase + c * EPI_CHUNK < p.N) ? 1 : 0;
       }
-      const int4* ctile = colbuf + acc * BN + h * EPI_COLS;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * EPI_COLS;
-      constexpr int NCHUNK = EPI_NCHUNK;
-      // residual tile of chunk c -> staging buffer (n_issued % 3); the store that last read that buffer is >= 2 back
-      auto issue_res = [&](int c) {
-        const int col0_ = n_idx + h * EPI_COLS + c * EPI_CHUNK;
-        if (EPI == VQ_EPI_GATE_RESIDUAL && col0_ < p.N && row0 < p.M) {
-          if (lane == 0) {
-            const uint32_t b = n_issued % EPI_NBUF;
-            tma_store_wait_read<1>();
-            mbar_arrive_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
-            tma_load_2d(stage0 + b * EPI_BUF_BYTES, &tmap_res, &my_res_bar[b], col0_, row0);
-          }
-          ++n_issued;
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(t_base, v[0]);
+      // the previous tile's TMA stores have finished reading the staging strip (they were issued a whole tile ago)
+      if (lane == 0 && nact > 0) {
+        tma_store_wait_read<0>();
+        if (EPI == VQ_EPI_GATE_RESIDUAL) {   // residual strip -> staging (same swizzle), landed on my_res_bar
+          mbar_arrive_expect_tx(my_res_bar, nact * EPI_BUF_BYTES);
+          for (int c = 0; c < nact; ++c)
+            tma_load_2d(stage0 + c * EPI_BUF_BYTES, &tmap_res, my_res_bar, cbase + c * EPI_CHUNK, row0);
         }
-      };
-      issue_res(0);
-      uint32_t v[2][EPI_CHUNK];
-      tmem_ld_chunk(t_base, v[0]);
+      }
+      mbar_wait(&colfull_bar[acc], acc_phase);
+      const int4* ctile = colbuf + acc * BN + h * EPI_COLS;
+      uint32_t packed[EPI_NCHUNK][16];
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        // software pipeline: the TMEM load (and residual TMA load) of chunk c+1 fly while chunk c is dequantised
-        if (c + 1 < NCHUNK) {
-          tmem_ld_chunk(t_base + (c + 1) * EPI_CHUNK, v[(c + 1) & 1]);
-          issue_res(c + 1);
-        }
-        const int col0 = n_idx + h * EPI_COLS + c * EPI_CHUNK;
-        if (EPI != VQ_EPI_DEBUG_MAINLOOP && col0 < p.N && row0 < p.M) {
-          const uint32_t b = n_done % EPI_NBUF;
-          uint8_t* stage = stage0 + b * EPI_BUF_BYTES;
-          if (EPI == VQ_EPI_GATE_RESIDUAL) {
-            mbar_wait(&my_res_bar[b], (n_done / EPI_NBUF) & 1);   // residual chunk has landed
-          } else {
-            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();   // the store that last read this buffer has drained
-            __syncwarp();
-          }
-          epilogue_chunk<EPI>(p, v[c & 1], row, col0, zx, rs, dx, row_ok, stage, lane, ctile + c * EPI_CHUNK);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmap_out, stage, col0, row0);
-            tma_store_commit();
-          }
-          ++n_done;
-        }
-        if (c + 1 < NCHUNK) {
-          tmem_ld_wait();
+      for (int c = 0; c < EPI_NCHUNK; ++c) {
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is dequantised
+        if (c + 1 < EPI_NCHUNK) {
+          tmem_ld_32x32b_x32(t_base + (c + 1) * EPI_CHUNK, v[(c + 1) & 1]);
         } else {
-          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          // the last TMEM load of this accumulator stage has completed: hand the stage back to the MMA warp now
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
+        if (EPI != VQ_EPI_DEBUG_MAINLOOP) dequant_chunk<EPI>(v[c & 1], rp.zx, rp.rs, rp.dx, ctile + c * EPI_CHUNK, packed[c]);
+        if (c + 1 < EPI_NCHUNK) tmem_ld_wait();
       }
-      // publish the next tile's column records; the barrier also orders this tile's reads of the other buffer
-      if (et < BN) colbuf[(acc ^ 1) * BN + et] = next_col;
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+      // the column records of this tile are consumed: release them before touching shared staging
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&colempty_bar[acc]);
+      if (nact > 0) {
+        if (EPI == VQ_EPI_GATE_RESIDUAL) {
+          mbar_wait(my_res_bar, res_uses & 1);
+          ++res_uses;
+        } else {
+          __syncwarp();   // lane 0's wait_read above precedes every lane's staging writes
+        }
+#pragma unroll
+        for (int c = 0; c < EPI_NCHUNK; ++c)
+          if (c < nact) stage_chunk<EPI>(p, packed[c], row, row_ok, cbase + c * EPI_CHUNK, stage0 + c * EPI_BUF_BYTES, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          for (int c = 0; c < nact; ++c) tma_store_2d(&tmap_out, stage0 + c * EPI_BUF_BYTES, cbase + c * EPI_CHUNK, row0);
+          tma_store_commit();
+        }
+      }
     }
     if (lane == 0) tma_store_wait<0>();
     __syncwarp();
@@ -407,10 +403,10 @@ int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   if (!enc) return VQ_ERR_DRIVER;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(EPI_CHUNK), 32u};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(EPI_CHUNK), 32u};   // 32 columns = 64 B
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, EPI_CHUNK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;

@@ -34,6 +34,17 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// row minimum and maximum from per-lane packed partials: one half2 (min, -max) shuffle chain instead of two fp32 ones
+__device__ __forceinline__ void warp_minmax(__half2 mn2, __half2 mx2, float& mn, float& mx) {
+  __half2 v = __halves2half2(__hmin(__low2half(mn2), __high2half(mn2)), __hneg(__hmax(__low2half(mx2), __high2half(mx2))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint32_t u = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&v), o);
+    v = __hmin2(v, *reinterpret_cast<__half2*>(&u));
+  }
+  mn = __low2float(v);
+  mx = -__high2float(v);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -56,6 +67,20 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 //     [1024, 2048)), adding (zp - 512) gives 1024 + rint + zp exactly, clamping to [1024, 1024 + qmax] leaves the code
 //     in the low byte of each fp16 lane.  No F2I, two elements per instruction (FFMA2 / HADD2 / HMNMX2).
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// fp16( a / b ) held in fp32, for fp16-representable a, b (or b a small integer): Newton-corrected reciprocal multiply;
+// exact by the midpoint-distance argument above.
+__device__ __forceinline__ float h_div(float a, float b) {
+  const float r = rcp_approx(b);
+  const float q0 = a * r;
+  const float e = fmaf(-q0, b, a);
+  return h_round(fmaf(e, r, q0));
+}
+
 struct QuantConsts {
   float2 delta2, rdelta2;   // delta and ~1/delta broadcast to both lanes
   __half2 zpm;              // zp - 512
@@ -64,7 +89,7 @@ struct QuantConsts {
 
 __device__ __forceinline__ QuantConsts make_consts(float delta, float zp, float qmax) {
   QuantConsts c;
-  const float r = __frcp_rn(delta);
+  const float r = rcp_approx(delta);
   c.delta2 = make_float2(delta, delta);
   c.rdelta2 = make_float2(r, r);
   c.zpm = __float2half2_rn(zp - 512.0f);
@@ -100,7 +125,7 @@ __device__ __forceinline__ uint2 quant_chunk(const uint4& v, const QuantConsts& 
 // h(x / s) for fp16 x, s: the same exact Newton-corrected reciprocal
 __device__ __forceinline__ __half2 div_pair(__half2 x, __half2 s) {
   const float2 xf = __half22float2(x), sf = __half22float2(s);
-  const float2 r = make_float2(__frcp_rn(sf.x), __frcp_rn(sf.y));
+  const float2 r = make_float2(rcp_approx(sf.x), rcp_approx(sf.y));
   const float2 q0 = __fmul2_rn(xf, r);
   const float2 e = __ffma2_rn(make_float2(-q0.x, -q0.y), sf, xf);
   const float2 q1 = __ffma2_rn(e, r, q0);
@@ -119,9 +144,9 @@ __device__ __forceinline__ RowStats make_stats(float mn, float mx, float qmax) {
   mx = fmaxf(mx, 0.0f);
   RowStats s;
   float range = h_round(mx - mn);
-  s.delta = h_round(__fdiv_rn(range, qmax));
+  s.delta = h_div(range, qmax);
   s.degenerate = s.delta < 1e-6f;
-  s.zp = rintf(h_round(__fdiv_rn(-mn, s.delta)));
+  s.zp = rintf(h_div(-mn, s.delta));
   return s;
 }
 
@@ -186,7 +211,7 @@ __device__ __forceinline__ void apply_ln_modulate(RowRegs<MAXC>& r, const __half
     }
   }
   const float var = warp_sum(sq2.x + sq2.y) / static_cast<float>(K);
-  const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  const float rstd = rsqrtf(var + 1e-6f);
   const float2 rstd2 = make_float2(rstd, rstd);
   const __half2 one = __float2half2_rn(1.0f);
 #pragma unroll
@@ -287,7 +312,7 @@ __device__ __forceinline__ void uapply_ln_modulate(UnitRegs<U>& r, const __half*
     }
   }
   const float var = warp_sum(sq2.x + sq2.y) / static_cast<float>(K);
-  const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  const float rstd = rsqrtf(var + 1e-6f);
   const float2 rstd2 = make_float2(rstd, rstd);
   const __half2 one = __float2half2_rn(1.0f);
 #pragma unroll
@@ -373,8 +398,8 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
     }
     row_minmax<MAXC>(regs, nchunk, lane, mn2, mx2);
   }
-  const float mn = warp_min(fminf(__low2float(mn2), __high2float(mn2)));
-  const float mx = warp_max(fmaxf(__low2float(mx2), __high2float(mx2)));
+  float mn, mx;
+  warp_minmax(mn2, mx2, mn, mx);
   const RowStats st = make_stats(mn, mx, a.qmax);
   const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
   if (lane == 0) {
@@ -423,8 +448,8 @@ __global__ void __launch_bounds__(256) vq_act_quant_unit_kernel(const ActQuantAr
     }
     urow_minmax<U>(regs, mn2, mx2);
   }
-  const float mn = warp_min(fminf(__low2float(mn2), __high2float(mn2)));
-  const float mx = warp_max(fmaxf(__low2float(mx2), __high2float(mx2)));
+  float mn, mx;
+  warp_minmax(mn2, mx2, mn, mx);
   const RowStats st = make_stats(mn, mx, a.qmax);
   const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
   if (lane == 0) {
