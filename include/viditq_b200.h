@@ -66,6 +66,12 @@ int vq_prep_weight(const void* w, const void* delta, const void* zp, const void*
 int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, int64_t ld, const void* smooth,
                  int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream);
 
+/* (a1) on a head-major attention output x fp16 [G * rows / S, H, S, head_dim] (what fused attention kernels emit):
+ * same statistics and codes as vq_act_quant on the token-major view "(n H S D) -> (n S) (H D)", without the copy the
+ * reference pays (blocks.py:189-191 transpose + reshape). head_dim = 72, H * head_dim = 1152.                      */
+int vq_act_quant_heads(const void* x, int G, int rows, int H, int S, int head_dim, int n_bits, uint8_t* codes,
+                       void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream);
+
 /* LayerNorm(eps=1e-6, no affine) + t2i_modulate (blocks.py:51: x*(1+scale)+shift) + (a1), one pass.
  * x: fp16 [G*rows, K]; shift, scale: fp16 [G, K] (per sample); smooth: fp16 [K] or NULL (divides the modulated
  * tensor, quant_layer.py:140); y_out (optional, may be NULL): fp16 tensor the quantiser saw.                        */

@@ -263,3 +263,18 @@ def test_cross_attention_matches_fp32_reference(ops, B, N, lens):
     ref = torch.cat(refs, 0)
     err = (out.float() - ref).abs().max().item()
     assert err <= 4e-3 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("G,T,S", [(1, 4, 64), (2, 3, 40)])
+def test_act_quant_heads_equals_token_major(ops, G, T, S):
+    """Head-major input path (attention output [G*T, H, S, 72]) == quantising the transposed token-major copy."""
+    H, D = 16, 72
+    torch.manual_seed(2)
+    o = (torch.randn(G * T, H, S, D, device="cuda") * 1.3).half()
+    tok = o.transpose(1, 2).reshape(G, T * S, H * D).contiguous()
+    a = ops.act_quant_heads(o, G, T * S, S)
+    b = ops.act_quant(tok)
+    assert torch.equal(a.codes, b.codes) and torch.equal(a.delta, b.delta)
+    assert torch.equal(a.zp, b.zp) and torch.equal(a.rowsum, b.rowsum)
+    oa = O.dynamic_act_quant(tok.cpu().numpy())
+    np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(G, T * S, H * D), oa["codes"])

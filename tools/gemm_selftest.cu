@@ -158,18 +158,22 @@ static int run_case(int M, int N, int K, int epi, int period, bool timeit, bool 
     double us = ms * 1e3 / iters;
     double tops = 2.0 * M * N * (double)K / (us * 1e-6) / 1e12;
     printf("   time %.2f us  -> %.1f TOPS (warm L2, back-to-back)\n", us, tops);
-    // internal debug epilogue 3: accumulators discarded -> TMA->MMA pipeline alone
-    for (int i = 0; i < 3; ++i)
-      vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, 3, dres, N, dgate, rpg, dout, N, 0);
-    CK(cudaDeviceSynchronize());
-    CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i)
-      vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, 3, dres, N, dgate, rpg, dout, N, 0);
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    us = ms * 1e3 / iters;
-    printf("   mainloop-only %.2f us -> %.1f TOPS\n", us, 2.0 * M * N * (double)K / (us * 1e-6) / 1e12);
+    // internal debug epilogues: 3 = mainloop only, 5 = + TMEM loads, 6 = + dequant math, 7 = loads + staging + TMA stores
+    const int dbg[4] = {3, 5, 6, 7};
+    const char* dname[4] = {"mainloop-only", "+tmem loads", "+loads+math", "loads+stores"};
+    for (int di = 0; di < 4; ++di) {
+      for (int i = 0; i < 3; ++i)
+        vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, dbg[di], dres, N, dgate, rpg, dout, N, 0);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < iters; ++i)
+        vq_gemm_w8a8(da, dad, daz, dars, period, dw, dcol, M, N, K, dbg[di], dres, N, dgate, rpg, dout, N, 0);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      us = ms * 1e3 / iters;
+      printf("   %-14s %.2f us -> %.1f TOPS\n", dname[di], us, 2.0 * M * N * (double)K / (us * 1e-6) / 1e12);
+    }
   }
   cudaFree(da); cudaFree(dw); cudaFree(dad); cudaFree(daz); cudaFree(dars); cudaFree(dcol);
   cudaFree(dres); cudaFree(dgate); cudaFree(dout); cudaFree(dref);

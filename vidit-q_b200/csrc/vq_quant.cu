@@ -277,6 +277,18 @@ __device__ __forceinline__ void uload_row(UnitRegs<U>& r, const __half* row, int
   for (int i = 0; i < U; ++i) r.u[i] = __ldg(reinterpret_cast<const uint2*>(row) + lane + 32 * i);
 }
 
+// Token row gathered from a head-major attention output [n, H, S, 72]: unit u (4 halves) of token (b, s) belongs to
+// head u / 18 and sits at ((b * H + head) * S + s) * 72 + (u % 18) * 4. `tok0` points at (b, head 0, s, 0).
+template <int U>
+__device__ __forceinline__ void uload_row_heads(UnitRegs<U>& r, const __half* tok0, int S, int lane) {
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const int u = lane + 32 * i;
+    const int head = u / 18, w = u - head * 18;
+    r.u[i] = __ldg(reinterpret_cast<const uint2*>(tok0 + static_cast<size_t>(head) * S * 72) + w);
+  }
+}
+
 template <int U>
 __device__ __forceinline__ void uapply_smooth(UnitRegs<U>& r, const __half* smooth, int lane) {
 #pragma unroll
@@ -363,6 +375,7 @@ struct ActQuantArgs {
   const __half* shift;   // [G,K] (LN mode)
   const __half* scale;   // [G,K] (LN mode)
   __half* y_out;         // optional [G*rows, K] transformed input (LN mode)
+  int head_S;            // > 0: x is head-major [G*rows / head_S, H, head_S, 72] (attention output), H = K / 72
   float qmax;
   uint8_t* codes;
   __half* delta;
@@ -433,7 +446,13 @@ __global__ void __launch_bounds__(256) vq_act_quant_unit_kernel(const ActQuantAr
   UnitRegs<U> regs;
   __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
   for (int g = 0; g < a.G; ++g) {
-    uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
+    if (a.head_S > 0) {   // token r of sample g = (image b = r / S, position s = r % S) of a [*, H, S, 72] tensor
+      const int bb = r / a.head_S, ss = r - bb * a.head_S;
+      uload_row_heads<U>(regs, a.x + g * a.group_stride + (static_cast<size_t>(bb) * (a.K / 72) * a.head_S + ss) * 72,
+                         a.head_S, lane);
+    } else {
+      uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
+    }
     if (LN) {
       uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K,
                             lane);
@@ -459,7 +478,13 @@ __global__ void __launch_bounds__(256) vq_act_quant_unit_kernel(const ActQuantAr
   }
   for (int g = 0; g < a.G; ++g) {
     if (a.G > 1) {  // G == 1: the transformed row is still in registers
-      uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
+      if (a.head_S > 0) {
+        const int bb = r / a.head_S, ss = r - bb * a.head_S;
+        uload_row_heads<U>(regs, a.x + g * a.group_stride + (static_cast<size_t>(bb) * (a.K / 72) * a.head_S + ss) * 72,
+                           a.head_S, lane);
+      } else {
+        uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
+      }
       if (LN) {
         uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K,
                               a.K, lane);
@@ -556,6 +581,26 @@ extern "C" int vq_act_quant(const void* x, int G, int rows, int K, int64_t group
   a.G = G; a.rows = rows; a.K = K;
   a.group_stride = group_stride; a.ld = ld;
   a.smooth = static_cast<const __half*>(smooth);
+  a.qmax = static_cast<float>((1 << n_bits) - 1);
+  a.codes = codes;
+  a.delta = static_cast<__half*>(delta);
+  a.zp = static_cast<__half*>(zp);
+  a.rowsum = rowsum;
+  a.status = status;
+  return launch_act_quant<false>(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vq_act_quant_heads(const void* x, int G, int rows, int H, int S, int head_dim, int n_bits,
+                                  uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status,
+                                  void* stream) {
+  using namespace vq;
+  if (!x || !codes || !delta || !zp || !rowsum || G <= 0 || rows <= 0 || S <= 0 || (rows % S) != 0) return VQ_ERR_ARG;
+  if (head_dim != 72 || H * head_dim != 9 * 128 || n_bits < 2 || n_bits > 8) return VQ_ERR_UNSUPPORTED;
+  ActQuantArgs a{};
+  a.x = static_cast<const __half*>(x);
+  a.G = G; a.rows = rows; a.K = H * head_dim;
+  a.group_stride = static_cast<long long>(rows) * a.K; a.ld = a.K;
+  a.head_S = S;
   a.qmax = static_cast<float>((1 << n_bits) - 1);
   a.codes = codes;
   a.delta = static_cast<__half*>(delta);

@@ -118,6 +118,21 @@ def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None) -> ActCo
     return a
 
 
+def act_quant_heads(x, G, rows, S, n_bits=8, out: Optional[ActCodes] = None) -> ActCodes:
+    """x: fp16 head-major attention output [G * rows / S, H, S, 72] (contiguous). Quantises the token-major view
+    [G, rows, H*72] without materialising it."""
+    _need_cuda_f16(x, "x")
+    n, H, S_, D = x.shape
+    if S_ != S or n * S != G * rows:
+        raise _lib.VqError(f"act_quant_heads: shape {tuple(x.shape)} inconsistent with G={G} rows={rows} S={S}")
+    a = out if out is not None else _alloc_act(G, rows, H * D, x.device)
+    rc = _lib.lib().vq_act_quant_heads(_ptr(x), G, rows, H, S, D, n_bits, _ptr(a.codes), _ptr(a.delta), _ptr(a.zp),
+                                       _ptr(a.rowsum), _ptr(status_word(x.device)), _stream())
+    _lib.check(rc, "vq_act_quant_heads")
+    _count()
+    return a
+
+
 def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional[ActCodes] = None, smooth=None):
     """x: fp16 [G, rows, K]; shift/scale: fp16 [G, K]; smooth: fp16 [K] or None. Returns (ActCodes, y or None)."""
     _need_cuda_f16(x, "x")

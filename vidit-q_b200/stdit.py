@@ -376,9 +376,13 @@ class FusedBlocks:
             # ---- spatial attention: LN + modulate + quantise once, one q|k|v GEMM
             qkv = self._qkv_project(blk.attn, (i, "s"), x, ln=(shift_msa, scale_msa)).view(B * T, S, 3, H, D)
             o = F.scaled_dot_product_attention(qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2),
-                                               qkv[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
-            o = o.transpose(1, 2).reshape(B, N, C)
-            a = blk.attn.proj.quantize_input(o.view(B * T, S, C))
+                                               qkv[:, :, 2].transpose(1, 2), scale=blk.attn.scale)   # [B*T, H, S, D]
+            pj = blk.attn.proj
+            if o.is_contiguous() and D == 72 and C == 1152 and not pj.smooth_quant:
+                # quantise straight from the head-major layout the attention kernel emits (no transpose copy)
+                a = ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits)
+            else:
+                a = pj.quantize_input(o.transpose(1, 2).reshape(B * T, S, C))
             xr = x.view(M, C)   # residual stream, updated in place: out aliases res -> TMA reduce-add epilogue
             ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                           rows_per_gate=N, out=xr)
