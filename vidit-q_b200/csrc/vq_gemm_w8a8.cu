@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vq_ptx.cuh"
 #include "vq_internal.h"
@@ -65,6 +66,7 @@ struct GemmArgs {
   int ldr;
   const __half* gate;       // [M / rows_per_gate, N]
   int rows_per_gate;
+  uint64_t store_policy;    // L2 cache policy of the output stores (kEvictFirst unless VQ_STORE_POLICY=normal)
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -208,8 +210,9 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx);
-          tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx);
+          // operand tiles are re-read by other CTAs (A by every n-tile, B by every m-tile): keep them in L2
+          tma_load_2d_hint(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx, kEvictLast);
+          tma_load_2d_hint(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
@@ -315,7 +318,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (EPI == VQ_EPI_GATE_RESIDUAL) {   // residual strip -> staging (same swizzle), landed on my_res_bar
           mbar_arrive_expect_tx(my_res_bar, nact * EPI_BUF_BYTES);
           for (int c = 0; c < nact; ++c)
-            tma_load_2d(stage0 + c * EPI_BUF_BYTES, &tmap_res, my_res_bar, cbase + c * EPI_CHUNK, row0);
+            tma_load_2d_hint(stage0 + c * EPI_BUF_BYTES, &tmap_res, my_res_bar, cbase + c * EPI_CHUNK, row0, kEvictFirst);
         }
       }
       mbar_wait(&colfull_bar[acc], acc_phase);
@@ -365,7 +368,9 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          for (int c = 0; c < nact; ++c) tma_store_2d(&tmap_out, stage0 + c * EPI_BUF_BYTES, cbase + c * EPI_CHUNK, row0);
+          // streaming output: evict-first so it does not push the operand tiles out of L2
+          for (int c = 0; c < nact; ++c)
+            tma_store_2d_hint(&tmap_out, stage0 + c * EPI_BUF_BYTES, cbase + c * EPI_CHUNK, row0, p.store_policy);
           tma_store_commit();
         }
       }
@@ -489,6 +494,11 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   args.ldr = ldr;
   args.gate = static_cast<const __half*>(gate);
   args.rows_per_gate = rows_per_gate;
+  static const uint64_t store_policy = [] {
+    const char* e = getenv("VQ_STORE_POLICY");   // tuning knob: "normal" keeps outputs L2-resident for the consumer
+    return (e && e[0] == 'n') ? kEvictNormal : kEvictFirst;
+  }();
+  args.store_policy = store_policy;
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -93,6 +93,13 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// same with an L2 cache-policy operand (streaming outputs: kEvictFirst, so they do not displace the operand tiles)
+__device__ __forceinline__ void tma_store_2d_hint(const void* desc, const void* smem_src, int32_t c0, int32_t c1,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(desc),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
 // 2-D tiled reduction shared -> global: global[tile] = global[tile] + smem[tile], element type from the tensor map
 // (fp16 add, round-to-nearest-even, performed by the memory system; bulk group completion like a store).
 __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
