@@ -37,6 +37,7 @@ constexpr int BN = 192;
 constexpr int BK = 128;  // bytes == u8 elements per K block (one 128B swizzle row)
 constexpr int UMMA_K = 32;
 constexpr int STAGES = 4;
+constexpr int B_PAIR_STAGE_BYTES = (BN / 2) * BK;   // cta_group::2: each CTA of the pair stages half of the B tile
 constexpr int A_STAGE_BYTES = BM * BK;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK;  // 24 KB
 constexpr int ACC_STAGES = 2;
@@ -138,7 +139,10 @@ __device__ __forceinline__ void stage_chunk(const GemmArgs& p, uint32_t (&packed
     sts_v4_addr(base + ((g ^ sw) << 4), packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
 }
 
-template <int EPI>
+// PAIR = true: launched as 2-CTA clusters; one output tile is 256 rows (128 per CTA) x 192 columns, the leader CTA
+// (cluster rank 0) issues tcgen05.mma.cta_group::2 for both, every CTA TMA-loads its own 128 A rows and HALF of the
+// B tile (96 rows) — 30 % less operand traffic per SM than two independent CTAs — and drains its own TMEM half.
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -163,10 +167,16 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_tiles = (p.M + BM - 1) / BM;
+  // tile = (m-tile, n-tile); with PAIR an m-tile is 256 rows shared by the two CTAs of a cluster
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int num_n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (p.K + BK - 1) / BK;
+  const int m_cta = static_cast<int>(cta_rank) * BM;   // this CTA's row offset inside a tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -181,7 +191,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+      mbar_init(&tempty_bar[a], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);   // leader collects both CTAs' epilogues
     }
     for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     for (int b = 0; b < 2; ++b) {
@@ -191,11 +201,17 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync();   // peer barriers must be initialised before remote arrives / multicast commits
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -204,15 +220,23 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (elect_one()) {
       int s = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_idx = (tile % num_m_tiles) * BM;
-        const int n_idx = (tile / num_m_tiles) * BN;
+      constexpr uint32_t kStageBytes = PAIR ? 2 * (A_STAGE_BYTES + B_PAIR_STAGE_BYTES) : (A_STAGE_BYTES + B_STAGE_BYTES);
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m_idx = (tile % num_m_tiles) * TILE_M + m_cta;
+        const int n_idx = (tile / num_m_tiles) * BN + (PAIR ? static_cast<int>(cta_rank) * (BN / 2) : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
           // operand tiles are re-read by other CTAs (A by every n-tile, B by every m-tile): keep them in L2
-          tma_load_2d_hint(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx, kEvictLast);
-          tma_load_2d_hint(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
+          if (PAIR) {
+            // both CTAs' bytes are accounted on the leader's full barrier, which the leader arms for the pair
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+            tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx, kEvictLast);
+            tma_load_2d_pair(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+            tma_load_2d_hint(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx, kEvictLast);
+            tma_load_2d_hint(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
+          }
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
@@ -220,12 +244,12 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_i8(BM, BN, /*a_signed=*/0, /*b_signed=*/0);
+    if ((!PAIR || cta_rank == 0) && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_i8(TILE_M, BN, /*a_signed=*/0, /*b_signed=*/0);
       int s = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -239,12 +263,17 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advancing K by 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) start-address field
-            tc_mma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) tc_mma_i8_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc_mma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (PAIR) tc_commit_pair(&empty_bar[s], 0b11);
+          else tc_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (PAIR) tc_commit_pair(&tfull_bar[acc], 0b11);
+        else tc_commit(&tfull_bar[acc]);
       }
     }
     __syncwarp();
@@ -254,7 +283,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int4* colg = reinterpret_cast<const int4*>(p.col);
     const int nmax = p.N - 1;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
       const int b = local & 1;
       mbar_wait(&colempty_bar[b], ((local >> 1) & 1) ^ 1);
       const int n0 = (tile / num_m_tiles) * BN;
@@ -280,7 +309,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     struct RowP { float dx; int32_t zx, rs; };
     auto load_rowp = [&](int tile_) {
       RowP r;
-      const int row_ = (tile_ % num_m_tiles) * BM + q * 32 + lane;
+      const int row_ = (tile_ % num_m_tiles) * TILE_M + m_cta + q * 32 + lane;
       const int rc = row_ < p.M ? row_ : p.M - 1;
       const int sr = p.a_period >= p.M ? rc : rc % p.a_period;
       r.dx = __half2float(p.a_delta[sr]);
@@ -288,17 +317,17 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       r.rs = p.a_rowsum[rc];
       return r;
     };
-    RowP rp_next = load_rowp(blockIdx.x < num_tiles ? blockIdx.x : 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    RowP rp_next = load_rowp(worker < num_tiles ? worker : 0);
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int m_idx = (tile % num_m_tiles) * BM;
+      const int m_idx = (tile % num_m_tiles) * TILE_M + m_cta;
       const int n_idx = (tile / num_m_tiles) * BN;
       const int row0 = m_idx + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const RowP rp = rp_next;
-      if (tile + static_cast<int>(gridDim.x) < num_tiles) rp_next = load_rowp(tile + gridDim.x);
+      if (tile + num_workers < num_tiles) rp_next = load_rowp(tile + num_workers);
       const int cbase = n_idx + h * EPI_COLS;
       // active sub-tiles of this warp: rows in range and first column in range (N is a multiple of 8)
       int nact = 0;
@@ -334,7 +363,10 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // the last TMEM load of this accumulator stage has completed: hand the stage back to the MMA warp now
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);   // the leader's MMA thread waits for both CTAs
+            else mbar_arrive(&tempty_bar[acc]);
+          }
         }
         if (EPI == VQ_EPI_DEBUG_LOADS || EPI == VQ_EPI_DEBUG_STORES) {
 #pragma unroll
@@ -380,10 +412,12 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync();   // the peer may still address this CTA's barriers / shared memory
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -443,18 +477,37 @@ int num_sms() {
   return n;
 }
 
-template <int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                       const GemmArgs& args, int grid, cudaStream_t stream) {
+template <int EPI, bool PAIR>
+static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                            const GemmArgs& args, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SMEM_BYTES);
     if (e != cudaSuccess) return VQ_ERR_LAUNCH;
     attr_set = true;
   }
-  vq_gemm_w8a8_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, args);
-  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, PAIR>, ta, tb, to, tr, args);
+  return e == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+template <int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                       const GemmArgs& args, int grid, bool pair, cudaStream_t stream) {
+  return pair ? launch_gemm_impl<EPI, true>(ta, tb, to, tr, args, grid, stream)
+              : launch_gemm_impl<EPI, false>(ta, tb, to, tr, args, grid, stream);
 }
 
 }  // namespace vq
@@ -468,10 +521,16 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0 || !out) return VQ_ERR_ARG;
   if (epi == VQ_EPI_GATE_RESIDUAL && (!res || !gate || rows_per_gate <= 0 || (ldr % 8) != 0)) return VQ_ERR_ARG;
   if (epi < 0 || epi > VQ_EPI_DEBUG_STORES || epi == 4) return VQ_ERR_ARG;
+  // CTA pairs (cta_group::2) whenever there is more than one 128-row tile; VQ_GEMM_PAIR=0 forces single-CTA tiles
+  static const bool allow_pair = [] {
+    const char* e = getenv("VQ_GEMM_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  const bool pair = allow_pair && M > BM;
   CUtensorMap ta, tb, to;
   int rc = make_u8_kmajor_tmap(&ta, a_codes, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM);
   if (rc != VQ_OK) return rc;
-  rc = make_u8_kmajor_tmap(&tb, w_codes, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN);
+  rc = make_u8_kmajor_tmap(&tb, w_codes, (uint64_t)N, (uint64_t)K, (uint64_t)K, pair ? BN / 2 : BN);
   if (rc != VQ_OK) return rc;
   rc = make_f16_out_tmap(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo);
   if (rc != VQ_OK) return rc;
@@ -499,16 +558,18 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
     return (e && e[0] == 'n') ? kEvictNormal : kEvictFirst;
   }();
   args.store_policy = store_policy;
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int tile_m = pair ? 2 * BM : BM;
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+  const int workers = pair ? num_sms() / 2 : num_sms();
+  const int grid = (tiles < workers ? tiles : workers) * (pair ? 2 : 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, tr, args, grid, st);
-    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, tr, args, grid, st);
-    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, tr, args, grid, st);
-    case VQ_EPI_DEBUG_LOADS: return launch_gemm<VQ_EPI_DEBUG_LOADS>(ta, tb, to, tr, args, grid, st);
-    case VQ_EPI_DEBUG_MATH: return launch_gemm<VQ_EPI_DEBUG_MATH>(ta, tb, to, tr, args, grid, st);
-    case VQ_EPI_DEBUG_STORES: return launch_gemm<VQ_EPI_DEBUG_STORES>(ta, tb, to, tr, args, grid, st);
-    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, tr, args, grid, st);
+    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_DEBUG_LOADS: return launch_gemm<VQ_EPI_DEBUG_LOADS>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_DEBUG_MATH: return launch_gemm<VQ_EPI_DEBUG_MATH>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_DEBUG_STORES: return launch_gemm<VQ_EPI_DEBUG_STORES>(ta, tb, to, tr, args, grid, pair, st);
+    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, tr, args, grid, pair, st);
   }
 }
