@@ -438,65 +438,83 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
   }
 }
 
+// one row of the unit mapping from either a token-major or a head-major tensor
+template <int U>
+__device__ __forceinline__ void uload_any(UnitRegs<U>& regs, const ActQuantArgs& a, int g, int r, int lane) {
+  if (a.head_S > 0) {   // token r of sample g = (image b = r / S, position s = r % S) of a [*, H, S, 72] tensor
+    const int bb = r / a.head_S, ss = r - bb * a.head_S;
+    uload_row_heads<U>(regs, a.x + g * a.group_stride + (static_cast<size_t>(bb) * (a.K / 72) * a.head_S + ss) * 72,
+                       a.head_S, lane);
+  } else {
+    uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
+  }
+}
+
 template <int U, bool LN>
-__global__ void __launch_bounds__(256) vq_act_quant_unit_kernel(const ActQuantArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= a.rows) return;
-  UnitRegs<U> regs;
-  __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
-  for (int g = 0; g < a.G; ++g) {
-    if (a.head_S > 0) {   // token r of sample g = (image b = r / S, position s = r % S) of a [*, H, S, 72] tensor
-      const int bb = r / a.head_S, ss = r - bb * a.head_S;
-      uload_row_heads<U>(regs, a.x + g * a.group_stride + (static_cast<size_t>(bb) * (a.K / 72) * a.head_S + ss) * 72,
-                         a.head_S, lane);
-    } else {
-      uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
-    }
-    if (LN) {
-      uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K,
-                            lane);
-      if (a.smooth) uapply_smooth<U>(regs, a.smooth, lane);
-      if (a.y_out) {
-        uint2* yrow = reinterpret_cast<uint2*>(a.y_out + (static_cast<size_t>(g) * a.rows + r) * a.K);
+__device__ __forceinline__ void utransform(UnitRegs<U>& regs, const ActQuantArgs& a, int g, int r, int lane) {
+  if (LN) {
+    uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K, lane);
+    if (a.smooth) uapply_smooth<U>(regs, a.smooth, lane);
+    if (a.y_out) {
+      uint2* yrow = reinterpret_cast<uint2*>(a.y_out + (static_cast<size_t>(g) * a.rows + r) * a.K);
 #pragma unroll
-        for (int i = 0; i < U; ++i) yrow[lane + 32 * i] = regs.u[i];
-      }
-    } else if (a.smooth) {
-      uapply_smooth<U>(regs, a.smooth, lane);
+      for (int i = 0; i < U; ++i) yrow[lane + 32 * i] = regs.u[i];
     }
-    urow_minmax<U>(regs, mn2, mx2);
+  } else if (a.smooth) {
+    uapply_smooth<U>(regs, a.smooth, lane);
   }
-  float mn, mx;
-  warp_minmax(mn2, mx2, mn, mx);
-  const RowStats st = make_stats(mn, mx, a.qmax);
-  const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
-  if (lane == 0) {
-    a.delta[r] = __float2half_rn(st.delta);
-    a.zp[r] = __float2half_rn(st.zp);
-    if (st.degenerate && a.status) atomicOr(a.status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
-  }
-  for (int g = 0; g < a.G; ++g) {
-    if (a.G > 1) {  // G == 1: the transformed row is still in registers
-      if (a.head_S > 0) {
-        const int bb = r / a.head_S, ss = r - bb * a.head_S;
-        uload_row_heads<U>(regs, a.x + g * a.group_stride + (static_cast<size_t>(bb) * (a.K / 72) * a.head_S + ss) * 72,
-                           a.head_S, lane);
-      } else {
-        uload_row<U>(regs, a.x + g * a.group_stride + r * a.ld, lane);
-      }
-      if (LN) {
-        uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K,
-                              a.K, lane);
-        if (a.smooth) uapply_smooth<U>(regs, a.smooth, lane);
-      } else if (a.smooth) {
-        uapply_smooth<U>(regs, a.smooth, lane);
+}
+
+// Persistent: every warp walks rows r, r + W, r + 2W, ... and (for G == 1, the hot case) keeps the NEXT row's loads
+// in flight while it quantises the current one, so HBM requests are outstanding all the time.
+template <int U, bool LN>
+__global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuantArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a.rows) return;
+  UnitRegs<U> regs, nxt;
+  if (a.G == 1) uload_any<U>(regs, a, 0, r, lane);
+  for (; r < a.rows; r += wstride) {
+    const bool has_next = a.G == 1 && r + wstride < a.rows;
+    if (has_next) uload_any<U>(nxt, a, 0, r + wstride, lane);   // prefetch
+    __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
+    if (a.G == 1) {
+      utransform<U, LN>(regs, a, 0, r, lane);
+      urow_minmax<U>(regs, mn2, mx2);
+    } else {
+      for (int g = 0; g < a.G; ++g) {
+        uload_any<U>(regs, a, g, r, lane);
+        utransform<U, LN>(regs, a, g, r, lane);
+        urow_minmax<U>(regs, mn2, mx2);
       }
     }
-    const size_t orow = static_cast<size_t>(g) * a.rows + r;
-    int s = uquant_store_row<U>(regs, a.codes + orow * a.K, lane, qc);
-    s = warp_sum_i(s);
-    if (lane == 0) a.rowsum[orow] = s;
+    float mn, mx;
+    warp_minmax(mn2, mx2, mn, mx);
+    const RowStats st = make_stats(mn, mx, a.qmax);
+    const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
+    if (lane == 0) {
+      a.delta[r] = __float2half_rn(st.delta);
+      a.zp[r] = __float2half_rn(st.zp);
+      if (st.degenerate && a.status) atomicOr(a.status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
+    }
+    for (int g = 0; g < a.G; ++g) {
+      if (a.G > 1) {  // G == 1: the transformed row is still in registers
+        uload_any<U>(regs, a, g, r, lane);
+        UnitRegs<U>& rr = regs;
+        if (LN) {
+          uapply_ln_modulate<U>(rr, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K, lane);
+          if (a.smooth) uapply_smooth<U>(rr, a.smooth, lane);
+        } else if (a.smooth) {
+          uapply_smooth<U>(rr, a.smooth, lane);
+        }
+      }
+      const size_t orow = static_cast<size_t>(g) * a.rows + r;
+      int s = uquant_store_row<U>(regs, a.codes + orow * a.K, lane, qc);
+      s = warp_sum_i(s);
+      if (lane == 0) a.rowsum[orow] = s;
+    }
+    if (has_next) regs = nxt;
   }
 }
 
@@ -508,7 +526,11 @@ static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
   dim3 grid((a.rows + warps - 1) / warps), block(warps * 32);
   // K = 1152 is 4.5 sixteen-byte chunks per lane (divergent in the chunk mapping) but exactly 9 eight-byte units;
   // K = 4608 is 18 full chunk rounds, where the chunk mapping is already branch-free and lighter on registers.
-  if (a.K == 9 * 128) vq_act_quant_unit_kernel<9, LN><<<grid, block, 0, st>>>(a);
+  if (a.K == 9 * 128) {
+    const int blocks_needed = (a.rows + warps - 1) / warps;
+    const int persistent = num_sms() * 3;   // 3 resident 8-warp blocks per SM (80 registers), rows strided across them
+    vq_act_quant_unit_kernel<9, LN><<<blocks_needed < persistent ? blocks_needed : persistent, block, 0, st>>>(a);
+  }
   else if (maxc <= 5) vq_act_quant_kernel<5, LN><<<grid, block, 0, st>>>(a);
   else if (maxc <= 9) vq_act_quant_kernel<9, LN><<<grid, block, 0, st>>>(a);
   else if (maxc <= 18) vq_act_quant_kernel<18, LN><<<grid, block, 0, st>>>(a);
