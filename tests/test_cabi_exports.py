@@ -46,6 +46,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", viditq_b200.build_library()], capture_output=True, text=True).stdout
     assert "UTCIMMA" in sass       # tcgen05.mma.kind::i8
     assert "UTMALDG" in sass       # cp.async.bulk.tensor loads
+    assert "UTMASTG" in sass       # TMA stores from the epilogue
     assert "UTCIMMA.2CTA" in sass  # cta_group::2 CTA-pair variant
     assert "UTCBAR.2CTA.MULTICAST" in sass   # tcgen05.commit multicast to both CTAs of a pair
     assert "LDTM" in sass          # tcgen05.ld

@@ -21,9 +21,17 @@
   } while (0)
 
 __device__ float ref_gelu(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+  // same operation order as the kernel's packed version (gelu_tanh_pair)
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  float x2 = __fmul_rn(x, x);
+  float a = __fmaf_rn(x2, k0k1, k0);
+  float u = __fmul_rn(x, a);
+  float w = __fmul_rn(u, -2.0f * 1.4426950408889634f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(w));
+  float d = __fadd_rn(e, 1.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return __fmul_rn(x, r);
 }
 
 __global__ void ref_gemm(const uint8_t* a, const __half* ad, const __half* az, const int32_t* ars, int period,
@@ -40,7 +48,7 @@ __global__ void ref_gemm(const uint8_t* a, const __half* ad, const __half* az, c
   int rs = ars[m];
   VqColParam c = col[n];
   int t = acc - zx * c.c1 - rs * c.zw;
-  float f = fmaf((float)t, dx * c.dw, c.bias);
+  float f = __fmaf_rn((float)t, __fmul_rn(dx, c.dw), c.bias);
   __half y = __float2half_rn(f);
   if (epi == VQ_EPI_GELU_TANH) y = __float2half_rn(ref_gelu(__half2float(y)));
   if (epi == VQ_EPI_GATE_RESIDUAL) {

@@ -83,6 +83,14 @@ for name, be in (("cudnn", torch.nn.attention.SDPBackend.CUDNN_ATTENTION),
         timeit(f"spatial SDPA {name} (+layout)", sp, ops_=4.0 * 16 * 16 * 1024 * 1024 * 72)
     except Exception as e:  # noqa: BLE001
         print(f"spatial SDPA {name}: {type(e).__name__}: {e}")
+def sp_only():
+    return F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2),
+                                          q5[:, :, 2].transpose(1, 2), scale=72 ** -0.5)
+timeit("spatial SDPA default (no out copy)", sp_only, ops_=4.0 * 16 * 16 * 1024 * 1024 * 72)
+oh = sp_only()
+print("sdpa out contiguous [BT,H,S,D]:", oh.is_contiguous(), tuple(oh.shape), tuple(oh.stride()))
+ah = ops.act_quant_heads(oh, 1, M, 1024)
+timeit("act_quant_heads (head-major in)", lambda: ops.act_quant_heads(oh, 1, M, 1024, out=ah), algo_bytes=M * C * 3)
 try:
     from flash_attn import flash_attn_func
     timeit("spatial flash_attn_func", lambda: flash_attn_func(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2],

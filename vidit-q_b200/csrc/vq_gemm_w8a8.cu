@@ -16,10 +16,10 @@
 //   warp 3      : stages each tile's per-column dequant records in smem one tile ahead (mbarrier hand-off)
 //   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half)
 // Pipelines: smem full/empty ring (4 stages x 40 KB) and TMEM full/empty (2 stages), all mbarrier based.
-// Epilogue output path: registers (thread = row) -> per-warp padded 32x96 fp16 strip in smem -> coalesced 16-byte
-// st.global (full 192-byte row segments, L2 evict-first). For the gated-residual epilogue the residual strip is
-// brought into the same smem strip with cp.async at tile start; out may alias res (in-place residual stream).
-// Neither direction uses the TMA engine, which stays dedicated to the operand tiles.
+// Epilogue output path: registers -> per-warp 32x32 fp16 staging tile in smem (64B swizzle, bank-conflict free)
+// -> TMA store (cp.async.bulk.tensor, coalesced, clipped at the M/N edges by the tensor map). For the gated-residual
+// epilogue the residual tile is TMA-loaded into the same staging tile one chunk ahead (per-warp mbarriers), so the
+// SM never issues row-scattered global loads; out may alias res (in-place residual stream).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -46,13 +46,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int NUM_EPI_WARPS = 8;                      // warp%4 = TMEM lane quarter, (warp-4)/4 = column half
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int EPI_COLS = BN / 2;                      // 96 output columns per epilogue warp per tile
-constexpr int EPI_CHUNK = 32;                         // columns per TMEM load
+constexpr int EPI_CHUNK = 32;                         // columns per TMEM load / staging sub-tile (64 B of fp16 per row)
 constexpr int EPI_NCHUNK = EPI_COLS / EPI_CHUNK;      // 3
-constexpr int EPI_ROW_BYTES = EPI_COLS * 2;           // 192 B of fp16 per staged row
-constexpr int EPI_PITCH = EPI_ROW_BYTES + 16;         // 208 B = 13 x 16 B: odd pitch -> conflict-free 16-byte accesses
-constexpr int EPI_V4_PER_ROW = EPI_ROW_BYTES / 16;    // 12
-constexpr int EPI_STRIP_BYTES = 32 * EPI_PITCH;       // one warp's 32 x 96 staging strip
-constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_STRIP_BYTES;
+constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one sub-tile: 32 rows x 64 B, SWIZZLE_64B
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_NCHUNK * EPI_BUF_BYTES;   // one 32 x 96 strip per warp
 constexpr int COLBUF_BYTES = 2 * BN * 16;                // per-tile {c1, zw, dw, bias} records, double-buffered
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
 
@@ -73,12 +70,23 @@ struct GemmArgs {
   uint64_t store_policy;    // L2 cache policy of the output stores (kEvictFirst unless VQ_STORE_POLICY=normal)
 };
 
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  // nn.GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
-  // 0.5 (1 + tanh(u)) == 1 / (1 + exp(-2u)); __expf/__fdividef error (~1e-6 rel) is far below one fp16 ulp
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+// nn.GELU(approximate="tanh") on a pair: 0.5 x (1 + tanh(u)) == x / (1 + exp(-2u)), u = k0 x (1 + k1 x^2).
+// MUFU.EX2 / MUFU.RCP (~1e-7 relative) are far below one fp16 ulp; everything else is packed fp32 (FFMA2 / FMUL2).
+__device__ __forceinline__ float2 gelu_tanh_pair(float2 x) {
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 a = __ffma2_rn(x2, make_float2(k0k1, k0k1), make_float2(k0, k0));
+  const float2 u = __fmul2_rn(x, a);
+  const float c = -2.0f * 1.4426950408889634f;   // exp(-2u) = 2^(c u)
+  const float2 w = __fmul2_rn(u, make_float2(c, c));
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w.y));
+  const float2 d = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+  return __fmul2_rn(x, make_float2(r0, r1));
 }
 
 constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (measures the TMA->MMA pipeline alone)
@@ -91,33 +99,35 @@ constexpr int VQ_EPI_DEBUG_STORES = 7;    // internal: TMEM loads + staging + TM
 template <int EPI>
 __device__ __forceinline__ void dequant_chunk(const uint32_t (&v)[32], int32_t zx, int32_t rs, float dx,
                                               const int4* colp, uint32_t (&packed)[16]) {
-  // colp: this chunk's 32 column records in shared memory (warp-uniform address -> broadcast LDS.128)
+  // colp: this chunk's 16 column-PAIR records in shared memory, two int4 per pair (warp-uniform -> broadcast LDS.128):
+  //   [2j]   = {c1(n), c1(n+1), zw(n), zw(n+1)}      [2j+1] = {dw(n), dw(n+1), bias(n), bias(n+1)} (fp32 bits)
+  const float2 dx2 = make_float2(dx, dx);
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float f[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int4 cp = lds_v4(colp + j + e);
-      int32_t t = static_cast<int32_t>(v[j + e]) - zx * cp.x - rs * cp.y;
-      float s = dx * __int_as_float(cp.z);
-      f[e] = fmaf(static_cast<float>(t), s, __int_as_float(cp.w));
-    }
-    __half2 h2 = __floats2half2_rn(f[0], f[1]);
+  for (int j = 0; j < 16; ++j) {
+    const int4 ci = lds_v4(colp + 2 * j);
+    const int4 cf = lds_v4(colp + 2 * j + 1);
+    const int32_t t0 = static_cast<int32_t>(v[2 * j]) - zx * ci.x - rs * ci.z;
+    const int32_t t1 = static_cast<int32_t>(v[2 * j + 1]) - zx * ci.y - rs * ci.w;
+    const float2 s2 = __fmul2_rn(dx2, make_float2(__int_as_float(cf.x), __int_as_float(cf.y)));
+    const float2 f2 = __ffma2_rn(make_float2(static_cast<float>(t0), static_cast<float>(t1)), s2,
+                                 make_float2(__int_as_float(cf.z), __int_as_float(cf.w)));
+    __half2 h2 = __floats2half2_rn(f2.x, f2.y);
     if (EPI == VQ_EPI_GELU_TANH) {
-      float2 y = __half22float2(h2);
-      h2 = __floats2half2_rn(gelu_tanh_f(y.x), gelu_tanh_f(y.y));
+      const float2 g = gelu_tanh_pair(__half22float2(h2));
+      h2 = __floats2half2_rn(g.x, g.y);
     }
-    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+    packed[j] = *reinterpret_cast<uint32_t*>(&h2);
   }
 }
 
-// Write one chunk (32 columns of this thread's row) into the warp's staging strip (row-major, 208-byte pitch). For the
-// gated residual the strip already holds the residual (cp.async, same layout): x_new = res + gate * y with the
-// reference's two fp16 roundings.
+// Write one chunk (32 columns of this thread's row) into its staging sub-tile: row-major 64-byte rows, 16-byte piece
+// index XOR ((row >> 1) & 3) == CU_TENSOR_MAP_SWIZZLE_64B (conflict-free). For the gated residual the sub-tile already
+// holds the residual (TMA load, same swizzle): x_new = res + gate * y with the reference's two fp16 roundings.
 template <int EPI>
 __device__ __forceinline__ void stage_chunk(const GemmArgs& p, uint32_t (&packed)[16], int row, bool row_ok, int col0,
-                                            uint32_t strip_row_addr, int c) {
-  const uint32_t base = strip_row_addr + c * (EPI_CHUNK * 2);
+                                            uint8_t* sub, int lane) {
+  const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+  const uint32_t base = smem_u32(sub) + lane * (EPI_CHUNK * 2);
   if (EPI == VQ_EPI_GATE_RESIDUAL) {
     const __half* gate_row = p.gate + static_cast<size_t>((row_ok ? row : 0) / p.rows_per_gate) * p.N;
 #pragma unroll
@@ -125,7 +135,7 @@ __device__ __forceinline__ void stage_chunk(const GemmArgs& p, uint32_t (&packed
       const int n = col0 + g * 8;
       uint4 gv = make_uint4(0, 0, 0, 0);
       if (n < p.N) gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
-      const int4 rv = lds_v4_addr(base + (g << 4));
+      const int4 rv = lds_v4_addr(base + ((g ^ sw) << 4));
       const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
       const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
@@ -138,7 +148,7 @@ __device__ __forceinline__ void stage_chunk(const GemmArgs& p, uint32_t (&packed
   }
 #pragma unroll
   for (int g = 0; g < 4; ++g)
-    sts_v4_addr(base + (g << 4), packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+    sts_v4_addr(base + ((g ^ sw) << 4), packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
 }
 
 // PAIR = true: launched as 2-CTA clusters; one output tile is 256 rows (128 per CTA) x 192 columns, the leader CTA
@@ -147,6 +157,7 @@ __device__ __forceinline__ void stage_chunk(const GemmArgs& p, uint32_t (&packed
 template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -160,7 +171,8 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
-  uint64_t* colfull_bar = bars + 2 * STAGES + 2 * ACC_STAGES;   // [2] column records of a tile are in colbuf[b]
+  uint64_t* res_bar = bars + 2 * STAGES + 2 * ACC_STAGES;   // [NUM_EPI_WARPS] residual strip landed
+  uint64_t* colfull_bar = res_bar + NUM_EPI_WARPS;           // [2] column records of a tile are in colbuf[b]
   uint64_t* colempty_bar = colfull_bar + 2;                  // [2] all epilogue warps are done with colbuf[b]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(colempty_bar + 2);
 
@@ -181,6 +193,8 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (EPI == VQ_EPI_GATE_RESIDUAL) tma_prefetch_desc(&tmap_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -191,6 +205,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);   // leader collects both CTAs' epilogues
     }
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&colfull_bar[b], 1);
       mbar_init(&colempty_bar[b], NUM_EPI_WARPS);
@@ -285,9 +300,13 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&colempty_bar[b], ((local >> 1) & 1) ^ 1);
       const int n0 = (tile / num_m_tiles) * BN;
 #pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        const int n = n0 + lane + 32 * i;
-        colbuf[b * BN + lane + 32 * i] = __ldg(colg + (n < nmax ? n : nmax));
+      for (int i = 0; i < BN / 64; ++i) {   // 96 column pairs per tile, 3 per lane
+        const int pr = lane + 32 * i;
+        const int n = n0 + 2 * pr;
+        const int4 r0 = __ldg(colg + (n < nmax ? n : nmax));
+        const int4 r1 = __ldg(colg + (n + 1 < nmax ? n + 1 : nmax));
+        colbuf[b * BN + 2 * pr] = make_int4(r0.x, r1.x, r0.y, r1.y);       // {c1, c1', zw, zw'}
+        colbuf[b * BN + 2 * pr + 1] = make_int4(r0.z, r1.z, r0.w, r1.w);   // {dw, dw', bias, bias'}
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&colfull_bar[b]);
@@ -295,12 +314,12 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // Per tile and warp: 32 rows x 96 columns. The strip is dequantised into registers chunk by chunk (TMEM loads
-    // software-pipelined), transposed through a padded shared-memory strip (thread = row in, 16-byte pieces out) and
-    // written with coalesced 16-byte stores: full 192-byte row segments, through the LSU path — the TMA engine and its
-    // queue stay dedicated to the operand tiles (TMA stores measurably stalled the mainloop: profiles/).
+    // software-pipelined), then staged and handed to the TMA with ONE proxy fence and three bulk stores per tile.
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int h = (warp - 4) >> 2;   // column half
-    const uint32_t strip_addr = smem_u32(smem_epi + (warp - 4) * EPI_STRIP_BYTES);
+    uint8_t* stage0 = smem_epi + (warp - 4) * EPI_NCHUNK * EPI_BUF_BYTES;
+    uint64_t* my_res_bar = res_bar + (warp - 4);
+    uint32_t res_uses = 0;
     int local = 0;
     // per-row dequant parameters {delta, zero point, row sum}, fetched one tile ahead
     struct RowP { float dx; int32_t zx, rs; };
@@ -326,7 +345,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const RowP rp = rp_next;
       if (tile + num_workers < num_tiles) rp_next = load_rowp(tile + num_workers);
       const int cbase = n_idx + h * EPI_COLS;
-      // active 32-column chunks of this warp: rows in range and first column in range (N is a multiple of 8)
+      // active sub-tiles of this warp: rows in range and first column in range (N is a multiple of 8)
       int nact = 0;
       if (EPI != VQ_EPI_DEBUG_MAINLOOP && EPI != VQ_EPI_DEBUG_LOADS && EPI != VQ_EPI_DEBUG_MATH && row0 < p.M) {
 #pragma unroll
@@ -338,18 +357,14 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * EPI_COLS;
       uint32_t v[2][32];
       tmem_ld_32x32b_x32(t_base, v[0]);
-      // residual strip -> staging via cp.async (LSU path; the TMA engine stays dedicated to the operand tiles).
-      // The strip is free: the previous tile's copy-out below ended with a __syncwarp().
-      if (EPI == VQ_EPI_GATE_RESIDUAL && nact > 0) {
-#pragma unroll
-        for (int i = 0; i < EPI_V4_PER_ROW; ++i) {
-          const int f = lane + 32 * i;                 // 16-byte piece index inside the 32 x 12 strip
-          const int rr = f / EPI_V4_PER_ROW, cc = f - rr * EPI_V4_PER_ROW;
-          const bool ok = (row0 + rr < p.M) && (cbase + cc * 8 < p.N);
-          const __half* src = ok ? p.res + static_cast<size_t>(row0 + rr) * p.ldr + cbase + cc * 8 : p.res;
-          cp_async16_hint(strip_addr + rr * EPI_PITCH + cc * 16, src, ok ? 16 : 0);
+      // the previous tile's TMA stores have finished reading the staging strip (they were issued a whole tile ago)
+      if (lane == 0 && nact > 0) {
+        tma_store_wait_read<0>();
+        if (EPI == VQ_EPI_GATE_RESIDUAL) {   // residual strip -> staging (same swizzle), landed on my_res_bar
+          mbar_arrive_expect_tx(my_res_bar, nact * EPI_BUF_BYTES);
+          for (int c = 0; c < nact; ++c)
+            tma_load_2d_hint(stage0 + c * EPI_BUF_BYTES, &tmap_res, my_res_bar, cbase + c * EPI_CHUNK, row0, kEvictFirst);
         }
-        cp_async_commit();
       }
       mbar_wait(&colfull_bar[acc], acc_phase);
       const int4* ctile = colbuf + acc * BN + h * EPI_COLS;
@@ -390,27 +405,26 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (nact > 0) {
         if (EPI == VQ_EPI_GATE_RESIDUAL) {
-          cp_async_wait_all_();   // each lane's own pieces have landed ...
-          __syncwarp();           // ... and are visible to the lane that owns the row
+          mbar_wait(my_res_bar, res_uses & 1);
+          ++res_uses;
+        } else {
+          __syncwarp();   // lane 0's wait_read above precedes every lane's staging writes
         }
-        const uint32_t my_row_addr = strip_addr + lane * EPI_PITCH;
 #pragma unroll
         for (int c = 0; c < EPI_NCHUNK; ++c)
-          if (c < nact) stage_chunk<EPI>(p, packed[c], row, row_ok, cbase + c * EPI_CHUNK, my_row_addr, c);
+          if (c < nact) stage_chunk<EPI>(p, packed[c], row, row_ok, cbase + c * EPI_CHUNK, stage0 + c * EPI_BUF_BYTES, lane);
+        fence_proxy_async_smem();
         __syncwarp();
-        // copy-out: every instruction writes 512 contiguous bytes of the strip = full 192-byte row segments in global
-#pragma unroll
-        for (int i = 0; i < EPI_V4_PER_ROW; ++i) {
-          const int f = lane + 32 * i;
-          const int rr = f / EPI_V4_PER_ROW, cc = f - rr * EPI_V4_PER_ROW;
-          if ((row0 + rr < p.M) && (cbase + cc * 8 < p.N)) {
-            const int4 v4 = lds_v4_addr(strip_addr + rr * EPI_PITCH + cc * 16);
-            stg_v4_hint(p.out + static_cast<size_t>(row0 + rr) * p.ldo + cbase + cc * 8, v4, p.store_policy);
-          }
+        if (lane == 0) {
+          // streaming output: evict-first so it does not push the operand tiles out of L2
+          for (int c = 0; c < nact; ++c)
+            tma_store_2d_hint(&tmap_out, stage0 + c * EPI_BUF_BYTES, cbase + c * EPI_CHUNK, row0, p.store_policy);
+          tma_store_commit();
         }
-        __syncwarp();   // strip reusable by the next tile
       }
     }
+    if (lane == 0) tma_store_wait<0>();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -454,6 +468,21 @@ int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
 }
 
+// rows x cols fp16 matrix (row pitch ld elements); box = 32 rows x EPI_CHUNK cols, matching swizzle: the epilogue staging tile.
+int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return VQ_ERR_DRIVER;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(EPI_CHUNK), 32u};   // 32 columns = 64 B
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -465,8 +494,8 @@ int num_sms() {
 }
 
 template <int EPI, bool PAIR>
-static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int grid,
-                            cudaStream_t stream) {
+static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                            const GemmArgs& args, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -486,15 +515,15 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, PAIR>, ta, tb, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, PAIR>, ta, tb, to, tr, args);
   return e == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int grid, bool pair,
-                       cudaStream_t stream) {
-  return pair ? launch_gemm_impl<EPI, true>(ta, tb, args, grid, stream)
-              : launch_gemm_impl<EPI, false>(ta, tb, args, grid, stream);
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                       const GemmArgs& args, int grid, bool pair, cudaStream_t stream) {
+  return pair ? launch_gemm_impl<EPI, true>(ta, tb, to, tr, args, grid, stream)
+              : launch_gemm_impl<EPI, false>(ta, tb, to, tr, args, grid, stream);
 }
 
 }  // namespace vq
@@ -514,11 +543,18 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
     return !(e && e[0] == '0');
   }();
   const bool pair = allow_pair && M > BM;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
   int rc = make_u8_kmajor_tmap(&ta, a_codes, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM);
   if (rc != VQ_OK) return rc;
   rc = make_u8_kmajor_tmap(&tb, w_codes, (uint64_t)N, (uint64_t)K, (uint64_t)K, pair ? BN / 2 : BN);
   if (rc != VQ_OK) return rc;
+  rc = make_f16_out_tmap(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo);
+  if (rc != VQ_OK) return rc;
+  CUtensorMap tr = to;
+  if (epi == VQ_EPI_GATE_RESIDUAL) {
+    rc = make_f16_out_tmap(&tr, res, (uint64_t)M, (uint64_t)N, (uint64_t)ldr);
+    if (rc != VQ_OK) return rc;
+  }
   GemmArgs args;
   args.M = M; args.N = N; args.K = K;
   args.a_delta = static_cast<const __half*>(a_delta);
@@ -544,12 +580,12 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   const int grid = (tiles < workers ? tiles : workers) * (pair ? 2 : 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, args, grid, pair, st);
-    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, args, grid, pair, st);
-    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, args, grid, pair, st);
-    case VQ_EPI_DEBUG_LOADS: return launch_gemm<VQ_EPI_DEBUG_LOADS>(ta, tb, args, grid, pair, st);
-    case VQ_EPI_DEBUG_MATH: return launch_gemm<VQ_EPI_DEBUG_MATH>(ta, tb, args, grid, pair, st);
-    case VQ_EPI_DEBUG_STORES: return launch_gemm<VQ_EPI_DEBUG_STORES>(ta, tb, args, grid, pair, st);
-    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, args, grid, pair, st);
+    case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_DEBUG_LOADS: return launch_gemm<VQ_EPI_DEBUG_LOADS>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_DEBUG_MATH: return launch_gemm<VQ_EPI_DEBUG_MATH>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_DEBUG_STORES: return launch_gemm<VQ_EPI_DEBUG_STORES>(ta, tb, to, tr, args, grid, pair, st);
+    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, tr, args, grid, pair, st);
   }
 }

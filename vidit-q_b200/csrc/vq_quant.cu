@@ -439,9 +439,9 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
 }
 
 // one row of the unit mapping from either a token-major or a head-major tensor
-template <int U>
+template <int U, bool HEADS>
 __device__ __forceinline__ void uload_any(UnitRegs<U>& regs, const ActQuantArgs& a, int g, int r, int lane) {
-  if (a.head_S > 0) {   // token r of sample g = (image b = r / S, position s = r % S) of a [*, H, S, 72] tensor
+  if (HEADS) {   // token r of sample g = (image b = r / S, position s = r % S) of a [*, H, S, 72] tensor
     const int bb = r / a.head_S, ss = r - bb * a.head_S;
     uload_row_heads<U>(regs, a.x + g * a.group_stride + (static_cast<size_t>(bb) * (a.K / 72) * a.head_S + ss) * 72,
                        a.head_S, lane);
@@ -467,24 +467,24 @@ __device__ __forceinline__ void utransform(UnitRegs<U>& regs, const ActQuantArgs
 
 // Persistent: every warp walks rows r, r + W, r + 2W, ... and (for G == 1, the hot case) keeps the NEXT row's loads
 // in flight while it quantises the current one, so HBM requests are outstanding all the time.
-template <int U, bool LN>
+template <int U, bool LN, bool HEADS>
 __global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuantArgs a) {
   const int lane = threadIdx.x & 31;
   const int wstride = gridDim.x * (blockDim.x >> 5);
   int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= a.rows) return;
   UnitRegs<U> regs, nxt;
-  if (a.G == 1) uload_any<U>(regs, a, 0, r, lane);
+  if (a.G == 1) uload_any<U, HEADS>(regs, a, 0, r, lane);
   for (; r < a.rows; r += wstride) {
     const bool has_next = a.G == 1 && r + wstride < a.rows;
-    if (has_next) uload_any<U>(nxt, a, 0, r + wstride, lane);   // prefetch
+    if (has_next) uload_any<U, HEADS>(nxt, a, 0, r + wstride, lane);   // prefetch
     __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
     if (a.G == 1) {
       utransform<U, LN>(regs, a, 0, r, lane);
       urow_minmax<U>(regs, mn2, mx2);
     } else {
       for (int g = 0; g < a.G; ++g) {
-        uload_any<U>(regs, a, g, r, lane);
+        uload_any<U, HEADS>(regs, a, g, r, lane);
         utransform<U, LN>(regs, a, g, r, lane);
         urow_minmax<U>(regs, mn2, mx2);
       }
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuan
     }
     for (int g = 0; g < a.G; ++g) {
       if (a.G > 1) {  // G == 1: the transformed row is still in registers
-        uload_any<U>(regs, a, g, r, lane);
+        uload_any<U, HEADS>(regs, a, g, r, lane);
         UnitRegs<U>& rr = regs;
         if (LN) {
           uapply_ln_modulate<U>(rr, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K, lane);
@@ -529,7 +529,9 @@ static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
   if (a.K == 9 * 128) {
     const int blocks_needed = (a.rows + warps - 1) / warps;
     const int persistent = num_sms() * 3;   // 3 resident 8-warp blocks per SM (80 registers), rows strided across them
-    vq_act_quant_unit_kernel<9, LN><<<blocks_needed < persistent ? blocks_needed : persistent, block, 0, st>>>(a);
+    const int g2 = blocks_needed < persistent ? blocks_needed : persistent;
+    if (a.head_S > 0) vq_act_quant_unit_kernel<9, LN, true><<<g2, block, 0, st>>>(a);
+    else vq_act_quant_unit_kernel<9, LN, false><<<g2, block, 0, st>>>(a);
   }
   else if (maxc <= 5) vq_act_quant_kernel<5, LN><<<grid, block, 0, st>>>(a);
   else if (maxc <= 9) vq_act_quant_kernel<9, LN><<<grid, block, 0, st>>>(a);
