@@ -87,10 +87,11 @@ def sp_only():
     return F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2),
                                           q5[:, :, 2].transpose(1, 2), scale=72 ** -0.5)
 timeit("spatial SDPA default (no out copy)", sp_only, ops_=4.0 * 16 * 16 * 1024 * 1024 * 72)
-oh = sp_only()
-print("sdpa out contiguous [BT,H,S,D]:", oh.is_contiguous(), tuple(oh.shape), tuple(oh.stride()))
+oh_raw = sp_only()
+print("sdpa out contiguous [BT,H,S,D]:", oh_raw.is_contiguous(), tuple(oh_raw.shape), tuple(oh_raw.stride()))
+oh = oh_raw.contiguous()
 ah = ops.act_quant_heads(oh, 1, M, 1024)
-timeit("act_quant_heads (head-major in)", lambda: ops.act_quant_heads(oh, 1, M, 1024, out=ah), algo_bytes=M * C * 3)
+timeit("act_quant_heads (head-major in)", lambda: ops.act_quant_heads(oh, 1, M, 1024), algo_bytes=M * C * 3)
 try:
     from flash_attn import flash_attn_func
     timeit("spatial flash_attn_func", lambda: flash_attn_func(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2],
