@@ -83,6 +83,28 @@ for name, be in (("cudnn", torch.nn.attention.SDPBackend.CUDNN_ATTENTION),
         timeit(f"spatial SDPA {name} (+layout)", sp, ops_=4.0 * 16 * 16 * 1024 * 1024 * 72)
     except Exception as e:  # noqa: BLE001
         print(f"spatial SDPA {name}: {type(e).__name__}: {e}")
+# library yardstick for the GEMM shapes: cuBLASLt fp8 (same bytes, same tensor rate as INT8) with row/column scales, fp16 out
+try:
+    f8 = torch.float8_e4m3fn
+    for (n_, k_) in ((C, C), (3 * C, C), (4 * C, C), (C, 4 * C)):
+        A8 = torch.randn(M, k_, device=dev).to(f8)
+        B8 = torch.randn(n_, k_, device=dev).to(f8)
+        sa = torch.rand(M, 1, device=dev) + 0.5
+        sb = torch.rand(1, n_, device=dev) + 0.5
+        bias8 = torch.randn(n_, device=dev, dtype=torch.float16)
+        o8 = torch.empty(M, n_, device=dev, dtype=torch.float16)
+        timeit(f"cublasLt fp8 rowwise N={n_} K={k_}",
+               lambda: torch._scaled_mm(A8, B8.t(), scale_a=sa, scale_b=sb, bias=bias8, out_dtype=torch.float16, out=o8),
+               ops_=2.0 * M * n_ * k_)
+except Exception as e:  # noqa: BLE001
+    print(f"cublasLt fp8 yardstick: {type(e).__name__}: {str(e)[:200]}")
+try:
+    for (n_, k_) in ((C, C), (3 * C, C), (4 * C, C), (C, 4 * C)):
+        A8 = torch.randint(-8, 8, (M, k_), device=dev, dtype=torch.int8)
+        B8 = torch.randint(-8, 8, (k_, n_), device=dev, dtype=torch.int8)
+        timeit(f"cublasLt int8->int32 N={n_} K={k_}", lambda: torch._int_mm(A8, B8), ops_=2.0 * M * n_ * k_)
+except Exception as e:  # noqa: BLE001
+    print(f"cublasLt int8 yardstick: {type(e).__name__}: {str(e)[:200]}")
 def sp_only():
     return F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2),
                                           q5[:, :, 2].transpose(1, 2), scale=72 ** -0.5)

@@ -55,6 +55,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
   uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Asynchronously copy `rows` rows of 72 halves (global row stride gstride elements) into a [tile_rows, PITCH] smem
@@ -185,6 +186,7 @@ struct TemporalArgs {
 constexpr int TEMPORAL_WARPS = 8;
 
 __global__ void __launch_bounds__(TEMPORAL_WARPS * 32) vq_attn_temporal_kernel(const TemporalArgs a) {
+  grid_dep_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __half* sQ = reinterpret_cast<__half*>(smem_attn) + warp * 3 * 16 * PITCH;
@@ -233,25 +235,46 @@ struct CrossArgs {
 constexpr int CROSS_WARPS = 8;
 constexpr int CROSS_KT = 8;   // 128 keys
 
+// One CTA = one (sample, head) and a contiguous range of 16-query groups: K/V (<= 128 keys) are loaded once per CTA, every
+// warp then walks its own groups with a double-buffered Q tile (cp.async of group i+1 in flight under the MMAs of group
+// i), so there is no CTA-wide barrier after the first one and the K/V load is amortised over ~7 groups per warp.
 __global__ void __launch_bounds__(CROSS_WARPS * 32, 2) vq_attn_cross_kernel(const CrossArgs a) {
+  grid_dep_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __half* sK = reinterpret_cast<__half*>(smem_attn);
   __half* sV = sK + CROSS_KT * 16 * PITCH;
-  __half* sQ = sV + CROSS_KT * 16 * PITCH + warp * 16 * PITCH;
+  __half* sQ = sV + CROSS_KT * 16 * PITCH + warp * 2 * 16 * PITCH;   // two buffers per warp
   const int h = blockIdx.y, b = blockIdx.z;
   const int C = a.H * HD;
   const int lk = a.kv_len[b];
   const __half* kbase = a.kv + static_cast<long long>(a.kv_start[b]) * 2 * C + h * HD;
   load_tile(sK, kbase, 2LL * C, lk, CROSS_KT * 16, threadIdx.x, CROSS_WARPS * 32);
   load_tile(sV, kbase + C, 2LL * C, lk, CROSS_KT * 16, threadIdx.x, CROSS_WARPS * 32);
-  const int row0 = (blockIdx.x * CROSS_WARPS + warp) * 16;
-  const int nq = min(16, a.N - row0);
-  const long long tok0 = static_cast<long long>(b) * a.N + row0;
-  if (nq > 0) load_tile(sQ, a.q + tok0 * C + h * HD, C, nq, 16, lane, 32);
+  cp_async_commit();
+  const int groups = (a.N + 15) >> 4;
+  const int per_cta = (groups + gridDim.x - 1) / gridDim.x;
+  const int g_end = min(groups, (static_cast<int>(blockIdx.x) + 1) * per_cta);
+  int grp = blockIdx.x * per_cta + warp;
+  const __half* qbase = a.q + static_cast<long long>(b) * a.N * C + h * HD;
+  __half* obase = a.out + static_cast<long long>(b) * a.N * C + h * HD;
+  if (grp < g_end) load_tile(sQ, qbase + static_cast<long long>(grp) * 16 * C, C, min(16, a.N - grp * 16), 16, lane, 32);
+  cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
-  if (nq > 0) warp_attend<4>(sQ, sK, sV, lk, a.scale_log2e, a.out + tok0 * C + h * HD, C, nq, lane);
+  int buf = 0;
+  for (; grp < g_end; grp += CROSS_WARPS) {
+    const int nxt = grp + CROSS_WARPS;
+    if (nxt < g_end)
+      load_tile(sQ + (buf ^ 1) * 16 * PITCH, qbase + static_cast<long long>(nxt) * 16 * C, C, min(16, a.N - nxt * 16), 16,
+                lane, 32);
+    cp_async_commit();
+    warp_attend<4>(sQ + buf * 16 * PITCH, sK, sV, lk, a.scale_log2e, obase + static_cast<long long>(grp) * 16 * C, C,
+                   min(16, a.N - grp * 16), lane);
+    cp_async_wait_all();
+    __syncwarp();
+    buf ^= 1;
+  }
 }
 
 }  // namespace vq
@@ -271,7 +294,7 @@ extern "C" int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S,
     attr = true;
   }
   const unsigned grid = static_cast<unsigned>((units + TEMPORAL_WARPS - 1) / TEMPORAL_WARPS);
-  vq_attn_temporal_kernel<<<grid, TEMPORAL_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(vq_attn_temporal_kernel, dim3(grid), dim3(TEMPORAL_WARPS * 32), smem, static_cast<cudaStream_t>(stream), a);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
@@ -282,14 +305,20 @@ extern "C" int vq_attn_cross(const void* q, const void* kv, void* out, const int
   if (head_dim != HD || max_len <= 0 || max_len > CROSS_KT * 16) return VQ_ERR_UNSUPPORTED;
   CrossArgs a{static_cast<const __half*>(q), static_cast<const __half*>(kv), static_cast<__half*>(out), kv_start,
               kv_len, B, N, H, scale * 1.4426950408889634f};
-  const int smem = (2 * CROSS_KT * 16 + CROSS_WARPS * 16) * PITCH * 2;
+  const int smem = (2 * CROSS_KT * 16 + 2 * CROSS_WARPS * 16) * PITCH * 2;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(vq_attn_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return VQ_ERR_LAUNCH;
     attr = true;
   }
-  dim3 grid((N + CROSS_WARPS * 16 - 1) / (CROSS_WARPS * 16), H, B);
-  vq_attn_cross_kernel<<<grid, CROSS_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  // two CTAs per SM, all resident at once; each covers >= one 16-query group per warp
+  const int groups = (N + 15) / 16;
+  int chunks = 2 * num_sms() / (H * B);
+  chunks = chunks < 1 ? 1 : chunks;
+  const int max_chunks = (groups + CROSS_WARPS - 1) / CROSS_WARPS;
+  if (chunks > max_chunks) chunks = max_chunks;
+  dim3 grid(chunks, H, B);
+  launch_pdl(vq_attn_cross_kernel, dim3(grid), dim3(CROSS_WARPS * 32), smem, static_cast<cudaStream_t>(stream), a);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }

@@ -15,7 +15,7 @@
 //   warp 2      : TMEM allocator (512 columns = 2 accumulator stages x 256)
 //   warp 3      : stages each tile's per-column dequant records in smem one tile ahead (mbarrier hand-off)
 //   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half)
-// Pipelines: smem full/empty ring (4 stages x 40 KB) and TMEM full/empty (2 stages), all mbarrier based.
+// Pipelines: smem full/empty ring (4 stages x 40 KB; CTA pairs 6 x 28 KB) and TMEM full/empty (2 stages), all mbarrier based.
 // Epilogue output path: registers -> per-warp 32x32 fp16 staging tile in smem (64B swizzle, bank-conflict free)
 // -> TMA store (cp.async.bulk.tensor, coalesced, clipped at the M/N edges by the tensor map). For the gated-residual
 // epilogue the residual tile is TMA-loaded into the same staging tile one chunk ahead (per-warp mbarriers), so the
@@ -36,7 +36,9 @@ constexpr int BM = 128;
 constexpr int BN = 192;
 constexpr int BK = 128;  // bytes == u8 elements per K block (one 128B swizzle row)
 constexpr int UMMA_K = 32;
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;        // single-CTA tiles: 4 x (16 KB A + 24 KB B)
+constexpr int PAIR_STAGES = 6;   // CTA pairs stage half a B tile each: 6 x (16 KB A + 12 KB B)
+constexpr int MAX_STAGES = 6;
 constexpr int B_PAIR_STAGE_BYTES = (BN / 2) * BK;   // cta_group::2: each CTA of the pair stages half of the B tile
 constexpr int A_STAGE_BYTES = BM * BK;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK;  // 24 KB
@@ -51,7 +53,11 @@ constexpr int EPI_NCHUNK = EPI_COLS / EPI_CHUNK;      // 3
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one sub-tile: 32 rows x 64 B, SWIZZLE_64B
 constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_NCHUNK * EPI_BUF_BYTES;   // one 32 x 96 strip per warp
 constexpr int COLBUF_BYTES = 2 * BN * 16;                // per-tile {c1, zw, dw, bias} records, double-buffered
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
+constexpr int OPERAND_BYTES_SINGLE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+constexpr int OPERAND_BYTES_PAIR = PAIR_STAGES * (A_STAGE_BYTES + B_PAIR_STAGE_BYTES);
+constexpr int OPERAND_BYTES = OPERAND_BYTES_PAIR > OPERAND_BYTES_SINGLE ? OPERAND_BYTES_PAIR : OPERAND_BYTES_SINGLE;
+constexpr int SMEM_BYTES = OPERAND_BYTES + EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 struct GemmArgs {
   int M, N, K;
@@ -162,16 +168,18 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NS = PAIR ? PAIR_STAGES : STAGES;
+  constexpr int BSB = PAIR ? B_PAIR_STAGE_BYTES : B_STAGE_BYTES;   // per-CTA bytes of one B stage
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smem_epi = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  uint8_t* smem_b = smem + NS * A_STAGE_BYTES;
+  uint8_t* smem_epi = smem + OPERAND_BYTES;
   int4* colbuf = reinterpret_cast<int4*>(smem_epi + EPI_STAGING_BYTES);   // [2][BN] records
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGING_BYTES + COLBUF_BYTES);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
-  uint64_t* res_bar = bars + 2 * STAGES + 2 * ACC_STAGES;   // [NUM_EPI_WARPS] residual strip landed
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + ACC_STAGES;
+  uint64_t* res_bar = bars + 2 * MAX_STAGES + 2 * ACC_STAGES;   // [NUM_EPI_WARPS] residual strip landed
   uint64_t* colfull_bar = res_bar + NUM_EPI_WARPS;           // [2] column records of a tile are in colbuf[b]
   uint64_t* colempty_bar = colfull_bar + 2;                  // [2] all epilogue warps are done with colbuf[b]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(colempty_bar + 2);
@@ -197,7 +205,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (EPI == VQ_EPI_GATE_RESIDUAL) tma_prefetch_desc(&tmap_res);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -226,6 +234,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -243,13 +252,13 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // both CTAs' bytes are accounted on the leader's full barrier, which the leader arms for the pair
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
             tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx, kEvictLast);
-            tma_load_2d_pair(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
+            tma_load_2d_pair(smem_b + s * BSB, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
             tma_load_2d_hint(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_idx, kEvictLast);
-            tma_load_2d_hint(smem_b + s * B_STAGE_BYTES, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
+            tma_load_2d_hint(smem_b + s * BSB, &tmap_b, &full_bar[s], kb * BK, n_idx, kEvictLast);
           }
-          if (++s == STAGES) { s = 0; phase ^= 1; }
+          if (++s == NS) { s = 0; phase ^= 1; }
         }
       }
     }
@@ -271,7 +280,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&full_bar[s], phase);
           tc_fence_after();
           const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
-          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(smem_b + s * BSB));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advancing K by 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) start-address field
@@ -281,7 +290,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
           if (PAIR) tc_commit_pair(&empty_bar[s], 0b11);
           else tc_commit(&empty_bar[s]);
-          if (++s == STAGES) { s = 0; phase ^= 1; }
+          if (++s == NS) { s = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
         if (PAIR) tc_commit_pair(&tfull_bar[acc], 0b11);
@@ -508,13 +517,15 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const 
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, PAIR>, ta, tb, to, tr, args);
   return e == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }

@@ -386,6 +386,7 @@ struct ActQuantArgs {
 
 template <int MAXC, bool LN>
 __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a) {
+  grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= a.rows) return;
@@ -469,6 +470,7 @@ __device__ __forceinline__ void utransform(UnitRegs<U>& regs, const ActQuantArgs
 // in flight while it quantises the current one, so HBM requests are outstanding all the time.
 template <int U, bool LN, bool HEADS>
 __global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuantArgs a) {
+  grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int wstride = gridDim.x * (blockDim.x >> 5);
   int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -530,13 +532,13 @@ static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
     const int blocks_needed = (a.rows + warps - 1) / warps;
     const int persistent = num_sms() * 3;   // 3 resident 8-warp blocks per SM (80 registers), rows strided across them
     const int g2 = blocks_needed < persistent ? blocks_needed : persistent;
-    if (a.head_S > 0) vq_act_quant_unit_kernel<9, LN, true><<<g2, block, 0, st>>>(a);
-    else vq_act_quant_unit_kernel<9, LN, false><<<g2, block, 0, st>>>(a);
+    if (a.head_S > 0) launch_pdl(vq_act_quant_unit_kernel<9, LN, true>, g2, block, 0, st, a);
+    else launch_pdl(vq_act_quant_unit_kernel<9, LN, false>, g2, block, 0, st, a);
   }
-  else if (maxc <= 5) vq_act_quant_kernel<5, LN><<<grid, block, 0, st>>>(a);
-  else if (maxc <= 9) vq_act_quant_kernel<9, LN><<<grid, block, 0, st>>>(a);
-  else if (maxc <= 18) vq_act_quant_kernel<18, LN><<<grid, block, 0, st>>>(a);
-  else if (maxc <= 36) vq_act_quant_kernel<36, LN><<<grid, block, 0, st>>>(a);
+  else if (maxc <= 5) launch_pdl(vq_act_quant_kernel<5, LN>, grid, block, 0, st, a);
+  else if (maxc <= 9) launch_pdl(vq_act_quant_kernel<9, LN>, grid, block, 0, st, a);
+  else if (maxc <= 18) launch_pdl(vq_act_quant_kernel<18, LN>, grid, block, 0, st, a);
+  else if (maxc <= 36) launch_pdl(vq_act_quant_kernel<36, LN>, grid, block, 0, st, a);
   else return VQ_ERR_UNSUPPORTED;
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
@@ -555,6 +557,7 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(256) vq_prep_weight_kernel(const PrepArgs a) {
+  grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= a.N) return;
@@ -674,7 +677,7 @@ extern "C" int vq_prep_weight(const void* w, const void* delta, const void* zp, 
   a.codes = codes;
   a.col = col;
   const int warps = 8;
-  vq_prep_weight_kernel<<<(N + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(vq_prep_weight_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), 0, static_cast<cudaStream_t>(stream), a);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 

@@ -304,7 +304,12 @@ class STDiT(nn.Module):
         if segments is None:
             segments = self.kv_segments(y_lens, x.device)
         x = eng.run(x, y, t0, y_lens, segments)
-        x = self.final_layer(x, t)
+        # final layer (FP, remain_fp.txt): LayerNorm + modulate in one pass of the fused kernel (its codes are unused)
+        fl = self.final_layer
+        shift, scale = (fl.scale_shift_table[None] + t[:, None]).chunk(2, dim=1)
+        B, _, C = x.shape
+        _, xm = ops.ln_modulate_act_quant(x, shift.reshape(B, C).contiguous(), scale.reshape(B, C).contiguous(), want_y=True)
+        x = fl.linear(xm)
         return self.unpatchify(x).to(torch.float32)
 
 
