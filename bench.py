@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--depth", type=int, default=DEPTH, help="debug only: fewer blocks (result is then NOT the metric)")
     ap.add_argument("--no-graph", action="store_true", help="debug: eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg-mode", default="stacked", choices=["stacked", "split"],
+                    help="cfg_split's cond / uncond forwards as one stacked launch sequence (default) or two calls")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -200,10 +202,14 @@ def main():
     h_t = torch.zeros(1).pin_memory()
     h_coef = torch.zeros(4).pin_memory()
     h_out = torch.empty(1, 4, T_FRAMES, 64, 64).pin_memory()
-    d_z, d_yc, d_yu = h_z.to(dev), h_yc.to(dev), h_yu.to(dev)
+    d_z = h_z.to(dev)
+    d_y = torch.cat([h_yc, h_yu]).to(dev)                 # cond | uncond captions, one stacked device buffer
+    d_yc, d_yu = d_y[:1], d_y[1:]
     d_t, d_coef = torch.zeros(1, device=dev), torch.zeros(4, device=dev)
-    plan = model.mask_select_plan(mask.to(dev))
+    plan = model.mask_select_plan(mask.repeat(2, 1).to(dev))
     segments = model.kv_segments(plan[1], dev)
+    plan1 = model.mask_select_plan(mask.to(dev))
+    segments1 = model.kv_segments(plan1[1], dev)
     sched = [(ddim.model_timestep(i), ddim.coefficients(i, "cpu")) for i in range(ddim.num_timesteps)]
 
     def set_step(i):
@@ -213,9 +219,16 @@ def main():
         return i
 
     def step_device():
-        """The denoise step on device-resident inputs (iddpm forward_with_cfg + ddim_sample, cfg_split)."""
-        out_c = model.forward_fused(d_z, d_t, d_yc, plan=plan, segments=segments)
-        out_u = model.forward_fused(d_z, d_t, d_yu, plan=plan, segments=segments)
+        """The denoise step on device-resident inputs (iddpm forward_with_cfg + ddim_sample, cfg_split): the cond and
+        uncond forwards of cfg_split run as one stacked launch sequence with un-pooled statistics (== two batch-1 calls,
+        tests/test_gpu_stdit.py::test_stacked_cfg_split_equals_two_separate_forwards)."""
+        if args.cfg_mode == "stacked":
+            out = model.forward_fused(torch.cat([d_z, d_z]), d_t.expand(2), d_y, plan=plan, segments=segments,
+                                      independent=True)
+            out_c, out_u = out[:1], out[1:]
+        else:
+            out_c = model.forward_fused(d_z, d_t, d_yc, plan=plan1, segments=segments1)
+            out_u = model.forward_fused(d_z, d_t, d_yu, plan=plan1, segments=segments1)
         out = SpacedDDIM.cfg_combine(out_c, out_u, ddim.cfg_scale)
         return SpacedDDIM.ddim_update(d_z, out, d_coef)
 
@@ -330,9 +343,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "STDiT-XL/2 16x512x512 (T=16,S=1024 -> 16384 tokens, 28 blocks) W8A8 per-token "
-                                   "dynamic (w8a8_dynamic.yaml), cfg_split: 2 forwards + CFG + DDIM per step",
+                                   "dynamic (w8a8_dynamic.yaml), cfg_split: cond + uncond forwards (one stacked launch sequence, "
+                                   "un-pooled statistics == two batch-1 calls) + CFG + DDIM per step",
                        "samples_per_gpu": 1, "parallelism": f"sample-sharded x{world} (no data-path collective)",
-                       "cuda_graph": graph is not None, "depth": args.depth,
+                       "cuda_graph": graph is not None, "depth": args.depth, "cfg_mode": args.cfg_mode,
                        "l2": "working set per step (0.74 GB weight codes + >1 GB activations) exceeds the 126 MB L2",
                        "linear_TOP_per_step": 2 * linear_ops_per_forward() / 1e12 * args.depth / DEPTH},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -66,6 +66,14 @@ int vq_prep_weight(const void* w, const void* delta, const void* zp, const void*
 int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, int64_t ld, const void* smooth,
                  int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream);
 
+/* nn.GELU(approximate="tanh") + (a1), one pass: the activation between Mlp.fc1 and Mlp.fc2 (reference
+ * opensora/models/stdit/stdit.py:109-111 timm Mlp with approx_gelu; PixArt_blocks / PixArtMS.py:60 likewise) applied to
+ * the fp16 fc1 output x on its way into fc2's DynamicActQuantizer (quant_layer.py:137-140: smooth division, then
+ * quantise). Same arguments and outputs as vq_act_quant; the statistics and codes are those of gelu(x) (/ smooth).   */
+int vq_gelu_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, int64_t ld, const void* smooth,
+                      int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status,
+                      void* stream);
+
 /* (a1) on a head-major attention output x fp16 [G * rows / S, H, S, head_dim] (what fused attention kernels emit):
  * same statistics and codes as vq_act_quant on the token-major view "(n H S D) -> (n S) (H D)", without the copy the
  * reference pays (blocks.py:189-191 transpose + reshape). head_dim = 72, H * head_dim = 1152.                      */
@@ -73,11 +81,16 @@ int vq_act_quant_heads(const void* x, int G, int rows, int H, int S, int head_di
                        void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream);
 
 /* LayerNorm(eps=1e-6, no affine) + t2i_modulate (blocks.py:51: x*(1+scale)+shift) + (a1), one pass.
- * x: fp16 [G*rows, K]; shift, scale: fp16 [G, K] (per sample); smooth: fp16 [K] or NULL (divides the modulated
- * tensor, quant_layer.py:140); y_out (optional, may be NULL): fp16 tensor the quantiser saw.                        */
+ * x: fp16 [G*rows, K]; shift, scale: fp16 [G * rows / rows_per_mod, K] — row (g, r) is modulated by vector
+ * (g * rows + r) / rows_per_mod.  rows_per_mod == rows: one vector per pooled batch entry (the reference's batched
+ * forward, statistics pooled over G, quirk Q1).  G == 1 with rows_per_mod < rows: several samples stacked along the
+ * rows, each with its own modulation and its own un-pooled statistics == the reference's cfg_split=True, which runs
+ * the cond / uncond halves as separate batch-1 forwards (qdiff/models/quant_model.py cfg_split branch).
+ * smooth: fp16 [K] or NULL (divides the modulated tensor, quant_layer.py:140); y_out (optional, may be NULL): the
+ * fp16 tensor the quantiser saw.                                                                                     */
 int vq_ln_modulate_act_quant(const void* x, const void* shift, const void* scale, const void* smooth, int G, int rows,
-                             int K, int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp, int32_t* rowsum,
-                             uint32_t* status, void* stream);
+                             int K, int rows_per_mod, int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp,
+                             int32_t* rowsum, uint32_t* status, void* stream);
 
 /* (a3-a7) integer GEMM + dequant epilogue on prepared operands. a_codes u8 [M,K]; a_delta/a_zp fp16 [rows] indexed
  * by (m % a_rows_period) — pass a_rows_period = M when every row has its own scale; w_codes u8 [N,K]; out fp16

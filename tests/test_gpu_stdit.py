@@ -151,6 +151,30 @@ def test_w8a8_end_to_end_is_inside_the_simulation_noise_band(qnn_gpu, small):  #
         assert r[1] <= 1.25 * band[1] and r[1] <= 5e-3, (r, band)
 
 
+def test_stacked_cfg_split_equals_two_separate_forwards(qnn_gpu, small):  # noqa: F811
+    """cfg_split=True (iddpm/__init__.py:156-157): the reference calls the model twice per step (cond / uncond, batch 1
+    each).  forward_fused(..., independent=True) runs both as ONE stacked launch sequence with un-pooled statistics;
+    every kernel is row- / sample-local, so the result must equal the two separate calls (bit-exact unless the library
+    attention picks another tiling for the larger batch — hence the tiny tolerance)."""
+    qnn, model = qnn_gpu
+    _set_w8a8(qnn)
+    x, t, y, mask = _inputs(small)
+    torch.manual_seed(3)
+    y_u = (torch.randn_like(y.float()) * y.float().std()).half()          # a different "null" caption
+    with torch.no_grad():
+        qnn.set_timestep_id_for_quantlayer(float(small["t"][0]))
+        o_c = model.forward_fused(x, t, y, mask=mask)
+        o_u = model.forward_fused(x, t, y_u, mask=mask)
+        both = model.forward_fused(torch.cat([x, x]), torch.cat([t, t]), torch.cat([y, y_u]), mask=mask, independent=True)
+        pooled = model.forward_fused(torch.cat([x, x]), torch.cat([t, t]), torch.cat([y, y_u]), mask=mask)
+    sep = torch.cat([o_c, o_u]).cpu().numpy()
+    inf, l2 = _rel(both.cpu().numpy(), sep)
+    print("stacked independent vs two calls: %.3e %.3e; exact=%s" % (inf, l2, bool((both.cpu().numpy() == sep).all())))
+    assert l2 <= 1e-4 and inf <= 1e-3, (inf, l2)
+    # the reference's own batch-2 forward pools the statistics over the pair (quirk Q1): a different function
+    assert _rel(pooled.cpu().numpy(), sep)[1] > 10 * max(l2, 1e-6)
+
+
 def test_w8a8_against_reference_run_on_cpu(qnn_gpu, small):  # noqa: F811
     """Against the golden output of the unmodified reference executed on CPU (fp16). The two runs differ in back end
     (CPU eager attention / CPU LayerNorm / CPU half GEMM vs GPU), whose fp16 noise alone is measured by the fp16-graph

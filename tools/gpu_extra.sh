@@ -1,4 +1,4 @@
-VQ_STORE_POLICY=normal timeout 120 tools/gemm_selftest --time > gpurun_out/selftest_normal.log 2>&1
-timeout 300 python tools/prof_kernels.py > gpurun_out/prof_kernels.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:vq_attn_cross -s 2 -c 1 -f -o gpurun_out/cross python tools/prof_kernels.py > gpurun_out/ncu_cross.log 2>&1
-grep -E "case M=16384|time|mainloop|loads\+" gpurun_out/selftest_normal.log | tail -30; cat gpurun_out/prof_kernels.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --cfg-mode split > gpurun_out/bench_split.log 2>&1
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --cfg-mode stacked > gpurun_out/bench_stacked2.log 2>&1
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --cfg-mode split > gpurun_out/bench_split2.log 2>&1
+for f in bench_split bench_stacked2 bench_split2; do tail -1 gpurun_out/$f.log | cut -c1-200; done

@@ -52,6 +52,7 @@ xr = x.view(M, C)
 timeit("act_quant K=1152", lambda: ops.act_quant(x, out=a), algo_bytes=M * C * 3 + 8 * M)
 timeit("ln_modulate_act_quant K=1152", lambda: ops.ln_modulate_act_quant(x, shift, scale, out=a), algo_bytes=M * C * 3)
 timeit("act_quant K=4608", lambda: ops.act_quant(h, out=a4), algo_bytes=M * 4 * C * 3)
+timeit("gelu + act_quant K=4608", lambda: ops.act_quant(h, out=a4, gelu=True), algo_bytes=M * 4 * C * 3)
 o1 = torch.empty(M, C, device=dev, dtype=torch.float16)
 o3 = torch.empty(M, 3 * C, device=dev, dtype=torch.float16)
 o4 = torch.empty(M, 4 * C, device=dev, dtype=torch.float16)

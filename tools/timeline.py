@@ -37,14 +37,14 @@ def main():
     mask[0, :109] = 1
     d_t = torch.full((1,), float(ddim.model_timestep(ddim.num_timesteps - 1)), device=dev)
     d_coef = ddim.coefficients(ddim.num_timesteps - 1, "cpu").to(dev)
-    plan = model.mask_select_plan(mask.to(dev))
+    plan = model.mask_select_plan(mask.repeat(2, 1).to(dev))
     segments = model.kv_segments(plan[1], dev)
     qnn.set_timestep_id_for_quantlayer(float(d_t[0]))
 
     def step():
-        oc = model.forward_fused(d_z, d_t, d_yc, plan=plan, segments=segments)
-        ou = model.forward_fused(d_z, d_t, d_yu, plan=plan, segments=segments)
-        return SpacedDDIM.ddim_update(d_z, SpacedDDIM.cfg_combine(oc, ou, ddim.cfg_scale), d_coef)
+        o = model.forward_fused(torch.cat([d_z, d_z]), d_t.expand(2), torch.cat([d_yc, d_yu]), plan=plan,
+                                segments=segments, independent=True)
+        return SpacedDDIM.ddim_update(d_z, SpacedDDIM.cfg_combine(o[:1], o[1:], ddim.cfg_scale), d_coef)
 
     for _ in range(2):
         step()

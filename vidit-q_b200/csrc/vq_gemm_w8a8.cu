@@ -76,25 +76,6 @@ struct GemmArgs {
   uint64_t store_policy;    // L2 cache policy of the output stores (kEvictFirst unless VQ_STORE_POLICY=normal)
 };
 
-// nn.GELU(approximate="tanh") on a pair: 0.5 x (1 + tanh(u)) == x / (1 + exp(-2u)), u = k0 x (1 + k1 x^2).
-// MUFU.EX2 / MUFU.RCP (~1e-7 relative) are far below one fp16 ulp; everything else is packed fp32 (FFMA2 / FMUL2).
-__device__ __forceinline__ float2 gelu_tanh_pair(float2 x) {
-  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
-  const float2 x2 = __fmul2_rn(x, x);
-  const float2 a = __ffma2_rn(x2, make_float2(k0k1, k0k1), make_float2(k0, k0));
-  const float2 u = __fmul2_rn(x, a);
-  const float c = -2.0f * 1.4426950408889634f;   // exp(-2u) = 2^(c u)
-  const float2 w = __fmul2_rn(u, make_float2(c, c));
-  float e0, e1;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w.x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w.y));
-  const float2 d = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
-  float r0, r1;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
-  return __fmul2_rn(x, make_float2(r0, r1));
-}
-
 constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (measures the TMA->MMA pipeline alone)
 constexpr int VQ_EPI_DEBUG_LOADS = 5;     // internal: + TMEM loads (no math, no stores)
 constexpr int VQ_EPI_DEBUG_MATH = 6;      // internal: + dequant math (no staging / stores)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/viditq_b200.h"
@@ -26,6 +27,25 @@ inline bool pdl_enabled() {
 }
 
 #ifdef __CUDACC__
+// nn.GELU(approximate="tanh") on a pair: 0.5 x (1 + tanh(u)) == x / (1 + exp(-2u)), u = k0 x (1 + k1 x^2).
+// MUFU.EX2 / MUFU.RCP (~1e-7 relative) are far below one fp16 ulp; everything else is packed fp32 (FFMA2 / FMUL2).
+__device__ __forceinline__ float2 gelu_tanh_pair(float2 x) {
+  // exp(-2u) = 2^(c u), c = -2 log2(e), folded into the cubic's coefficients: w = x (A + B x^2)
+  const float A = -2.0f * 1.4426950408889634f * 0.7978845608028654f;
+  const float B = -2.0f * 1.4426950408889634f * 0.7978845608028654f * 0.044715f;
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 a = __ffma2_rn(x2, make_float2(B, B), make_float2(A, A));
+  const float2 w = __fmul2_rn(x, a);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w.y));
+  const float2 d = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+  return __fmul2_rn(x, make_float2(r0, r1));
+}
+
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // first statements of every kernel, executed by every thread (a CTA that skipped the wait could let the grid finish,

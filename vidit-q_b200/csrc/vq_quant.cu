@@ -374,6 +374,7 @@ struct ActQuantArgs {
   const __half* smooth;  // [K] or null
   const __half* shift;   // [G,K] (LN mode)
   const __half* scale;   // [G,K] (LN mode)
+  int rows_per_mod;      // LN mode: row (g, r) uses modulation vector (g * rows + r) / rows_per_mod
   __half* y_out;         // optional [G*rows, K] transformed input (LN mode)
   int head_S;            // > 0: x is head-major [G*rows / head_S, H, head_S, 72] (attention output), H = K / 72
   float qmax;
@@ -384,7 +385,30 @@ struct ActQuantArgs {
   uint32_t* status;
 };
 
-template <int MAXC, bool LN>
+// x <- h(gelu_tanh(x)): the activation between fc1 and fc2 (timm Mlp.act, nn.GELU(approximate="tanh") on the fp16 fc1
+// output), applied while the row is in registers on its way to fc2's quantiser — the fc1 GEMM then runs its plain
+// bias epilogue (the GELU epilogue made that GEMM epilogue-bound) and this HBM-bound pass absorbs the MUFU work.
+template <int MAXC>
+__device__ __forceinline__ void apply_gelu(RowRegs<MAXC>& r, int nchunk, int lane) {
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    int ci = lane + 32 * i;
+    if (ci < nchunk) {
+      __half2* x = reinterpret_cast<__half2*>(&r.c[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 g = gelu_tanh_pair(__half22float2(x[e]));
+        x[e] = __floats2half2_rn(g.x, g.y);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ size_t mod_offset(const ActQuantArgs& a, int g, int r) {
+  return static_cast<size_t>((static_cast<long long>(g) * a.rows + r) / a.rows_per_mod) * a.K;
+}
+
+template <int MAXC, bool LN, bool GELU = false>
 __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a) {
   grid_dep_sync();
   const int lane = threadIdx.x & 31;
@@ -396,7 +420,7 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
   for (int g = 0; g < a.G; ++g) {
     load_row<MAXC>(regs, a.x + g * a.group_stride + r * a.ld, nchunk, lane);
     if (LN) {
-      apply_ln_modulate<MAXC>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K,
+      apply_ln_modulate<MAXC>(regs, a.shift + mod_offset(a, g, r), a.scale + mod_offset(a, g, r),
                               a.K, nchunk, lane);
       if (a.smooth) apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
       if (a.y_out) {
@@ -407,8 +431,9 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
           if (ci < nchunk) reinterpret_cast<uint4*>(yrow)[ci] = regs.c[i];
         }
       }
-    } else if (a.smooth) {
-      apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
+    } else {
+      if (GELU) apply_gelu<MAXC>(regs, nchunk, lane);
+      if (a.smooth) apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
     }
     row_minmax<MAXC>(regs, nchunk, lane, mn2, mx2);
   }
@@ -425,11 +450,12 @@ __global__ void __launch_bounds__(256) vq_act_quant_kernel(const ActQuantArgs a)
     if (a.G > 1) {  // G == 1: the transformed row is still in registers
       load_row<MAXC>(regs, a.x + g * a.group_stride + r * a.ld, nchunk, lane);
       if (LN) {
-        apply_ln_modulate<MAXC>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K,
+        apply_ln_modulate<MAXC>(regs, a.shift + mod_offset(a, g, r), a.scale + mod_offset(a, g, r),
                                 a.K, nchunk, lane);
         if (a.smooth) apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
-      } else if (a.smooth) {
-        apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
+      } else {
+        if (GELU) apply_gelu<MAXC>(regs, nchunk, lane);
+        if (a.smooth) apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
       }
     }
     const size_t orow = static_cast<size_t>(g) * a.rows + r;
@@ -454,7 +480,7 @@ __device__ __forceinline__ void uload_any(UnitRegs<U>& regs, const ActQuantArgs&
 template <int U, bool LN>
 __device__ __forceinline__ void utransform(UnitRegs<U>& regs, const ActQuantArgs& a, int g, int r, int lane) {
   if (LN) {
-    uapply_ln_modulate<U>(regs, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K, lane);
+    uapply_ln_modulate<U>(regs, a.shift + mod_offset(a, g, r), a.scale + mod_offset(a, g, r), a.K, lane);
     if (a.smooth) uapply_smooth<U>(regs, a.smooth, lane);
     if (a.y_out) {
       uint2* yrow = reinterpret_cast<uint2*>(a.y_out + (static_cast<size_t>(g) * a.rows + r) * a.K);
@@ -505,7 +531,7 @@ __global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuan
         uload_any<U, HEADS>(regs, a, g, r, lane);
         UnitRegs<U>& rr = regs;
         if (LN) {
-          uapply_ln_modulate<U>(rr, a.shift + static_cast<size_t>(g) * a.K, a.scale + static_cast<size_t>(g) * a.K, a.K, lane);
+          uapply_ln_modulate<U>(rr, a.shift + mod_offset(a, g, r), a.scale + mod_offset(a, g, r), a.K, lane);
           if (a.smooth) uapply_smooth<U>(rr, a.smooth, lane);
         } else if (a.smooth) {
           uapply_smooth<U>(rr, a.smooth, lane);
@@ -520,12 +546,96 @@ __global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuan
   }
 }
 
-template <bool LN>
+// K = 1152 * WPR (2304, 4608: the Mlp hidden width), G == 1: one warp per 1152-column SEGMENT of a row, so a lane holds 18
+// registers of row data instead of 72 and five 8-warp blocks fit an SM; the WPR warps of a row combine their min / max
+// and their code sums through shared memory (two block barriers per row batch).  GELU = true applies
+// nn.GELU(approximate="tanh") to the loaded fp16 values first (MUFU-heavy: the occupancy is what hides it).
+template <int U>
+__device__ __forceinline__ void uapply_gelu(UnitRegs<U>& r) {
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    __half2* x = reinterpret_cast<__half2*>(&r.u[i]);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float2 g = gelu_tanh_pair(__half22float2(x[e]));
+      x[e] = __floats2half2_rn(g.x, g.y);
+    }
+  }
+}
+
+template <int WPR, bool GELU>
+__global__ void __launch_bounds__(256) vq_act_quant_seg_kernel(const ActQuantArgs a) {
+  grid_dep_sync();
+  constexpr int RPB = 8 / WPR;   // rows per block
+  __shared__ float s_mn[8], s_mx[8];
+  __shared__ int s_sum[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rl = warp / WPR, seg = warp - rl * WPR;
+  const int r = blockIdx.x * RPB + rl;
+  const bool ok = r < a.rows;
+  UnitRegs<9> regs;
+  __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
+  if (ok) {
+    uload_row<9>(regs, a.x + static_cast<size_t>(r) * a.ld + seg * 1152, lane);
+    if (GELU) uapply_gelu<9>(regs);
+    if (a.smooth) uapply_smooth<9>(regs, a.smooth + seg * 1152, lane);
+    urow_minmax<9>(regs, mn2, mx2);
+  }
+  float mn, mx;
+  warp_minmax(mn2, mx2, mn, mx);
+  if (lane == 0) {
+    s_mn[warp] = mn;
+    s_mx[warp] = mx;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < WPR; ++j) {
+    mn = fminf(mn, s_mn[rl * WPR + j]);
+    mx = fmaxf(mx, s_mx[rl * WPR + j]);
+  }
+  const RowStats st = make_stats(mn, mx, a.qmax);
+  const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
+  if (ok) {
+    if (seg == 0 && lane == 0) {
+      a.delta[r] = __float2half_rn(st.delta);
+      a.zp[r] = __float2half_rn(st.zp);
+      if (st.degenerate && a.status) atomicOr(a.status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
+    }
+    int sum = uquant_store_row<9>(regs, a.codes + static_cast<size_t>(r) * a.K + seg * 1152, lane, qc);
+    sum = warp_sum_i(sum);
+    if (lane == 0) s_sum[warp] = sum;
+  }
+  __syncthreads();
+  if (ok && seg == 0 && lane == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int j = 0; j < WPR; ++j) tot += s_sum[rl * WPR + j];
+    a.rowsum[r] = tot;
+  }
+}
+
+template <bool LN, bool GELU = false>
 static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
   const int nchunk = a.K >> 3;
   const int maxc = (nchunk + 31) / 32;
   const int warps = 8;
   dim3 grid((a.rows + warps - 1) / warps), block(warps * 32);
+  if (!LN && a.G == 1 && a.head_S == 0 && (a.K == 4608 || a.K == 2304 || (GELU && a.K == 1152))) {
+    const int wpr = a.K / 1152;
+    dim3 g((a.rows * wpr + 7) / 8);
+    if (wpr == 4) launch_pdl(vq_act_quant_seg_kernel<4, GELU>, g, block, 0, st, a);
+    else if (wpr == 2) launch_pdl(vq_act_quant_seg_kernel<2, GELU>, g, block, 0, st, a);
+    else launch_pdl(vq_act_quant_seg_kernel<1, GELU>, g, block, 0, st, a);
+    return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+  }
+  if (GELU) {   // other K (or pooled batches): chunk-mapped kernel
+    if (maxc <= 5) launch_pdl(vq_act_quant_kernel<5, false, true>, grid, block, 0, st, a);
+    else if (maxc <= 9) launch_pdl(vq_act_quant_kernel<9, false, true>, grid, block, 0, st, a);
+    else if (maxc <= 18) launch_pdl(vq_act_quant_kernel<18, false, true>, grid, block, 0, st, a);
+    else if (maxc <= 36) launch_pdl(vq_act_quant_kernel<36, false, true>, grid, block, 0, st, a);
+    else return VQ_ERR_UNSUPPORTED;
+    return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+  }
   // K = 1152 is 4.5 sixteen-byte chunks per lane (divergent in the chunk mapping) but exactly 9 eight-byte units;
   // K = 4608 is 18 full chunk rounds, where the chunk mapping is already branch-free and lighter on registers.
   if (a.K == 9 * 128) {
@@ -617,6 +727,26 @@ extern "C" int vq_act_quant(const void* x, int G, int rows, int K, int64_t group
   return launch_act_quant<false>(a, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int vq_gelu_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, int64_t ld,
+                                 const void* smooth, int n_bits, uint8_t* codes, void* delta, void* zp,
+                                 int32_t* rowsum, uint32_t* status, void* stream) {
+  using namespace vq;
+  if (!x || !codes || !delta || !zp || !rowsum || G <= 0 || rows <= 0 || K <= 0) return VQ_ERR_ARG;
+  if ((K % 8) != 0 || (ld % 8) != 0 || (group_stride % 8) != 0 || n_bits < 2 || n_bits > 8) return VQ_ERR_ARG;
+  ActQuantArgs a{};
+  a.x = static_cast<const __half*>(x);
+  a.G = G; a.rows = rows; a.K = K;
+  a.group_stride = group_stride; a.ld = ld;
+  a.smooth = static_cast<const __half*>(smooth);
+  a.qmax = static_cast<float>((1 << n_bits) - 1);
+  a.codes = codes;
+  a.delta = static_cast<__half*>(delta);
+  a.zp = static_cast<__half*>(zp);
+  a.rowsum = rowsum;
+  a.status = status;
+  return launch_act_quant<false, true>(a, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vq_act_quant_heads(const void* x, int G, int rows, int H, int S, int head_dim, int n_bits,
                                   uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status,
                                   void* stream) {
@@ -638,11 +768,12 @@ extern "C" int vq_act_quant_heads(const void* x, int G, int rows, int H, int S, 
 }
 
 extern "C" int vq_ln_modulate_act_quant(const void* x, const void* shift, const void* scale, const void* smooth, int G,
-                                        int rows, int K, int n_bits, void* y_out, uint8_t* codes, void* delta, void* zp,
-                                        int32_t* rowsum, uint32_t* status, void* stream) {
+                                        int rows, int K, int rows_per_mod, int n_bits, void* y_out, uint8_t* codes,
+                                        void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream) {
   using namespace vq;
   if (!x || !shift || !scale || !codes || !delta || !zp || !rowsum || G <= 0 || rows <= 0 || K <= 0)
     return VQ_ERR_ARG;
+  if (rows_per_mod <= 0 || rows_per_mod > rows || (rows % rows_per_mod) != 0) return VQ_ERR_ARG;
   if ((K % 8) != 0 || n_bits < 2 || n_bits > 8) return VQ_ERR_ARG;
   ActQuantArgs a{};
   a.x = static_cast<const __half*>(x);
@@ -651,6 +782,7 @@ extern "C" int vq_ln_modulate_act_quant(const void* x, const void* shift, const 
   a.shift = static_cast<const __half*>(shift);
   a.scale = static_cast<const __half*>(scale);
   a.smooth = static_cast<const __half*>(smooth);
+  a.rows_per_mod = rows_per_mod;
   a.y_out = static_cast<__half*>(y_out);
   a.qmax = static_cast<float>((1 << n_bits) - 1);
   a.codes = codes;

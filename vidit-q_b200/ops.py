@@ -104,16 +104,18 @@ def _alloc_act(G, rows, K, device):
                     torch.empty(G * rows, dtype=torch.int32, device=device), G, rows, K)
 
 
-def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None) -> ActCodes:
-    """x: fp16 [G, rows, K] (reference layout [BS, n_token, C]); statistics per token pooled over G."""
+def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None, gelu=False) -> ActCodes:
+    """x: fp16 [G, rows, K] (reference layout [BS, n_token, C]); statistics per token pooled over G.
+    gelu=True quantises gelu_tanh(x) instead (the Mlp activation fused in front of fc2's quantiser)."""
     _need_cuda_f16(x, "x")
     G, rows, K = x.shape
     a = out if out is not None else _alloc_act(G, rows, K, x.device)
     if smooth is not None:
         _need_cuda_f16(smooth, "smooth")
-    rc = _lib.lib().vq_act_quant(_ptr(x), G, rows, K, rows * K, K, _ptr(smooth), n_bits, _ptr(a.codes), _ptr(a.delta),
-                                 _ptr(a.zp), _ptr(a.rowsum), _ptr(status_word(x.device)), _stream())
-    _lib.check(rc, "vq_act_quant")
+    fn = _lib.lib().vq_gelu_act_quant if gelu else _lib.lib().vq_act_quant
+    rc = fn(_ptr(x), G, rows, K, rows * K, K, _ptr(smooth), n_bits, _ptr(a.codes), _ptr(a.delta),
+            _ptr(a.zp), _ptr(a.rowsum), _ptr(status_word(x.device)), _stream())
+    _lib.check(rc, "vq_gelu_act_quant" if gelu else "vq_act_quant")
     _count()
     return a
 
@@ -133,17 +135,24 @@ def act_quant_heads(x, G, rows, S, n_bits=8, out: Optional[ActCodes] = None) -> 
     return a
 
 
-def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional[ActCodes] = None, smooth=None):
-    """x: fp16 [G, rows, K]; shift/scale: fp16 [G, K]; smooth: fp16 [K] or None. Returns (ActCodes, y or None)."""
+def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional[ActCodes] = None, smooth=None,
+                          rows_per_mod=None):
+    """x: fp16 [G, rows, K]; shift/scale: fp16 [G * rows / rows_per_mod, K] (default one per batch entry); smooth: fp16
+    [K] or None. rows_per_mod < rows (G must be 1): samples stacked along the rows, un-pooled statistics (cfg_split).
+    Returns (ActCodes, y or None)."""
     _need_cuda_f16(x, "x")
     _need_cuda_f16(shift, "shift")
     _need_cuda_f16(scale, "scale")
     G, rows, K = x.shape
+    rpm = rows if rows_per_mod is None else int(rows_per_mod)
+    if shift.numel() != (G * rows // rpm) * K or scale.numel() != shift.numel() or (rpm != rows and G != 1):
+        raise _lib.VqError(f"ln_modulate_act_quant: shift/scale of {shift.numel()} elements do not match G={G} "
+                           f"rows={rows} rows_per_mod={rpm} K={K}")
     a = out if out is not None else _alloc_act(G, rows, K, x.device)
     y = torch.empty_like(x) if want_y else None
     if smooth is not None:
         _need_cuda_f16(smooth, "smooth")
-    rc = _lib.lib().vq_ln_modulate_act_quant(_ptr(x), _ptr(shift), _ptr(scale), _ptr(smooth), G, rows, K, n_bits, _ptr(y),
+    rc = _lib.lib().vq_ln_modulate_act_quant(_ptr(x), _ptr(shift), _ptr(scale), _ptr(smooth), G, rows, K, rpm, n_bits, _ptr(y),
                                              _ptr(a.codes), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum),
                                              _ptr(status_word(x.device)), _stream())
     _lib.check(rc, "vq_ln_modulate_act_quant")

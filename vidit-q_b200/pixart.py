@@ -171,8 +171,8 @@ class PixArtMS(nn.Module):
             ops.gemm_w8a8(ca.proj.quantize_input(o), ca.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr,
                           gate=ones, rows_per_gate=M, out=xr)
             a, _ = ops.ln_modulate_act_quant(x, shift_mlp, scale_mlp, n_bits=nb)
-            h = ops.gemm_w8a8(a, blk.mlp.fc1.prepared_weight(), epi=ops.VQ_EPI_GELU_TANH).view(B, N, -1)
-            ops.gemm_w8a8(blk.mlp.fc2.quantize_input(h), blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
+            h = ops.gemm_w8a8(a, blk.mlp.fc1.prepared_weight()).view(B, N, -1)   # GELU fused into fc2's quantise pass
+            ops.gemm_w8a8(blk.mlp.fc2.quantize_input(h, gelu=True), blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
                           res=xr, gate=gate_mlp, rows_per_gate=N, out=xr)
         return self.unpatchify(self.final_layer(x, t))
 

@@ -214,15 +214,21 @@ class QuantLayer(nn.Module):
             raise NotImplementedError("fused path supports dynamic per-token asymmetric activations, <= 8 bits "
                                       "(the ViDiT-Q W8A8 / W4A8 configs)")
 
-    def quantize_input(self, input):
-        """Per-token dynamic activation quantisation of a [*, n, C] fp16 tensor -> ops.ActCodes."""
+    def quantize_input(self, input, gelu=False, independent=False):
+        """Per-token dynamic activation quantisation of a [*, n, C] fp16 tensor -> ops.ActCodes.
+        gelu=True: `input` is the pre-activation of the preceding nn.GELU(approximate="tanh"); the activation is applied
+        inside the quantise pass (fused schedules only — the module graph applies GELU itself).
+        independent=True: the batch entries are separate forward calls stacked along the batch (cfg_split's cond / uncond
+        halves at one prompt each): nothing is pooled, every row gets its own statistics."""
         self._check_act_quantizer()
         G, rows = self._pool_view(input)
+        if independent:
+            G, rows = 1, G * rows
         x = input.reshape(G, rows, input.shape[-1])
         if not x.is_contiguous():
             x = x.contiguous()
         pw = self.prepared_weight()
-        return ops.act_quant(x, n_bits=self.act_quantizer.n_bits, smooth=getattr(pw, "smooth", None))
+        return ops.act_quant(x, n_bits=self.act_quantizer.n_bits, smooth=getattr(pw, "smooth", None), gelu=gelu)
 
     # -- forward ---------------------------------------------------------------------------------------------------
     def forward(self, input: torch.Tensor, scale: float = 1.0, split: int = 0, smooth_quant_enable: bool = False):

@@ -74,11 +74,18 @@ class SpacedDDIM:
         eps2 = (coef[0] * x - pred_xstart) / coef[1]
         return pred_xstart * coef[2] + coef[3] * eps2
 
-    def step(self, model_forward, x, i, y_cond, y_uncond, mask):
-        """One denoising step on latent x [n, C, T, H, W] (cfg_split: two forwards of batch n)."""
+    def step(self, model_forward, x, i, y_cond, y_uncond, mask, stacked_forward=None):
+        """One denoising step on latent x [n, C, T, H, W] (cfg_split: two forwards of batch n).
+        stacked_forward(x2, t2, y2, mask=) — e.g. functools.partial(STDiT.forward_fused, independent=True) — runs the
+        cond and uncond calls as one stacked launch sequence; only used for n == 1, where "statistics pooled over the
+        batch of each call" (quirk Q1) and "every row on its own" are the same thing."""
         t = torch.full((x.shape[0],), self.model_timestep(i), device=x.device)
-        out_c = model_forward(x, t, y_cond, mask=mask)
-        out_u = model_forward(x, t, y_uncond, mask=mask)
+        if stacked_forward is not None and x.shape[0] == 1:
+            out = stacked_forward(torch.cat([x, x]), torch.cat([t, t]), torch.cat([y_cond, y_uncond]), mask=mask)
+            out_c, out_u = out[:1], out[1:]
+        else:
+            out_c = model_forward(x, t, y_cond, mask=mask)
+            out_u = model_forward(x, t, y_uncond, mask=mask)
         out = self.cfg_combine(out_c, out_u, self.cfg_scale)
         return self.ddim_update(x, out, self.coefficients(i, x.device))
 
@@ -124,7 +131,8 @@ class TimestepMixedPrecision:
         return True
 
 
-def ddim_sample_loop(ddim: SpacedDDIM, model_forward, z, y_cond, y_uncond, mask, qnn=None, on_step=None):
+def ddim_sample_loop(ddim: SpacedDDIM, model_forward, z, y_cond, y_uncond, mask, qnn=None, on_step=None,
+                     stacked_forward=None):
     """iddpm IDDPM.sample(..., 'ddim') for cfg_split models: all steps from num_timesteps-1 down to 0."""
     mp = TimestepMixedPrecision(qnn) if qnn is not None else None
     for i in range(ddim.num_timesteps - 1, -1, -1):
@@ -132,7 +140,7 @@ def ddim_sample_loop(ddim: SpacedDDIM, model_forward, z, y_cond, y_uncond, mask,
             mp.before_step(i)
         if qnn is not None:
             qnn.set_timestep_id_for_quantlayer(ddim.model_timestep(i))
-        z = ddim.step(model_forward, z, i, y_cond, y_uncond, mask)
+        z = ddim.step(model_forward, z, i, y_cond, y_uncond, mask, stacked_forward=stacked_forward)
         if on_step is not None:
             on_step(i, z)
     return z

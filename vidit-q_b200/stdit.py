@@ -295,15 +295,19 @@ class STDiT(nn.Module):
         return self.unpatchify(x).to(torch.float32)
 
     # ---- fused B200 schedule ----------------------------------------------------------------------------------------
-    def forward_fused(self, x, timestep, y, mask=None, plan=None, segments=None):
-        """plan / segments: host-precomputed mask_select_plan(mask) and kv_segments(y_lens) make the call sync-free."""
+    def forward_fused(self, x, timestep, y, mask=None, plan=None, segments=None, independent=False):
+        """plan / segments: host-precomputed mask_select_plan(mask) and kv_segments(y_lens) make the call sync-free.
+        independent=True: the batch entries are SEPARATE reference forward calls stacked into one launch sequence — the
+        cond / uncond halves of cfg_split=True (iddpm/__init__.py:156-157 calls the model twice with batch n_prompts = 1).
+        Their per-token statistics are not pooled (each row is quantised on its own, which is what two batch-1 calls do);
+        results are identical to calling forward_fused once per entry, at half the launches and better-filled GEMM waves."""
         x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan)
         eng = getattr(self, "_engine", None)
         if eng is None:
             eng = self._engine = FusedBlocks(self)
         if segments is None:
             segments = self.kv_segments(y_lens, x.device)
-        x = eng.run(x, y, t0, y_lens, segments)
+        x = eng.run(x, y, t0, y_lens, segments, independent)
         # final layer (FP, remain_fp.txt): LayerNorm + modulate in one pass of the fused kernel (its codes are unused)
         fl = self.final_layer
         shift, scale = (fl.scale_shift_table[None] + t[:, None]).chunk(2, dim=1)
@@ -345,14 +349,19 @@ class FusedBlocks:
             pw = self._qkv[key] = self._cat_prepared(layers)
         return pw
 
-    def _qkv_project(self, attn, tag, x, ln=None):
+    def _qkv_project(self, attn, tag, x, ln=None, independent=False):
         """q|k|v of one attention as one [M, 3C] tensor. ln = (shift, scale) fuses LayerNorm+modulate in front.
         Without smooth-quant: one quantise pass + one N=3C GEMM. With it (w4a8_timestep_aware_cb.yaml): each layer has
         its own channel scale, hence its own codes; the three GEMMs write column slices of the same output."""
         pw = self._qkv_weight(attn, tag)
         nb = attn.q.act_quantizer.n_bits
+        rpm = None
+        if independent:   # stacked separate calls: un-pooled statistics, per-entry modulation vectors
+            rpm = x.shape[1]
+            x = x.view(1, -1, x.shape[2])
         if pw is not None:
-            a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb)[0] if ln is not None else ops.act_quant(x, n_bits=nb)
+            a = (ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, rows_per_mod=rpm)[0] if ln is not None
+                 else ops.act_quant(x, n_bits=nb))
             return ops.gemm_w8a8(a, pw)
         B, N, C = x.shape
         out = torch.empty(B * N, 3 * C, dtype=x.dtype, device=x.device)
@@ -360,13 +369,13 @@ class FusedBlocks:
             lw = layer.prepared_weight()
             sm = getattr(lw, "smooth", None)
             if ln is not None:
-                a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, smooth=sm)[0]
+                a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, smooth=sm, rows_per_mod=rpm)[0]
             else:
                 a = ops.act_quant(x, n_bits=nb, smooth=sm)
             ops.gemm_w8a8(a, lw, out=out[:, j * C:(j + 1) * C], ldo=3 * C)
         return out
 
-    def run(self, x, y, t0, y_lens, segments):
+    def run(self, x, y, t0, y_lens, segments, independent=False):
         m = self.m
         B, N, C = x.shape
         T, S, H = m.num_temporal, m.num_spatial, m.num_heads
@@ -375,25 +384,29 @@ class FusedBlocks:
         x = x.contiguous()   # fresh tensor from embed(): the residual stream is updated in place below
         ones = torch.ones(1, C, dtype=x.dtype, device=x.device)
         tpe = m.pos_embed_temporal.to(x.dtype)
+        # all blocks' t2i modulation vectors in three launches: [L, 6, B, C] = scale_shift_table[None] + t0 (stdit.py:100-102)
+        tables = torch.stack([blk.scale_shift_table for blk in m.blocks]).to(x.dtype)
+        mod = (tables[:, None] + t0.reshape(1, B, 6, C)).permute(0, 2, 1, 3).contiguous()
         for i, blk in enumerate(m.blocks):
-            shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = (
-                v.reshape(B, C).contiguous() for v in blk.modulation(t0))
+            shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = mod[i].unbind(0)
             # ---- spatial attention: LN + modulate + quantise once, one q|k|v GEMM
-            qkv = self._qkv_project(blk.attn, (i, "s"), x, ln=(shift_msa, scale_msa)).view(B * T, S, 3, H, D)
+            qkv = self._qkv_project(blk.attn, (i, "s"), x, ln=(shift_msa, scale_msa),
+                                    independent=independent).view(B * T, S, 3, H, D)
             o = F.scaled_dot_product_attention(qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2),
                                                qkv[:, :, 2].transpose(1, 2), scale=blk.attn.scale)   # [B*T, H, S, D]
             pj = blk.attn.proj
             if o.is_contiguous() and D == 72 and C == 1152 and not pj.smooth_quant:
                 # quantise straight from the head-major layout the attention kernel emits (no transpose copy)
-                a = ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits)
+                a = (ops.act_quant_heads(o, 1, B * N, S, n_bits=pj.act_quantizer.n_bits) if independent
+                     else ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits))
             else:
-                a = pj.quantize_input(o.transpose(1, 2).reshape(B * T, S, C))
+                a = pj.quantize_input(o.transpose(1, 2).reshape(B * T, S, C), independent=independent)
             xr = x.view(M, C)   # residual stream, updated in place: out aliases res -> TMA reduce-add epilogue
             ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                           rows_per_gate=N, out=xr)
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
             xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
-            qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt)
+            qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt, independent=independent)
             if T <= 16 and D == 72:      # own kernel: reads the (T S) layout in place, no permute copies
                 o = ops.attn_temporal(qkv, B, T, S, H, D, blk.attn_temp.scale).view(B, N, C)
             else:                        # library path for shapes the kernel does not cover
@@ -401,25 +414,28 @@ class FusedBlocks:
                 qt, kt, vt = (q5[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
                 o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)
                 o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
-            a = blk.attn_temp.proj.quantize_input(o.view(B * S, T, C))   # per-token statistics: row order irrelevant
+            # per-token statistics: row order irrelevant
+            a = blk.attn_temp.proj.quantize_input(o.view(B * S, T, C), independent=independent)
             ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                           rows_per_gate=N, out=xr)
             # ---- cross attention
             ca = blk.cross_attn
-            q = ops.gemm_w8a8(ca.q_linear.quantize_input(x), ca.q_linear.prepared_weight())
+            q = ops.gemm_w8a8(ca.q_linear.quantize_input(x, independent=independent), ca.q_linear.prepared_weight())
             kv = ops.gemm_w8a8(ca.kv_linear.quantize_input(y), ca.kv_linear.prepared_weight())
             if D == 72 and max(y_lens) <= 128:
                 o = ops.attn_cross(q, kv, segments[0], segments[1], B, N, H, D, max(y_lens), D ** -0.5).view(B, N, C)
             else:
                 o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
-            ops.gemm_w8a8(ca.proj.quantize_input(o), ca.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
-                          res=xr, gate=ones, rows_per_gate=M, out=xr)
+            ops.gemm_w8a8(ca.proj.quantize_input(o, independent=independent), ca.proj.prepared_weight(),
+                          epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=ones, rows_per_gate=M, out=xr)
             # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
             fc1w = blk.mlp.fc1.prepared_weight()
-            a, _ = ops.ln_modulate_act_quant(x, shift_mlp, scale_mlp, n_bits=blk.mlp.fc1.act_quantizer.n_bits,
-                                             smooth=getattr(fc1w, "smooth", None))
-            h = ops.gemm_w8a8(a, fc1w, epi=ops.VQ_EPI_GELU_TANH).view(B, N, -1)
-            a = blk.mlp.fc2.quantize_input(h)
+            a, _ = ops.ln_modulate_act_quant(x.view(1, M, C) if independent else x, shift_mlp, scale_mlp,
+                                             n_bits=blk.mlp.fc1.act_quantizer.n_bits,
+                                             smooth=getattr(fc1w, "smooth", None), rows_per_mod=N if independent else None)
+            # GELU rides in fc2's quantise pass (HBM-bound, idle MUFU) instead of fc1's epilogue (epilogue-bound)
+            h = ops.gemm_w8a8(a, fc1w).view(B, N, -1)
+            a = blk.mlp.fc2.quantize_input(h, gelu=True, independent=independent)
             ops.gemm_w8a8(a, blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp,
                           rows_per_gate=N, out=xr)
         return x
