@@ -26,6 +26,21 @@ T_FRAMES, S_TOKENS, HIDDEN, DEPTH, HEADS, PROMPT_LEN = 16, 1024, 1152, 28, 16, 1
 FP_LAYERS = ["x_embedder", "t_block", "t_embedder", "y_embedder", "final_layer"]   # remain_fp.txt
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE vq_gemm_w8a8_kernel launch at M = 16384, from the `ncu --set full`
+# captures of the four block shapes (profiles/r01_s13_gemm_16384_<N>_<K>_<epi>.md), in MB keyed by (N, K).  Below the
+# algorithmic bytes (136 / 96 / 175 / 156 MB) because inputs written by the previous kernel still sit in the 126 MB L2
+# and part of the output is still there when the kernel ends.
+NCU_GEMM_DRAM_MB = {(3 * HIDDEN, HIDDEN): 85.4, (HIDDEN, HIDDEN): 64.6, (4 * HIDDEN, HIDDEN): 125.1,
+                    (HIDDEN, 4 * HIDDEN): 228.8}
+
+
+def gemm_dram_bytes_per_step(depth):
+    """Per denoise step (two forwards): 2 q|k|v, 4 hidden->hidden, fc1, fc2 GEMMs per block (kv_linear: < 1 MB, ignored)."""
+    per_block = (2 * NCU_GEMM_DRAM_MB[(3 * HIDDEN, HIDDEN)] + 4 * NCU_GEMM_DRAM_MB[(HIDDEN, HIDDEN)]
+                 + NCU_GEMM_DRAM_MB[(4 * HIDDEN, HIDDEN)] + NCU_GEMM_DRAM_MB[(HIDDEN, 4 * HIDDEN)])
+    return 2 * depth * per_block * 1e6
+
+
 def linear_ops_per_forward(n_tok=T_FRAMES * S_TOKENS, L=PROMPT_LEN):
     C = HIDDEN
     per_block = 10 * n_tok * C * C + 2 * n_tok * C * 4 * C + L * C * 2 * C
@@ -54,19 +69,24 @@ class ClockSampler:
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.samples, self._stop, self._th = gpu_index, [], threading.Event(), None
+        self.idx, self.samples, self._stop, self._th, self._proc = gpu_index, [], threading.Event(), None, None
+        self.t0 = self.t1 = None   # host-time window of the timed region (device work is bracketed by synchronize)
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        # one streaming nvidia-smi (-lms 50): a fresh process per sample costs > 100 ms and would see only a couple of
+        # samples of a sub-second timed region
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
+                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        for line in self._proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
+            if len(parts) >= 6 and self.t0 is not None and self.t1 is None:   # inside the timed region only
+                self.samples.append(parts)
+            if self._stop.is_set():
+                break
 
     def __enter__(self):
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -75,6 +95,9 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self._stop.set()
+        proc = getattr(self, "_proc", None)
+        if proc is not None:
+            proc.terminate()       # the exact child we started
         self._th.join(timeout=10)
 
     def summary(self):
@@ -289,16 +312,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: K steps, inputs resident in HBM ---------------------------------------------------------------
-    for _ in range(args.warmup):
-        run_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with ClockSampler(local) as clk:       # nvidia-smi streams from here on; only samples inside the timed region count
+        for _ in range(args.warmup):
+            run_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk.t0 = time.time()
         e0.record()
         for _ in range(args.steps):
             run_step()
         e1.record()
         barrier()
+        clk.t1 = time.time()
     ms = e0.elapsed_time(e1)
     # ---- e2e: host buffers in, host result out, every step ----------------------------------------------------
     for _ in range(max(1, args.warmup // 2)):
@@ -353,7 +378,12 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s",
-                         "frac": achieved / peak_tops, "traffic": None,
+                         "frac": achieved / peak_tops,
+                         "traffic": gemm_dram_bytes_per_step(args.depth) / max(1, len(gemm_events)),
+                         "traffic_unit": "bytes per launch (ncu dram read+write of the 4 block shapes at M=16384, "
+                                         "profiles/r01_s13_gemm_*.md, averaged over this step's launches)",
+                         "algorithmic_bytes_per_launch": 2 * args.depth * (2 * 136e6 + 3 * 95.6e6 + 57.9e6 + 175e6 + 156e6)
+                                                         / max(1, len(gemm_events)),
                          "kernel": "vq_gemm_w8a8_kernel (all QuantLinear GEMMs of a step)",
                          "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (INT8 dense = 2x bf16 on "
                                         "B200; no measured INT8 figure exists)" if peaks else "2 x 1400 fallback",
