@@ -66,6 +66,14 @@ int vq_prep_weight(const void* w, const void* delta, const void* zp, const void*
 int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, int64_t ld, const void* smooth,
                  int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status, void* stream);
 
+/* (N3) static activation scales: BaseQuantizer.forward with init_done (base_quantizer.py:112-144) on an ActQuantizer
+ * whose delta / zero_point were calibrated by PTQ and loaded from ckpt.pth — per-tensor (`per_group: False`,
+ * w8a8_naive.yaml: period = 1) or static per-token (period = rows).  x fp16 [M, K] (row pitch ld); delta, zp: DEVICE
+ * fp16 [period], row m uses index m % period; smooth fp16 [K] or NULL.  Outputs codes u8 [M, K], rowsum i32 [M]; feed
+ * vq_gemm_w8a8 with the same delta / zp and a_rows_period = period.                                                  */
+int vq_act_quant_static(const void* x, int M, int K, int64_t ld, const void* delta, const void* zp, int period,
+                        const void* smooth, int n_bits, uint8_t* codes, int32_t* rowsum, void* stream);
+
 /* nn.GELU(approximate="tanh") + (a1), one pass: the activation between Mlp.fc1 and Mlp.fc2 (reference
  * opensora/models/stdit/stdit.py:109-111 timm Mlp with approx_gelu; PixArt_blocks / PixArtMS.py:60 likewise) applied to
  * the fp16 fc1 output x on its way into fc2's DynamicActQuantizer (quant_layer.py:137-140: smooth division, then
@@ -108,6 +116,17 @@ int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S, int H, int
  * [B*N, H*head_dim]; kv fp16 [sum(len), 2*H*head_dim] (k | v); kv_start / kv_len: device int32 [B]; max_len <= 128. */
 int vq_attn_cross(const void* q, const void* kv, void* out, const int32_t* kv_start, const int32_t* kv_len, int B,
                   int N, int H, int head_dim, int max_len, float scale, void* stream);
+
+/* (a10 + N1) the sampler update of one denoise step for cfg_split models, fused: forward_with_cfg's combine
+ * (iddpm/__init__.py:166-184: model_out / (1 + ptqd_k); eps = u + s (c - u) on channels [:3] (sic), the rest from the
+ * conditional branch) + ddim_sample with eta = 0 (gaussian_diffusion.py:289-335, :540-552).  out_cond / out_uncond:
+ * fp32 [n, c_out, inner] (c_out = 2 c: eps | learned sigma); x, x_new: fp32 [n, c, inner]; coef: DEVICE fp32 [4] =
+ * {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, sqrt(alpha_bar_prev), sqrt(1 - alpha_bar_prev)} of the
+ * step (device-resident so a captured CUDA graph can be replayed for every step).  Bit-identical to the eager CUDA op
+ * sequence (every intermediate rounded to fp32 at the same places; `/ (1 + ptqd_k)` as ATen does it on CUDA: times the
+ * fp32 reciprocal of the Python scalar).                                              */
+int vq_cfg_ddim_step(const float* out_cond, const float* out_uncond, const float* x, const float* coef,
+                     float cfg_scale, double ptqd_k, int n, int c_out, int c, int64_t inner, float* x_new, void* stream);
 
 /* status word helpers (host side; the only calls here that synchronise) */
 int vq_status_read(const uint32_t* status_dev, uint32_t* host_out, void* stream);

@@ -88,6 +88,21 @@ def dynamic_act_quant(x16, n_bits=8, smooth16=None):
     return out
 
 
+def static_act_quant(x16, delta16, zp16, n_bits=8, smooth16=None):
+    """BaseQuantizer.forward with init_done (base_quantizer.py:129-143) for a calibrated ActQuantizer: delta16 / zp16 are
+    the checkpoint's fp16 buffers, 1 element (per_group False: w8a8_naive.yaml) or n_token elements (static per-token,
+    broadcast as [1, n_token, 1]).  Returns dict(codes u8, rowsum i32, xhat fp16) for x16 fp16 [B, n, C]."""
+    x = as_f32(x16)
+    if smooth16 is not None:
+        x = _h(x / as_f32(smooth16))
+    d, z = as_f32(delta16).reshape(-1), as_f32(zp16).reshape(-1)
+    if d.size > 1:
+        d, z = d[None, :, None], z[None, :, None]
+    q = quant_codes(x.astype(F16), d, z, n_bits)
+    return dict(codes=q.astype(np.uint8), rowsum=q.astype(np.int64).sum(axis=-1).astype(np.int32),
+                xhat=dequant(q, d, z))
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # a2: WeightQuantizer with static per-output-channel parameters
 # ----------------------------------------------------------------------------------------------------------------------

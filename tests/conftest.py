@@ -23,3 +23,14 @@ def golden():
         name, field = key.rsplit("/", 1)
         cases.setdefault(name, {})[field] = z[key]
     return cases
+
+
+@pytest.fixture(scope="session")
+def golden_static():
+    """Reference-generated vectors of the STATIC activation-scale path (tests/golden/make_golden_static.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "static_act_golden.npz"))
+    cases = {}
+    for key in z.files:
+        name, field = key.rsplit("/", 1)
+        cases.setdefault(name, {})[field] = z[key]
+    return cases

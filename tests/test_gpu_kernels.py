@@ -302,3 +302,70 @@ def test_act_quant_heads_equals_token_major(ops, G, T, S):
     assert torch.equal(a.zp, b.zp) and torch.equal(a.rowsum, b.rowsum)
     oa = O.dynamic_act_quant(tok.cpu().numpy())
     np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(G, T * S, H * D), oa["codes"])
+
+
+@pytest.mark.parametrize("n,k", [(1, 0.0), (2, 0.25)])
+def test_cfg_ddim_step_is_bit_identical_to_the_eager_sequence(ops, n, k):
+    """vq_cfg_ddim_step == forward_with_cfg's combine + ddim_sample(eta=0) as separate fp32 ops (sampler.py restatement,
+    itself pinned to the reference by tests/golden/sampler_golden.npz)."""
+    from viditq_b200.sampler import SpacedDDIM
+    torch.manual_seed(4)
+    ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
+    x = torch.randn(n, 4, 5, 16, 16, device="cuda")
+    oc = torch.randn(n, 8, 5, 16, 16, device="cuda")
+    ou = torch.randn(n, 8, 5, 16, 16, device="cuda")
+    for i in (99, 37, 0):
+        coef = ddim.coefficients(i, "cuda")
+        want = SpacedDDIM.ddim_update(x, SpacedDDIM.cfg_combine(oc, ou, ddim.cfg_scale, ptqd_k=k), coef)
+        got = ops.cfg_ddim_step(oc, ou, x, coef, ddim.cfg_scale, ptqd_k=k)
+        assert torch.equal(got, want), (i, (got - want).abs().max().item())
+    with pytest.raises(Exception):
+        ops.cfg_ddim_step(oc.cpu(), ou.cpu(), x.cpu(), coef.cpu(), 4.0)
+
+
+@pytest.mark.parametrize("name", ["static/tensor_mlp", "static/tensor_spatial_b2", "static/tensor_bits6",
+                                  "static/token_mlp"])
+def test_static_act_scales_match_reference(ops, golden_static, name):
+    """vq_act_quant_static (N3, w8a8_naive.yaml): codes bit-exact against the unmodified reference's static
+    ActQuantizer, and the layer output through vq_gemm_w8a8 (a_rows_period = number of (delta, zp) pairs) <= 1e-3."""
+    c = golden_static[name]
+    bits = int(c["a_bits"])
+    x = c["x"]
+    a = ops.act_quant_static(dev(x), dev(c["adelta"]), dev(c["azp"]), n_bits=bits)
+    np.testing.assert_array_equal(a.codes.cpu().numpy().reshape(c["codes"].shape), c["codes"])
+    np.testing.assert_array_equal(a.rowsum.cpu().numpy().reshape(c["codes"].shape[:-1]),
+                                  c["codes"].astype(np.int64).sum(-1))
+    pw = ops.prep_weight(dev(c["weight"]), dev(c["wdelta"]), dev(c["wzp"]), bias=dev(c["bias"]))
+    y = ops.gemm_w8a8(a, pw).cpu().numpy().astype(np.float32).reshape(c["out"].shape)
+    ref = c["out"].astype(np.float32)
+    assert np.abs(y - ref).max() / np.abs(ref).max() <= 1e-3
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-3
+
+
+def test_static_quant_layer_module_path(ops, golden_static):
+    """The same through viditq_b200.qdiff.QuantLayer configured like w8a8_naive.yaml (per_group False, dynamic False) with
+    the reference's calibrated buffers loaded the way set_quant_params_dict does."""
+    import torch.nn as nn
+    from oracle import ref_shims
+    from viditq_b200 import qdiff
+    c = golden_static["static/tensor_mlp"]
+    N, K = c["weight"].shape
+    lin = nn.Linear(K, N)
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(c["weight"].astype(np.float32)))
+        lin.bias.copy_(torch.from_numpy(c["bias"].astype(np.float32)))
+    wq, aq = ref_shims.w8a8_dynamic_configs(n_temporal=4, n_spatial=16, n_prompt=8)
+    aq["dynamic"], aq["per_group"] = False, False
+    layer = qdiff.QuantLayer(lin, wq, aq)
+    layer.weight_quantizer.delta = torch.from_numpy(c["wdelta"].astype(np.float32)).reshape(-1, 1)
+    layer.weight_quantizer.zero_point = torch.from_numpy(c["wzp"].astype(np.float32)).reshape(-1, 1)
+    layer.act_quantizer.delta = torch.from_numpy(c["adelta"].astype(np.float32)).reshape(1, 1, 1)
+    layer.act_quantizer.zero_point = torch.from_numpy(c["azp"].astype(np.float32)).reshape(1, 1, 1)
+    layer.weight_quantizer.init_done = layer.act_quantizer.init_done = True
+    layer.set_quant_state(True, True)
+    layer.cuda().half()
+    with torch.no_grad():
+        y = layer(dev(c["x"])).cpu().numpy().astype(np.float32)
+    ref = c["out"].astype(np.float32)
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-3
+    assert np.abs(y - ref).max() / np.abs(ref).max() <= 1e-3

@@ -156,3 +156,33 @@ def test_torch_exact_operand_simulation_equals_integer_decomposition(golden, nam
     d = np.abs(ex.astype(np.float32) - y.astype(np.float32))
     assert d.max() <= 2 * float(np.spacing(np.float16(np.abs(y.astype(np.float32)).max())))
     assert (d > 0).mean() < 0.02
+
+
+STATIC_CASES = ["static/tensor_mlp", "static/tensor_spatial_b2", "static/tensor_bits6", "static/token_mlp"]
+
+
+def _static_view(c):
+    """[B, n, C] view whose dim 1 is the token axis of a static per-token quantiser (plain QuantLayer: as given)."""
+    x = c["x"]
+    return x.reshape(1, -1, x.shape[-1]) if not int(c["per_token"]) else x
+
+
+@pytest.mark.parametrize("name", STATIC_CASES)
+def test_static_act_quantizer_bit_exact(golden_static, name):
+    """N3 / w8a8_naive.yaml: calibrated per-tensor (and static per-token) activation scales, codes pinned bit-for-bit
+    to the unmodified reference, output of the whole layer within 1e-3 through the integer decomposition."""
+    c = golden_static[name]
+    bits = int(c["a_bits"])
+    xv = _static_view(c)
+    r = O.static_act_quant(xv, c["adelta"], c["azp"], bits)
+    np.testing.assert_array_equal(r["codes"].reshape(c["codes"].shape), c["codes"])
+    assert (c["codes"] == 0).any() and (c["codes"] == 2 ** bits - 1).any()      # the vectors do saturate
+    B, n, K = xv.shape
+    d = np.broadcast_to(c["adelta"].astype(np.float32), (n,)) if c["adelta"].size == 1 else c["adelta"].astype(np.float32)
+    z = np.broadcast_to(c["azp"].astype(np.float32), (n,)) if c["azp"].size == 1 else c["azp"].astype(np.float32)
+    wq = O.weight_quant(c["weight"], c["wdelta"], c["wzp"], 8)
+    y = O.quant_linear_int(r["codes"], d, z, r["rowsum"], wq["codes"], c["wdelta"], c["wzp"], c["bias"])
+    ref = c["out"].reshape(B, n, -1).astype(np.float32)
+    rel_inf = np.abs(y.astype(np.float32) - ref).max() / np.abs(ref).max()
+    rel_l2 = np.linalg.norm(y.astype(np.float32) - ref) / np.linalg.norm(ref)
+    assert rel_inf <= 1e-3 and rel_l2 <= 1e-3, (rel_inf, rel_l2)

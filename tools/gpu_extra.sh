@@ -1,4 +1,10 @@
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --cfg-mode split > gpurun_out/bench_split.log 2>&1
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --cfg-mode stacked > gpurun_out/bench_stacked2.log 2>&1
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --cfg-mode split > gpurun_out/bench_split2.log 2>&1
-for f in bench_split bench_stacked2 bench_split2; do tail -1 gpurun_out/$f.log | cut -c1-200; done
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+rm -f gpurun_out/*.ncu-rep
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 1 --warmup 3 --no-graph --depth 2 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+for c in "16384 3456 1152 0" "16384 1152 1152 2" "16384 4608 1152 0" "16384 1152 4608 2"; do
+  n=$(echo $c | tr ' ' '_')
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:vq_gemm -c 1 -f -o gpurun_out/gemm_$n \
+     tools/gemm_selftest --case $c > gpurun_out/ncu_gemm_$n.log 2>&1
+done
+tail -2 gpurun_out/smoke.log

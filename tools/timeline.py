@@ -26,6 +26,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.manual_seed(1234)
     torch.set_grad_enabled(False)
+    from viditq_b200 import ops
     from viditq_b200.sampler import SpacedDDIM
     qnn, model = bench.build_model(dev, args.depth)
     ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
@@ -44,7 +45,7 @@ def main():
     def step():
         o = model.forward_fused(torch.cat([d_z, d_z]), d_t.expand(2), torch.cat([d_yc, d_yu]), plan=plan,
                                 segments=segments, independent=True)
-        return SpacedDDIM.ddim_update(d_z, SpacedDDIM.cfg_combine(o[:1], o[1:], ddim.cfg_scale), d_coef)
+        return ops.cfg_ddim_step(o[:1], o[1:], d_z, d_coef, ddim.cfg_scale)
 
     for _ in range(2):
         step()

@@ -705,7 +705,75 @@ __global__ void __launch_bounds__(256) vq_prep_weight_kernel(const PrepArgs a) {
   }
 }
 
+// ----------------------------------------------------------------------------- static (calibrated) activation scales
+// BaseQuantizer.forward with init_done (base_quantizer.py:112-144) on an ActQuantizer whose delta / zero_point come from
+// the PTQ checkpoint instead of the live tensor: per-tensor (`per_group: False`, w8a8_naive.yaml — one scalar pair) or
+// static per-token ([rows] pairs, period = rows).  One streaming pass, one warp per row.
+struct StaticQuantArgs {
+  const __half* x;
+  int M, K;
+  long long ld;
+  const __half* delta;   // [period]
+  const __half* zp;      // [period]
+  int period;            // row m uses index m % period
+  const __half* smooth;  // [K] or null
+  float qmax;
+  uint8_t* codes;
+  int32_t* rowsum;
+};
+
+__global__ void __launch_bounds__(256) vq_act_quant_static_kernel(const StaticQuantArgs a) {
+  grid_dep_sync();
+  const int lane = threadIdx.x & 31;
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  for (int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < a.M; m += wstride) {
+    const int si = a.period == 1 ? 0 : m % a.period;
+    const float delta = __half2float(a.delta[si]);
+    const float zp = __half2float(a.zp[si]);
+    const QuantConsts qc = make_consts(delta, zp, a.qmax);
+    // calibrated step sizes do not bound |x / delta|: clamp so that the fp16 rounding trick stays exact (|x/delta| <=
+    // 511); beyond that the code saturates to 0 / qmax either way
+    const __half2 xl = __float2half2_rn(fminf(511.0f * delta, 65504.0f));
+    const __half* xrow = a.x + static_cast<size_t>(m) * a.ld;
+    uint8_t* crow = a.codes + static_cast<size_t>(m) * a.K;
+    int sum = 0;
+    for (int ci = lane; ci < (a.K >> 3); ci += 32) {
+      uint4 xv = __ldg(reinterpret_cast<const uint4*>(xrow) + ci);
+      __half2* x = reinterpret_cast<__half2*>(&xv);
+      if (a.smooth) {   // quant_layer.py:140 input / channel_wise_scale
+        uint4 sv = __ldg(reinterpret_cast<const uint4*>(a.smooth) + ci);
+        const __half2* sm = reinterpret_cast<const __half2*>(&sv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = div_pair(x[e], sm[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = __hmin2(__hmax2(x[e], __hneg2(xl)), xl);
+      reinterpret_cast<uint2*>(crow)[ci] = quant_chunk(xv, qc, sum);
+    }
+    sum = warp_sum_i(sum);
+    if (lane == 0) a.rowsum[m] = sum;
+  }
+}
+
 }  // namespace vq
+
+extern "C" int vq_act_quant_static(const void* x, int M, int K, int64_t ld, const void* delta, const void* zp,
+                                   int period, const void* smooth, int n_bits, uint8_t* codes, int32_t* rowsum,
+                                   void* stream) {
+  using namespace vq;
+  if (!x || !codes || !delta || !zp || !rowsum || M <= 0 || K <= 0 || period <= 0) return VQ_ERR_ARG;
+  if ((K % 8) != 0 || (ld % 8) != 0 || n_bits < 2 || n_bits > 8) return VQ_ERR_ARG;
+  StaticQuantArgs a{static_cast<const __half*>(x), M, K, ld, static_cast<const __half*>(delta),
+                    static_cast<const __half*>(zp), period, static_cast<const __half*>(smooth),
+                    static_cast<float>((1 << n_bits) - 1), codes, rowsum};
+  const int warps = 8;
+  long long blocks = (M + warps - 1) / warps;
+  const long long cap = 8LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  launch_pdl(vq_act_quant_static_kernel, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0,
+             static_cast<cudaStream_t>(stream), a);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
 
 extern "C" int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, int64_t ld,
                             const void* smooth, int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum,

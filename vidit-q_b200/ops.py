@@ -44,6 +44,25 @@ def status_word(device=None):
     return _status[dev]
 
 
+def cfg_ddim_step(out_cond, out_uncond, x, coef, cfg_scale, ptqd_k=0.0, out=None):
+    """Fused CFG combine + DDIM (eta = 0) update. out_cond / out_uncond: fp32 CUDA [n, 2c, ...]; x: fp32 [n, c, ...];
+    coef: fp32 CUDA [4] (SpacedDDIM.coefficients). Returns the next latent (fp32, x's shape)."""
+    for t, name in ((out_cond, "out_cond"), (out_uncond, "out_uncond"), (x, "x"), (coef, "coef")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise _lib.VqError(f"cfg_ddim_step: {name} must be a contiguous CUDA fp32 tensor (no CPU fallback)")
+    n, c = x.shape[0], x.shape[1]
+    inner = x.numel() // (n * c)
+    if out_cond.shape != out_uncond.shape or out_cond.shape[0] != n or out_cond.numel() != n * out_cond.shape[1] * inner:
+        raise _lib.VqError(f"cfg_ddim_step: shapes {tuple(out_cond.shape)} / {tuple(x.shape)} do not match")
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.lib().vq_cfg_ddim_step(_ptr(out_cond), _ptr(out_uncond), _ptr(x), _ptr(coef), float(cfg_scale),
+                                     float(ptqd_k), n, out_cond.shape[1], c, inner, _ptr(out), _stream())
+    _lib.check(rc, "vq_cfg_ddim_step")
+    _count()
+    return out
+
+
 def check_status(device=None):
     """Poll the sticky device status word (synchronises; call outside the hot loop). Raises on the reference's
     degenerate-eps quirk (base_quantizer.py:220-223), whose fp16 result is non-finite garbage in the reference."""
@@ -118,6 +137,28 @@ def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None, gelu=Fal
     _lib.check(rc, "vq_gelu_act_quant" if gelu else "vq_act_quant")
     _count()
     return a
+
+
+def act_quant_static(x, delta, zp, n_bits=8, smooth=None) -> ActCodes:
+    """Static (calibrated) activation scales: x fp16 [..., K]; delta / zp: fp16 CUDA [period] (1 = per-tensor, the
+    w8a8_naive.yaml case; rows = static per-token). Row m uses index m % period."""
+    _need_cuda_f16(x, "x")
+    _need_cuda_f16(delta, "delta")
+    _need_cuda_f16(zp, "zp")
+    K = x.shape[-1]
+    M = x.numel() // K
+    period = delta.numel()
+    if zp.numel() != period or M % period != 0:
+        raise _lib.VqError(f"act_quant_static: {M} rows are not a multiple of the {period} (delta, zp) pairs")
+    codes = torch.empty((M, K), dtype=torch.uint8, device=x.device)
+    rowsum = torch.empty(M, dtype=torch.int32, device=x.device)
+    if smooth is not None:
+        _need_cuda_f16(smooth, "smooth")
+    rc = _lib.lib().vq_act_quant_static(_ptr(x), M, K, K, _ptr(delta), _ptr(zp), period, _ptr(smooth), n_bits,
+                                        _ptr(codes), _ptr(rowsum), _stream())
+    _lib.check(rc, "vq_act_quant_static")
+    _count()
+    return ActCodes(codes, delta.reshape(-1), zp.reshape(-1), rowsum, M // period, period, K)
 
 
 def act_quant_heads(x, G, rows, S, n_bits=8, out: Optional[ActCodes] = None) -> ActCodes:

@@ -210,9 +210,22 @@ class QuantLayer(nn.Module):
 
     def _check_act_quantizer(self):
         aq = self.act_quantizer
-        if not isinstance(aq, DynamicActQuantizer) or aq.per_group != "token" or aq.sym or aq.n_bits > 8:
-            raise NotImplementedError("fused path supports dynamic per-token asymmetric activations, <= 8 bits "
-                                      "(the ViDiT-Q W8A8 / W4A8 configs)")
+        if aq.sym or aq.n_bits > 8:
+            raise NotImplementedError("fused path supports asymmetric activations of <= 8 bits")
+        if isinstance(aq, DynamicActQuantizer):
+            if aq.per_group != "token":
+                raise NotImplementedError("dynamic activation quantisation is per-token (the ViDiT-Q W8A8 / W4A8 configs)")
+        elif aq.per_group not in (False, None, "token") or aq.delta is None or not aq.init_done:
+            raise NotImplementedError("static activation quantisation needs calibrated per-tensor / per-token delta and "
+                                      "zero_point from a PTQ checkpoint (set_quant_params_dict + set_quant_init_done)")
+
+    def _static_act_params(self):
+        """(delta, zp) of a calibrated ActQuantizer as flat fp16 CUDA tensors: 1 element (per_group False,
+        w8a8_naive.yaml) or n_token elements (static per-token, buffers of shape [1, n_token, 1])."""
+        aq = self.act_quantizer
+        dev = self.weight.device
+        return (aq.delta.reshape(-1).to(dev, torch.float16).contiguous(),
+                aq.zero_point.reshape(-1).to(dev, torch.float16).contiguous())
 
     def quantize_input(self, input, gelu=False, independent=False):
         """Per-token dynamic activation quantisation of a [*, n, C] fp16 tensor -> ops.ActCodes.
@@ -221,6 +234,18 @@ class QuantLayer(nn.Module):
         independent=True: the batch entries are separate forward calls stacked along the batch (cfg_split's cond / uncond
         halves at one prompt each): nothing is pooled, every row gets its own statistics."""
         self._check_act_quantizer()
+        if not isinstance(self.act_quantizer, DynamicActQuantizer):
+            # static scales (base_quantizer.py:112-144 with init_done): nothing is computed from the live tensor
+            if gelu:
+                raise NotImplementedError("GELU fused into a static-scale quantise pass")
+            delta, zp = self._static_act_params()
+            x = input if input.is_contiguous() else input.contiguous()
+            if delta.numel() > 1:   # static per-token: index = token position inside the layer's pooled view
+                G, rows = self._pool_view(input)
+                if rows != delta.numel():
+                    raise NotImplementedError(f"static per-token scales for {delta.numel()} tokens, input has {rows}")
+            return ops.act_quant_static(x, delta, zp, n_bits=self.act_quantizer.n_bits,
+                                        smooth=getattr(self.prepared_weight(), "smooth", None))
         G, rows = self._pool_view(input)
         if independent:
             G, rows = 1, G * rows

@@ -86,8 +86,13 @@ class SpacedDDIM:
         else:
             out_c = model_forward(x, t, y_cond, mask=mask)
             out_u = model_forward(x, t, y_uncond, mask=mask)
+        coef = self.coefficients(i, x.device)
+        if x.is_cuda:   # fused sampler update (vq_cfg_ddim_step); the two static methods below are its restatement
+            from . import ops
+            return ops.cfg_ddim_step(out_c.float().contiguous(), out_u.float().contiguous(), x.float().contiguous(),
+                                     coef, self.cfg_scale)
         out = self.cfg_combine(out_c, out_u, self.cfg_scale)
-        return self.ddim_update(x, out, self.coefficients(i, x.device))
+        return self.ddim_update(x, out, coef)
 
 
 def get_key_for_value(dict_ranges, value):
