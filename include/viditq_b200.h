@@ -112,6 +112,13 @@ int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const void* a_zp, 
  * head_dim must be 72, T <= 16. scale = head_dim^-0.5.                                                             */
 int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S, int H, int head_dim, float scale, void* stream);
 
+/* (a9) spatial self-attention of STDiT (stdit.py:104-109, blocks.py:151-195 on "(B T) S C"; the reference calls
+ * flash-attn / xformers there) and PixArt (PixArt_blocks.py AttentionKVCompress, sr_ratio 1): n_seq independent sequences
+ * of S tokens, q|k|v read in place from the fused GEMM output qkv fp16 [n_seq*S, 3*H*head_dim]; out fp16
+ * [n_seq*S, H*head_dim] token-major (no transpose copy in front of the projection). tcgen05 flash attention with TMEM
+ * accumulators; head_dim must be 72 and S a multiple of 256. scale = head_dim^-0.5.                                  */
+int vq_attn_spatial(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale, void* stream);
+
 /* (a9) cross attention (blocks.py:292-310, xformers BlockDiagonalMask.from_seqlens([N]*B, y_lens)): q fp16
  * [B*N, H*head_dim]; kv fp16 [sum(len), 2*H*head_dim] (k | v); kv_start / kv_len: device int32 [B]; max_len <= 128. */
 int vq_attn_cross(const void* q, const void* kv, void* out, const int32_t* kv_start, const int32_t* kv_len, int B,

@@ -1,0 +1,500 @@
+// Spatial self-attention of STDiT / PixArt on tcgen05 (reference: t2v/opensora/models/layers/blocks.py:151-195 on the
+// "(B T) S C" view, stdit.py:104-109; flash-attn / xformers there).  fp16 Q/K/V, fp32 scores and softmax statistics,
+// fp16 probabilities, fp32 output accumulation: the arithmetic of the flash kernels the reference calls.
+//
+// One sequence = S tokens of one frame, 16 heads of 72 dims.  q|k|v are read IN PLACE from the fused q|k|v GEMM output
+// [n_seq * S, 3 * H * 72] through 4-D TMA tensor maps (dim, head, {q,k,v}, token); the output is written token-major
+// [n_seq * S, H * 72], i.e. already in the layout the projection's quantiser reads (the reference's
+// transpose(1, 2).reshape copy, blocks.py:189-191, does not exist).
+//
+// Work item = (sequence, head, 256 queries): two 128-query tiles share one stream of 128-key K / V tiles, which halves the
+// L2 -> shared-memory operand traffic (at 128 queries per K/V stream the kernel would sit on the L2 bandwidth roof).
+// Persistent CTAs (one per SM), 12 warps:
+//   warp 0      TMA producer: Q tiles of the item, then a 3-stage ring of K tiles and one of V tiles.  head_dim 72 is
+//               stored as a 64-dim SWIZZLE_128B tile plus a 16-dim SWIZZLE_32B tile whose dims 72..79 lie outside the
+//               tensor map's innermost extent and are zero-filled by the TMA unit (so K = 80 for the MMA, no padded copy).
+//   warp 1      MMA issuer.  S = Q K^T: 5 x tcgen05.mma.kind::f16 (M128 N128 K16; 4 in the SW128 tile, 1 in the SW32 tile)
+//               into TMEM.  O += P V: P is read from TMEM as the A operand (it overwrites S in place, two fp16 per column),
+//               V is the MN-major B operand straight from the TMA tile: per 16 keys one N=64 and one N=16 instruction.
+//   warp 2      TMEM allocation (512 columns: S/P 2 x 128, O 2 x 128).
+//   warps 4-7   softmax of query tile 0, one thread per query row (tcgen05.ld 32x32b: lane = row, no shuffles);
+//   warps 8-11  softmax of query tile 1.  While one tile is in its softmax the tensor core works on the other.
+// Online softmax with a lazy rescale: the running maximum is only raised (and O / the row sum rescaled in TMEM) when a
+// row's new maximum exceeds the one in use by more than 2^8 — after the first K tile that is rare, so the O round trip
+// through registers disappears from the steady state.  exp2 on MUFU with the log2(e) / sqrt(d) factor folded into one FFMA.
+// The kernel is MUFU-bound by design: 128 x 128 exponentials per tile pair against 5.2 MFLOP of tensor work.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "vq_internal.h"
+#include "vq_ptx.cuh"
+
+namespace vq {
+
+constexpr int SA_D = 72;
+constexpr int SA_BM = 128;                 // queries per tile
+constexpr int SA_BN = 64;                  // keys per tile
+constexpr int SA_QT = 2;                   // query tiles per item
+constexpr int SA_STAGES = 4;               // K ring and V ring depth
+constexpr int SA_TILE_A = SA_BM * 128;     // Q: dims 0..63: 128-byte rows, SWIZZLE_128B
+constexpr int SA_TILE_B = SA_BM * 32;      // Q: dims 64..79: 32-byte rows, SWIZZLE_32B (72..79 zero)
+constexpr int SA_TILE = SA_TILE_A + SA_TILE_B;
+constexpr int SA_KV_A = SA_BN * 128;       // K / V tile: same two pieces with 64 rows
+constexpr int SA_KV_B = SA_BN * 32;
+constexpr int SA_KV = SA_KV_A + SA_KV_B;
+constexpr int SA_OSTAGE = 128 * SA_D * 2;  // dense [128][72] fp16 staging tile of the output
+constexpr int SA_SMEM_K = SA_QT * SA_TILE;
+constexpr int SA_SMEM_V = SA_SMEM_K + SA_STAGES * SA_KV;
+constexpr int SA_SMEM_O = SA_SMEM_V + SA_STAGES * SA_KV;
+constexpr int SA_SMEM_BAR = SA_SMEM_O + SA_QT * SA_OSTAGE;
+constexpr int SA_SMEM_BYTES = SA_SMEM_BAR + 512 + 1024;   // barriers + alignment slack
+constexpr int SA_THREADS = 384;
+constexpr uint32_t SA_TMEM_COLS = 512;
+constexpr uint32_t SA_O_COL = 256;         // O accumulators start here; S/P buffer b of tile t at t * 128 + b * 64
+constexpr float SA_RESCALE_LOG2 = 8.0f;    // lazy-rescale threshold (log2 units): P stays <= 2^8 in fp16
+
+struct SpatialArgs {
+  int n_seq, S, H;
+  float scale_log2e;
+  int debug;        // 0 = attention; 1 = P := 1; 2 = P := identity on the first key tile; 3 = also dump S of key tile 0
+  float* dbg;       // debug 3: [items][2][128][128] raw scores of the first key tile
+  uint32_t v_lbo;   // leading byte offset written into the MN-major V descriptors (unused by the hardware when N fits one atom)
+};
+
+__device__ __forceinline__ float sa_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(SA_THREADS, 1)
+vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_constant__ CUtensorMap tmap_qb,
+                       const __grid_constant__ CUtensorMap tmap_ka, const __grid_constant__ CUtensorMap tmap_kb,
+                       const __grid_constant__ CUtensorMap tmap_o, const SpatialArgs a) {
+  extern __shared__ uint8_t sa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sa_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem + SA_SMEM_K;
+  uint8_t* smem_v = smem + SA_SMEM_V;
+  uint8_t* smem_o = smem + SA_SMEM_O;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA_SMEM_BAR);
+  uint64_t* q_full = bars;                     // Q tiles of the item landed
+  uint64_t* q_empty = bars + 1;                // last S MMA of the item has read them
+  uint64_t* k_full = bars + 2;                 // [SA_STAGES]
+  uint64_t* k_empty = k_full + SA_STAGES;
+  uint64_t* v_full = k_empty + SA_STAGES;
+  uint64_t* v_empty = v_full + SA_STAGES;
+  uint64_t* s_full = v_empty + SA_STAGES;      // [2 tiles][2 buffers] S is in TMEM
+  // The softmax of a tile may run up to two key tiles ahead of what the MMA warp has observed (its scores are produced two
+  // tiles ahead), so every softmax <-> MMA barrier exists once per score buffer: a barrier then never advances two phases
+  // between two waits of its consumer (with one barrier per tile the parity wait aliases: deadlock / early pass).
+  uint64_t* p_full = s_full + 2 * SA_QT;       // [2 tiles][2 buffers] P is in TMEM (and O rescaled if needed)
+  uint64_t* o_full = p_full + 2 * SA_QT;       // [2 tiles][2 buffers] the P V reading that buffer has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2 * SA_QT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nqp = a.S / (SA_QT * SA_BM);       // 256-query groups per sequence
+  const int nkv = a.S / SA_BN;                 // key tiles per sequence (even, >= 4)
+  const int num_items = a.n_seq * a.H * nqp;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qa);
+    tma_prefetch_desc(&tmap_qb);
+    tma_prefetch_desc(&tmap_ka);
+    tma_prefetch_desc(&tmap_kb);
+    tma_prefetch_desc(&tmap_o);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < SA_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < SA_QT; ++t) {
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&s_full[2 * t + b], 1);
+        mbar_init(&p_full[2 * t + b], 4);   // one arrival per softmax warp of the tile
+        mbar_init(&o_full[2 * t + b], 1);
+      }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, SA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t kc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int qp = item % nqp;
+        const int h = (item / nqp) % a.H;
+        const int seq = item / (nqp * a.H);
+        const int row_q0 = seq * a.S + qp * (SA_QT * SA_BM);
+        const int row_kv0 = seq * a.S;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, SA_QT * SA_TILE);
+        for (int t = 0; t < SA_QT; ++t) {
+          tma_load_4d_hint(smem_q + t * SA_TILE, &tmap_qa, q_full, 0, h, 0, row_q0 + t * SA_BM, kEvictFirst);
+          tma_load_4d_hint(smem_q + t * SA_TILE + SA_TILE_A, &tmap_qb, q_full, 64, h, 0, row_q0 + t * SA_BM, kEvictFirst);
+        }
+        for (int j = 0; j < nkv; ++j, ++kc) {
+          const int s = kc % SA_STAGES;
+          const uint32_t ph = (kc / SA_STAGES) & 1;
+          // K / V tiles of a (sequence, head) are re-read by the other query groups of that head: keep them in L2
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], SA_KV);
+          tma_load_4d_hint(smem_k + s * SA_KV, &tmap_ka, &k_full[s], 0, h, 1, row_kv0 + j * SA_BN, kEvictLast);
+          tma_load_4d_hint(smem_k + s * SA_KV + SA_KV_A, &tmap_kb, &k_full[s], 64, h, 1, row_kv0 + j * SA_BN, kEvictLast);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], SA_KV);
+          tma_load_4d_hint(smem_v + s * SA_KV, &tmap_ka, &v_full[s], 0, h, 2, row_kv0 + j * SA_BN, kEvictLast);
+          tma_load_4d_hint(smem_v + s * SA_KV + SA_KV_A, &tmap_kb, &v_full[s], 64, h, 2, row_kv0 + j * SA_BN, kEvictLast);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_f16(SA_BM, SA_BN, 0, 0);
+      constexpr uint32_t idesc_pv64 = make_idesc_f16(SA_BM, 64, 0, 1);   // B = V, MN-major
+      constexpr uint32_t idesc_pv16 = make_idesc_f16(SA_BM, 16, 0, 1);
+      // S[t][b] = Q[t] K^T: K dimension 80 = 4 steps of 16 inside the 128-byte swizzle rows + 1 step in the 32-byte tile
+      auto issue_s = [&](int t, int b, int ks) {
+        const uint32_t qa = smem_u32(smem_q + t * SA_TILE), qb = qa + SA_TILE_A;
+        const uint32_t ka = smem_u32(smem_k + ks * SA_KV), kb = ka + SA_KV_A;
+        const uint32_t d = tmem_base + t * 128 + b * SA_BN;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16_ss(d, make_smem_desc(qa + 32 * k, 16, 1024, 2), make_smem_desc(ka + 32 * k, 16, 1024, 2), idesc_s,
+                        k > 0 ? 1u : 0u);
+        tc_mma_f16_ss(d, make_smem_desc(qb, 16, 256, 6), make_smem_desc(kb, 16, 256, 6), idesc_s, 1u);
+        tc_commit(&s_full[2 * t + b]);
+      };
+      // O[t] (+)= P[t][b] V: 4 steps of 16 keys; dims 0..63 from the SW128 tile (N = 64), dims 64..79 from the SW32 tile (N = 16)
+      auto issue_pv = [&](int t, int b, int vs, uint32_t acc) {
+        const uint32_t va = smem_u32(smem_v + vs * SA_KV), vb = va + SA_KV_A;
+        const uint32_t p = tmem_base + t * 128 + b * SA_BN;
+        const uint32_t o = tmem_base + SA_O_COL + t * 128;
+#pragma unroll
+        for (int k = 0; k < SA_BN / 16; ++k) {
+          const uint32_t ak = (acc | static_cast<uint32_t>(k > 0)) ? 1u : 0u;
+          tc_mma_f16_ts(o, p + 8 * k, make_smem_desc(va + k * 2048, a.v_lbo, 1024, 2), idesc_pv64, ak);
+          tc_mma_f16_ts(o + 64, p + 8 * k, make_smem_desc(vb + k * 512, a.v_lbo, 256, 6), idesc_pv16, ak);
+        }
+        tc_commit(&o_full[2 * t + b]);
+      };
+      uint32_t kc = 0, vc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        mbar_wait(q_full, it & 1);
+        // the score buffers run two key tiles ahead of the softmax: S_0 and S_1 first
+        for (int i = 0; i < 2; ++i) {
+          const int ks = kc % SA_STAGES;
+          mbar_wait(&k_full[ks], (kc / SA_STAGES) & 1);
+          tc_fence_after();
+          issue_s(0, i, ks);
+          issue_s(1, i, ks);
+          tc_commit(&k_empty[ks]);
+          ++kc;
+          if (i == nkv - 1) tc_commit(q_empty);
+        }
+        for (int j = 0; j < nkv; ++j) {
+          const uint32_t bph = (static_cast<uint32_t>(it) * (nkv >> 1) + (j >> 1)) & 1;   // phase of the per-buffer barriers
+          const int b = j & 1;
+          const bool more = j + 2 < nkv;
+          const int vs = vc % SA_STAGES;
+          const int ks = kc % SA_STAGES;
+          mbar_wait(&v_full[vs], (vc / SA_STAGES) & 1);
+          if (more) mbar_wait(&k_full[ks], (kc / SA_STAGES) & 1);
+          for (int t = 0; t < SA_QT; ++t) {
+            mbar_wait(&p_full[2 * t + b], bph);
+            tc_fence_after();
+            issue_pv(t, b, vs, j > 0 ? 1u : 0u);
+            if (more) issue_s(t, b, ks);   // S_{j+2} into the buffer whose P this P V has just consumed (issue order)
+          }
+          tc_commit(&v_empty[vs]);
+          ++vc;
+          if (more) {
+            tc_commit(&k_empty[ks]);
+            ++kc;
+            if (j + 3 == nkv) tc_commit(q_empty);   // the item's last S MMAs are issued: Q may be overwritten
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== softmax / correction / epilogue =====================
+    const int t = (warp - 4) >> 2;               // query tile of this warpgroup
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;               // query row inside the tile
+    const int wg_thread = threadIdx.x - (4 + 4 * t) * 32;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_off + t * 128;
+    const uint32_t o_addr = tmem_base + lane_off + SA_O_COL + t * 128;
+    uint8_t* ostage = smem_o + t * SA_OSTAGE;
+    const float c = a.scale_log2e;
+    const float2 c2 = make_float2(c, c);
+    float m_used = 0.f, l = 0.f;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        const uint32_t sa = s_addr + b * SA_BN;
+        const uint32_t pairs = static_cast<uint32_t>(it) * (nkv >> 1);   // completions of every per-buffer barrier before this item
+        mbar_wait(&s_full[2 * t + b], (pairs + (j >> 1)) & 1);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(sa, v0);
+        tmem_ld_32x32b_x32(sa + 32, v1);
+        tmem_ld_wait();
+        // ---- row maximum of the 64 scores (four independent chains)
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3])));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (j == 0) {
+          m_used = mx;
+          l = 0.f;
+        } else {
+          const bool need = (mx - m_used) * c > SA_RESCALE_LOG2;
+          if (__any_sync(0xffffffffu, need)) {
+            // raise the maximum in use and rescale O and the row sum; rows that did not need it take the exact new maximum too
+            const float m_new = fmaxf(m_used, mx);
+            const float f = sa_exp2((m_used - m_new) * c);
+            const float2 f2 = make_float2(f, f);
+            m_used = m_new;
+            l *= f;
+            // the previous P V of this tile (key tile j-1, other buffer) has retired; the one before it certainly has
+            // (S_j was issued after it and has completed), so this parity wait cannot alias
+            mbar_wait(&o_full[2 * t + (b ^ 1)], (pairs + ((j - 1) >> 1)) & 1);
+            tc_fence_after();
+            // 80 accumulator columns in three sequential pieces (rare path: keep the live register set small)
+#pragma unroll 1
+            for (int piece = 0; piece < 3; ++piece) {
+              uint32_t w[32];
+              if (piece < 2) tmem_ld_32x32b_x32(o_addr + 32 * piece, w);
+              else tmem_ld_32x32b_x16(o_addr + 64, *reinterpret_cast<uint32_t(*)[16]>(w));
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float2 x = __fmul2_rn(make_float2(__uint_as_float(w[i]), __uint_as_float(w[i + 1])), f2);
+                w[i] = __float_as_uint(x.x);
+                w[i + 1] = __float_as_uint(x.y);
+              }
+              if (piece < 2) tmem_st_32x32b_x32(o_addr + 32 * piece, w);
+              else tmem_st_32x32b_x16(o_addr + 64, *reinterpret_cast<uint32_t(*)[16]>(w));
+            }
+            tmem_st_wait();
+          }
+        }
+        // ---- P = exp2(S c - m c) as fp16 pairs, written over S (32 columns); row sum in fp32
+        const float neg = -m_used * c;
+        const float2 neg2 = make_float2(neg, neg);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t* src = i < 16 ? v0 : v1;
+          const int k2 = 2 * (i & 15);
+          const float2 sv = make_float2(__uint_as_float(src[k2]), __uint_as_float(src[k2 + 1]));
+          const float2 x = __ffma2_rn(sv, c2, neg2);
+          float e0 = sa_exp2(x.x), e1 = sa_exp2(x.y);
+          if (DBG) {
+            const int key = 2 * i;
+            if (a.debug == 2) {
+              e0 = (j < 2 && j * SA_BN + key == row) ? 1.0f : 0.0f;
+              e1 = (j < 2 && j * SA_BN + key + 1 == row) ? 1.0f : 0.0f;
+            }
+            if (a.debug == 3 && j < 2) {
+              float* d = a.dbg + ((static_cast<size_t>(item) * SA_QT + t) * SA_BM + row) * 128 + j * SA_BN + key;
+              d[0] = sv.x;
+              d[1] = sv.y;
+            }
+          }
+          if (i & 1) lb = __fadd2_rn(lb, make_float2(e0, e1));
+          else la = __fadd2_rn(la, make_float2(e0, e1));
+          const __half2 hp = __floats2half2_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        tmem_st_32x32b_x32(sa, pk);
+        l += (la.x + la.y) + (lb.x + lb.y);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * t + b]);
+      }
+      // ---- epilogue: O / l -> fp16 -> dense staging tile -> one TMA store of [128 queries x 72 dims] at (head, row)
+      {
+        // last key tile nkv-1 is odd: buffer 1, its (nkv/2)-th use in this item
+        mbar_wait(&o_full[2 * t + 1], (static_cast<uint32_t>(it) * (nkv >> 1) + (nkv >> 1) - 1) & 1);
+        tc_fence_after();
+        uint32_t v0[32], v1[32], w[8];
+        tmem_ld_32x32b_x32(o_addr, v0);
+        tmem_ld_32x32b_x32(o_addr + 32, v1);
+        tmem_ld_32x32b_x8(o_addr + 64, w);
+        tmem_ld_wait();
+        const float inv = __fdividef(1.0f, l);
+        uint32_t pk[36];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(v0[2 * i]) * inv, __uint_as_float(v0[2 * i + 1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(v1[2 * i]) * inv, __uint_as_float(v1[2 * i + 1]) * inv);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h0);
+          pk[16 + i] = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(w[2 * i]) * inv, __uint_as_float(w[2 * i + 1]) * inv);
+          pk[32 + i] = *reinterpret_cast<const uint32_t*>(&h0);
+        }
+        // the previous item's store has finished reading the staging tile
+        if (wg_thread == 0) tma_store_wait_read<0>();
+        named_bar_sync(1 + t, 128);
+        const uint32_t dst = smem_u32(ostage) + row * (SA_D * 2);   // 144-byte rows: 16-byte pieces of 8 consecutive rows hit 8 bank groups
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sts_v4_addr(dst + 16 * i, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + t, 128);
+        if (wg_thread == 0) {
+          const int qp = item % nqp;
+          const int h = (item / nqp) % a.H;
+          const int seq = item / (nqp * a.H);
+          tma_store_3d(&tmap_o, ostage, 0, h, seq * a.S + qp * (SA_QT * SA_BM) + t * SA_BM);
+          tma_store_commit();
+        }
+      }
+    }
+    if (wg_thread == 0) tma_store_wait<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, SA_TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiledSA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiledSA sa_encode_fn() {
+  static PFN_encodeTiledSA fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiledSA>(ptr);
+  return fn;
+}
+
+// q|k|v as a 4-D tensor (dim 72, head H, {q,k,v} 3, token rows): box = box_d dims x 128 tokens of one (head, which).
+// Dims past 72 are outside the innermost extent: the TMA unit fills them with zeros.
+static int make_qkv_tmap(CUtensorMap* out, const void* base, uint64_t rows, int H, uint32_t box_d, uint32_t box_rows,
+                         CUtensorMapSwizzle sw) {
+  PFN_encodeTiledSA enc = sa_encode_fn();
+  if (!enc) return VQ_ERR_DRIVER;
+  const uint64_t C = static_cast<uint64_t>(H) * SA_D;
+  cuuint64_t gdim[4] = {SA_D, static_cast<cuuint64_t>(H), 3, rows};
+  cuuint64_t gstride[3] = {SA_D * 2, C * 2, 3 * C * 2};
+  cuuint32_t box[4] = {box_d, 1u, 1u, box_rows};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
+}
+
+// output [rows, H * 72] as (dim 72, head H, token rows): box = one head's 72 dims x 128 tokens, dense in shared memory
+static int make_attn_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, int H) {
+  PFN_encodeTiledSA enc = sa_encode_fn();
+  if (!enc) return VQ_ERR_DRIVER;
+  const uint64_t C = static_cast<uint64_t>(H) * SA_D;
+  cuuint64_t gdim[3] = {SA_D, static_cast<cuuint64_t>(H), rows};
+  cuuint64_t gstride[2] = {SA_D * 2, C * 2};
+  cuuint32_t box[3] = {SA_D, 1u, static_cast<cuuint32_t>(SA_BM)};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
+}
+
+template <bool DBG>
+static int launch_spatial(const CUtensorMap& qa, const CUtensorMap& qb, const CUtensorMap& ka, const CUtensorMap& kb,
+                          const CUtensorMap& to, const SpatialArgs& a, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(vq_attn_spatial_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM_BYTES) !=
+        cudaSuccess)
+      return VQ_ERR_LAUNCH;
+    attr = true;
+  }
+  launch_pdl(vq_attn_spatial_kernel<DBG>, dim3(grid), dim3(SA_THREADS), SA_SMEM_BYTES, st, qa, qb, ka, kb, to, a);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+static int attn_spatial_impl(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale, int debug,
+                             float* dbg, uint32_t v_lbo, void* stream) {
+  if (!qkv || !out || n_seq <= 0 || S <= 0 || H <= 0) return VQ_ERR_ARG;
+  if (head_dim != SA_D || (S % (SA_QT * SA_BM)) != 0 || S < 4 * SA_BN) return VQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return VQ_ERR_ARG;
+  const uint64_t rows = static_cast<uint64_t>(n_seq) * S;
+  if (rows * 3 * H * SA_D >= (1ull << 40)) return VQ_ERR_UNSUPPORTED;
+  CUtensorMap qa, qb, ka, kb, to;
+  int rc = make_qkv_tmap(&qa, qkv, rows, H, 64, SA_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != VQ_OK) return rc;
+  rc = make_qkv_tmap(&qb, qkv, rows, H, 16, SA_BM, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc != VQ_OK) return rc;
+  rc = make_qkv_tmap(&ka, qkv, rows, H, 64, SA_BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != VQ_OK) return rc;
+  rc = make_qkv_tmap(&kb, qkv, rows, H, 16, SA_BN, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc != VQ_OK) return rc;
+  rc = make_attn_out_tmap(&to, out, rows, H);
+  if (rc != VQ_OK) return rc;
+  SpatialArgs a{n_seq, S, H, scale * 1.4426950408889634f, debug, dbg, v_lbo};
+  const long long items = static_cast<long long>(n_seq) * H * (S / (SA_QT * SA_BM));
+  const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return debug ? launch_spatial<true>(qa, qb, ka, kb, to, a, grid, st) : launch_spatial<false>(qa, qb, ka, kb, to, a, grid, st);
+}
+
+}  // namespace vq
+
+extern "C" int vq_attn_spatial(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale,
+                               void* stream) {
+  return vq::attn_spatial_impl(qkv, out, n_seq, S, H, head_dim, scale, 0, nullptr, 16, stream);
+}
+
+// bring-up / bisection entry used by tools/attn_selftest.cu only (not part of the C ABI in include/viditq_b200.h)
+extern "C" int vq_attn_spatial_debug(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale,
+                                     int debug, float* dbg, unsigned v_lbo, void* stream) {
+  return vq::attn_spatial_impl(qkv, out, n_seq, S, H, head_dim, scale, debug, dbg, v_lbo, stream);
+}

@@ -234,6 +234,25 @@ def attn_temporal(qkv, B, T, S, H, head_dim, scale, out=None):
     return out
 
 
+def attn_spatial(qkv, n_seq, S, H, head_dim, scale, out=None):
+    """qkv: fp16 [n_seq*S, 3*H*head_dim] (fused q|k|v GEMM output; n_seq = B*T frames of S tokens) -> fp16
+    [n_seq*S, H*head_dim], token-major. tcgen05 flash attention; head_dim 72, S a multiple of 256."""
+    _need_cuda_f16(qkv, "qkv")
+    C = H * head_dim
+    if qkv.shape != (n_seq * S, 3 * C):
+        raise _lib.VqError(f"attn_spatial: qkv shape {tuple(qkv.shape)} != {(n_seq * S, 3 * C)}")
+    if out is None:
+        out = torch.empty((n_seq * S, C), dtype=torch.float16, device=qkv.device)
+    rc = _lib.lib().vq_attn_spatial(_ptr(qkv), _ptr(out), n_seq, S, H, head_dim, float(scale), _stream())
+    _lib.check(rc, "vq_attn_spatial")
+    _count()
+    return out
+
+
+def attn_spatial_supported(S, head_dim):
+    return head_dim == 72 and S >= 256 and S % 256 == 0
+
+
 def attn_cross(q, kv, kv_start, kv_len, B, N, H, head_dim, max_len, scale, out=None):
     """q: fp16 [B*N, C]; kv: fp16 [sum(len), 2C]; kv_start/kv_len: int32 device tensors [B] -> fp16 [B*N, C]."""
     _need_cuda_f16(q, "q")
