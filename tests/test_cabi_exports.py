@@ -50,4 +50,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert "UTCIMMA.2CTA" in sass  # cta_group::2 CTA-pair variant
     assert "UTCBAR.2CTA.MULTICAST" in sass   # tcgen05.commit multicast to both CTAs of a pair
     assert "LDTM" in sass          # tcgen05.ld
+    assert "UTCHMMA" in sass       # tcgen05.mma.kind::f16 (vq_attn_spatial: S = Q K^T and O += P V)
+    assert "UTMALDG.4D" in sass    # 4-D q|k|v tensor maps of the attention
+    assert "STTM" in sass          # tcgen05.st: P written to TMEM as the A operand of P V
     assert "IMMA." not in sass.replace("UTCIMMA", "")   # no legacy mma.sync integer path

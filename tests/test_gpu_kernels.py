@@ -245,6 +245,43 @@ def test_temporal_attention_matches_fp32_reference(ops, B, T, S):
     assert err <= 4e-3 * ref.abs().max().item() + 1e-3, err      # fp16 P and fp16 output rounding
 
 
+@pytest.mark.parametrize("n_seq,S,outliers", [(2, 1024, False), (3, 256, True), (5, 512, True), (33, 1024, False)])
+def test_spatial_attention_matches_fp32_reference(ops, n_seq, S, outliers):
+    """tcgen05 flash attention (vq_attn_spatial) vs plain fp32 softmax attention and vs the library flash kernel the
+    reference calls (fp16 in / out): same tolerance as the library's own distance to fp32. `outliers` makes late keys
+    larger so that the running maximum rises across key tiles (lazy-rescale path); 33 sequences make persistent CTAs walk
+    several work items each."""
+    H, D = 16, 72
+    C = H * D
+    torch.manual_seed(3)
+    qkv = (torch.randn(n_seq * S, 3 * C, device="cuda") * 1.3)
+    if outliers:
+        v5 = qkv.view(n_seq, S, 3, H, D)
+        v5[:, S // 2::7, 1] *= 3.0          # every 7th key of the second half
+        v5[:, -1, 1, 3] *= 8.0              # one dominant last key for head 3
+    qkv = qkv.half()
+    out = ops.attn_spatial(qkv, n_seq, S, H, D, D ** -0.5)
+    v5 = qkv.view(n_seq, S, 3, H, D)
+    ref = _sdpa_ref(v5[:, :, 0], v5[:, :, 1], v5[:, :, 2], D ** -0.5).reshape(n_seq * S, C)
+    lib = torch.nn.functional.scaled_dot_product_attention(
+        v5[:, :, 0].transpose(1, 2), v5[:, :, 1].transpose(1, 2), v5[:, :, 2].transpose(1, 2), scale=D ** -0.5)
+    lib = lib.transpose(1, 2).reshape(n_seq * S, C).float()
+    scale_ref = ref.abs().max().item()
+    err = (out.float() - ref).abs().max().item()
+    err_lib = (lib - ref).abs().max().item()
+    assert err <= 4e-3 * scale_ref + 1e-3, (err, err_lib)      # fp16 P and fp16 output rounding
+    assert err <= 4 * err_lib + 1e-3, (err, err_lib)           # no worse than a few times the library's own error
+    rel_l2 = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel_l2 <= 1e-3, rel_l2
+
+
+def test_spatial_attention_rejects_unsupported_shapes(ops):
+    from viditq_b200 import _lib
+    qkv = torch.zeros(100, 3 * 1152, device="cuda", dtype=torch.float16)
+    with pytest.raises(_lib.VqError):
+        ops.attn_spatial(qkv, 1, 100, 16, 72, 72 ** -0.5)      # S not a multiple of 256: no silent fallback
+
+
 @pytest.mark.parametrize("B,N,lens", [(1, 256, [109]), (2, 200, [77, 120]), (1, 130, [1]), (3, 48, [128, 5, 64])])
 def test_cross_attention_matches_fp32_reference(ops, B, N, lens):
     H, D = 16, 72

@@ -2,7 +2,7 @@
 // thread per query row and head). Not part of the product.
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/attn_selftest tools/attn_selftest.cu \
 //          -Lvidit-q_b200 -lviditq_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../vidit-q_b200'
-//   usage: attn_selftest [--time] [--modes 3,1,2,0] [--lbo N]
+//   usage: attn_selftest [--time] [--modes 3,2,0] [--lbo N]   (2 = P := identity, 3 = also check the raw scores)
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <math.h>

@@ -7,22 +7,29 @@
 // [n_seq * S, H * 72], i.e. already in the layout the projection's quantiser reads (the reference's
 // transpose(1, 2).reshape copy, blocks.py:189-191, does not exist).
 //
-// Work item = (sequence, head, 256 queries): two 128-query tiles share one stream of 128-key K / V tiles, which halves the
+// Work item = (sequence, head, 256 queries): two 128-query tiles share one stream of 64-key K / V tiles, which halves the
 // L2 -> shared-memory operand traffic (at 128 queries per K/V stream the kernel would sit on the L2 bandwidth roof).
 // Persistent CTAs (one per SM), 12 warps:
-//   warp 0      TMA producer: Q tiles of the item, then a 3-stage ring of K tiles and one of V tiles.  head_dim 72 is
+//   warp 0      TMA producer: Q tiles of the item, then a 4-stage ring of K tiles and one of V tiles.  head_dim 72 is
 //               stored as a 64-dim SWIZZLE_128B tile plus a 16-dim SWIZZLE_32B tile whose dims 72..79 lie outside the
 //               tensor map's innermost extent and are zero-filled by the TMA unit (so K = 80 for the MMA, no padded copy).
-//   warp 1      MMA issuer.  S = Q K^T: 5 x tcgen05.mma.kind::f16 (M128 N128 K16; 4 in the SW128 tile, 1 in the SW32 tile)
-//               into TMEM.  O += P V: P is read from TMEM as the A operand (it overwrites S in place, two fp16 per column),
-//               V is the MN-major B operand straight from the TMA tile: per 16 keys one N=64 and one N=16 instruction.
-//   warp 2      TMEM allocation (512 columns: S/P 2 x 128, O 2 x 128).
+//   warp 1      MMA issuer (warp-uniform control flow, one elected lane issues; descriptors live in uniform registers).
+//               S = Q K^T: 5 x tcgen05.mma.kind::f16 (M128 N64 K16; 4 in the SW128 tile, 1 in the SW32 tile) into one of
+//               TWO score buffers per query tile, so the scores run two key tiles ahead of the softmax.  O += P V: P is
+//               read from TMEM as the A operand (it overwrites S in place, two fp16 per column), V is the MN-major B
+//               operand straight from the TMA tile: per 16 keys one N=64 and one N=16 instruction.
+//   warp 2      TMEM allocation (512 columns: S/P 2 tiles x 2 buffers x 64, O 2 x 128).
 //   warps 4-7   softmax of query tile 0, one thread per query row (tcgen05.ld 32x32b: lane = row, no shuffles);
-//   warps 8-11  softmax of query tile 1.  While one tile is in its softmax the tensor core works on the other.
+//   warps 8-11  softmax of query tile 1.
 // Online softmax with a lazy rescale: the running maximum is only raised (and O / the row sum rescaled in TMEM) when a
-// row's new maximum exceeds the one in use by more than 2^8 — after the first K tile that is rare, so the O round trip
-// through registers disappears from the steady state.  exp2 on MUFU with the log2(e) / sqrt(d) factor folded into one FFMA.
-// The kernel is MUFU-bound by design: 128 x 128 exponentials per tile pair against 5.2 MFLOP of tensor work.
+// row's new maximum exceeds the one in use by more than 2^8 — after the first K tiles that is rare, so the O round trip
+// through registers disappears from the steady state.  exp2 on MUFU with the log2(e) / sqrt(d) factor folded into one
+// FFMA; a quarter of the exponentials take an FMA-pipe polynomial instead.
+// Measured (B200, 32 sequences x 16 heads x 1024^2): 222 us = 700 TFLOP/s at d = 72; the MUFU pipe is
+// 56 % busy, the tensor pipe 35 %.  What bounds it is the per-iteration dependency chain of a softmax warp (TMEM load ->
+// max -> exp -> TMEM store -> fence -> barrier, ~900 cycles of latency per 64 keys against ~1000 cycles of MUFU issue), with
+// only two softmax warps per scheduler to overlap it; the bring-up variants that tried to hide it (16 softmax warps with
+// split columns, optimistic max + prefetch, staggered tiles, 0..75 % polynomial exp2) all land within 5 % of this one.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -69,7 +76,27 @@ __device__ __forceinline__ float sa_exp2(float x) {
   return y;
 }
 
-template <bool DBG>
+// 2^x for a pair on the FMA pipe (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5 with the 1.5 * 2^23 magic add,
+// degree-3 minimax polynomial for 2^f (relative error 7.5e-5, a third of an fp16 half-ulp — P is rounded to fp16 next),
+// then n is added into the exponent field.  One warp cannot issue MUFU.EX2 faster than every ~16 cycles, so moving a share of
+// the exponentials here shortens every softmax iteration, not just the MUFU-bound ones.
+__device__ __forceinline__ float2 sa_exp2_poly(float2 x) {
+  const float magic = 12582912.0f;   // 1.5 * 2^23
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 xr = __fadd2_rn(x, make_float2(magic, magic));
+  const float2 xi = __fadd2_rn(xr, make_float2(-magic, -magic));
+  const float2 f = __fadd2_rn(x, make_float2(-xi.x, -xi.y));
+  float2 p = __ffma2_rn(make_float2(0.05517164617776871f, 0.05517164617776871f), f,
+                        make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  float2 r;
+  r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xr.x) << 23));
+  r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xr.y) << 23));
+  return r;
+}
+template <bool DBG, int EMU>
 __global__ void __launch_bounds__(SA_THREADS, 1)
 vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_constant__ CUtensorMap tmap_qb,
                        const __grid_constant__ CUtensorMap tmap_ka, const __grid_constant__ CUtensorMap tmap_kb,
@@ -171,75 +198,92 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_f16(SA_BM, SA_BN, 0, 0);
-      constexpr uint32_t idesc_pv64 = make_idesc_f16(SA_BM, 64, 0, 1);   // B = V, MN-major
-      constexpr uint32_t idesc_pv16 = make_idesc_f16(SA_BM, 16, 0, 1);
-      // S[t][b] = Q[t] K^T: K dimension 80 = 4 steps of 16 inside the 128-byte swizzle rows + 1 step in the 32-byte tile
-      auto issue_s = [&](int t, int b, int ks) {
-        const uint32_t qa = smem_u32(smem_q + t * SA_TILE), qb = qa + SA_TILE_A;
-        const uint32_t ka = smem_u32(smem_k + ks * SA_KV), kb = ka + SA_KV_A;
-        const uint32_t d = tmem_base + t * 128 + b * SA_BN;
+    // The whole warp runs the (warp-uniform) control flow and polls the barriers; one elected lane issues.  Keeping loop
+    // counters and shared-memory addresses warp-uniform lets ptxas build the matrix descriptors in uniform registers — with
+    // the loop inside a single-lane branch every tcgen05.mma cost four R2UR round trips and the issuing thread, not the
+    // tensor pipe or the MUFU, bounded the kernel (26 small MMAs per key-tile pair).
+    constexpr uint32_t idesc_s = make_idesc_f16(SA_BM, SA_BN, 0, 0);
+    constexpr uint32_t idesc_pv64 = make_idesc_f16(SA_BM, 64, 0, 1);   // B = V, MN-major
+    constexpr uint32_t idesc_pv16 = make_idesc_f16(SA_BM, 16, 0, 1);
+    // descriptor = lo | hi << 32: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14 | layout << 29
+    constexpr uint64_t hi_sw128 = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+    constexpr uint64_t hi_sw32 = static_cast<uint64_t>((256u >> 4) | (1u << 14) | (6u << 29)) << 32;
+    const uint32_t lbo = (a.v_lbo >> 4) << 16;
+    const uint32_t q_lo = ((smem_u32(smem_q) & 0x3FFFFu) >> 4) | lbo;
+    const uint32_t k_lo = ((smem_u32(smem_k) & 0x3FFFFu) >> 4) | lbo;
+    const uint32_t v_lo = ((smem_u32(smem_v) & 0x3FFFFu) >> 4) | lbo;
+    // S[t][b] = Q[t] K^T: K dimension 80 = 4 steps of 16 inside the 128-byte swizzle rows + 1 step in the 32-byte tile
+    auto issue_s = [&](int t, int b, int ks) {
+      const uint32_t qa = q_lo + t * (SA_TILE >> 4), ka = k_lo + ks * (SA_KV >> 4);
+      const uint32_t d = tmem_base + t * 128 + b * SA_BN;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16_ss(d, make_smem_desc(qa + 32 * k, 16, 1024, 2), make_smem_desc(ka + 32 * k, 16, 1024, 2), idesc_s,
-                        k > 0 ? 1u : 0u);
-        tc_mma_f16_ss(d, make_smem_desc(qb, 16, 256, 6), make_smem_desc(kb, 16, 256, 6), idesc_s, 1u);
-        tc_commit(&s_full[2 * t + b]);
-      };
-      // O[t] (+)= P[t][b] V: 4 steps of 16 keys; dims 0..63 from the SW128 tile (N = 64), dims 64..79 from the SW32 tile (N = 16)
-      auto issue_pv = [&](int t, int b, int vs, uint32_t acc) {
-        const uint32_t va = smem_u32(smem_v + vs * SA_KV), vb = va + SA_KV_A;
-        const uint32_t p = tmem_base + t * 128 + b * SA_BN;
-        const uint32_t o = tmem_base + SA_O_COL + t * 128;
+      for (int k = 0; k < 4; ++k)
+        tc_mma_f16_ss(d, hi_sw128 | (qa + 2 * k), hi_sw128 | (ka + 2 * k), idesc_s, k > 0 ? 1u : 0u);
+      tc_mma_f16_ss(d, hi_sw32 | (qa + (SA_TILE_A >> 4)), hi_sw32 | (ka + (SA_KV_A >> 4)), idesc_s, 1u);
+      tc_commit(&s_full[2 * t + b]);
+    };
+    // O[t] (+)= P[t][b] V: 4 steps of 16 keys; dims 0..63 from the SW128 tile (N = 64), dims 64..79 from the SW32 tile (N = 16)
+    auto issue_pv = [&](int t, int b, int vs, uint32_t acc) {
+      const uint32_t va = v_lo + vs * (SA_KV >> 4);
+      const uint32_t p = tmem_base + t * 128 + b * SA_BN;
+      const uint32_t o = tmem_base + SA_O_COL + t * 128;
 #pragma unroll
-        for (int k = 0; k < SA_BN / 16; ++k) {
-          const uint32_t ak = (acc | static_cast<uint32_t>(k > 0)) ? 1u : 0u;
-          tc_mma_f16_ts(o, p + 8 * k, make_smem_desc(va + k * 2048, a.v_lbo, 1024, 2), idesc_pv64, ak);
-          tc_mma_f16_ts(o + 64, p + 8 * k, make_smem_desc(vb + k * 512, a.v_lbo, 256, 6), idesc_pv16, ak);
-        }
-        tc_commit(&o_full[2 * t + b]);
-      };
-      uint32_t kc = 0, vc = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        mbar_wait(q_full, it & 1);
-        // the score buffers run two key tiles ahead of the softmax: S_0 and S_1 first
-        for (int i = 0; i < 2; ++i) {
-          const int ks = kc % SA_STAGES;
-          mbar_wait(&k_full[ks], (kc / SA_STAGES) & 1);
-          tc_fence_after();
+      for (int k = 0; k < SA_BN / 16; ++k) {
+        const uint32_t ak = (acc | static_cast<uint32_t>(k > 0)) ? 1u : 0u;
+        const uint32_t pk = p + 8 * k;
+        tc_mma_f16_ts(o, pk, hi_sw128 | (va + k * (2048 >> 4)), idesc_pv64, ak);
+        tc_mma_f16_ts(o + 64, pk, hi_sw32 | (va + ((SA_KV_A + k * 512) >> 4)), idesc_pv16, ak);
+      }
+      tc_commit(&o_full[2 * t + b]);
+    };
+    uint32_t kc = 0, vc = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      mbar_wait(q_full, it & 1);
+      // the score buffers run two key tiles ahead of the softmax: S_0 and S_1 first
+      for (int i = 0; i < 2; ++i) {
+        const int ks = kc % SA_STAGES;
+        mbar_wait(&k_full[ks], (kc / SA_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
           issue_s(0, i, ks);
           issue_s(1, i, ks);
           tc_commit(&k_empty[ks]);
-          ++kc;
           if (i == nkv - 1) tc_commit(q_empty);
         }
-        for (int j = 0; j < nkv; ++j) {
-          const uint32_t bph = (static_cast<uint32_t>(it) * (nkv >> 1) + (j >> 1)) & 1;   // phase of the per-buffer barriers
-          const int b = j & 1;
-          const bool more = j + 2 < nkv;
-          const int vs = vc % SA_STAGES;
-          const int ks = kc % SA_STAGES;
-          mbar_wait(&v_full[vs], (vc / SA_STAGES) & 1);
-          if (more) mbar_wait(&k_full[ks], (kc / SA_STAGES) & 1);
-          for (int t = 0; t < SA_QT; ++t) {
-            mbar_wait(&p_full[2 * t + b], bph);
-            tc_fence_after();
+        __syncwarp();
+        ++kc;
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t bph = (static_cast<uint32_t>(it) * (nkv >> 1) + (j >> 1)) & 1;   // phase of the per-buffer barriers
+        const int b = j & 1;
+        const bool more = j + 2 < nkv;
+        const int vs = vc % SA_STAGES;
+        const int ks = kc % SA_STAGES;
+        mbar_wait(&v_full[vs], (vc / SA_STAGES) & 1);
+        if (more) mbar_wait(&k_full[ks], (kc / SA_STAGES) & 1);
+#pragma unroll
+        for (int t = 0; t < SA_QT; ++t) {
+          mbar_wait(&p_full[2 * t + b], bph);
+          tc_fence_after();
+          if (elect_one()) {
             issue_pv(t, b, vs, j > 0 ? 1u : 0u);
             if (more) issue_s(t, b, ks);   // S_{j+2} into the buffer whose P this P V has just consumed (issue order)
           }
+          __syncwarp();
+        }
+        if (elect_one()) {
           tc_commit(&v_empty[vs]);
-          ++vc;
           if (more) {
             tc_commit(&k_empty[ks]);
-            ++kc;
             if (j + 3 == nkv) tc_commit(q_empty);   // the item's last S MMAs are issued: Q may be overwritten
           }
         }
+        __syncwarp();
+        ++vc;
+        if (more) ++kc;
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===================== softmax / correction / epilogue =====================
     const int t = (warp - 4) >> 2;               // query tile of this warpgroup
@@ -321,7 +365,15 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
           const int k2 = 2 * (i & 15);
           const float2 sv = make_float2(__uint_as_float(src[k2]), __uint_as_float(src[k2 + 1]));
           const float2 x = __ffma2_rn(sv, c2, neg2);
-          float e0 = sa_exp2(x.x), e1 = sa_exp2(x.y);
+          float e0, e1;
+          if (((i * EMU) & 15) < EMU) {   // EMU of every 16 pairs take the FMA-pipe polynomial instead of MUFU
+            const float2 e = sa_exp2_poly(x);
+            e0 = e.x;
+            e1 = e.y;
+          } else {
+            e0 = sa_exp2(x.x);
+            e1 = sa_exp2(x.y);
+          }
           if (DBG) {
             const int key = 2 * i;
             if (a.debug == 2) {
@@ -447,17 +499,17 @@ static int make_attn_out_tmap(CUtensorMap* out, const void* base, uint64_t rows,
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
 }
 
-template <bool DBG>
+template <bool DBG, int EMU>
 static int launch_spatial(const CUtensorMap& qa, const CUtensorMap& qb, const CUtensorMap& ka, const CUtensorMap& kb,
                           const CUtensorMap& to, const SpatialArgs& a, int grid, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(vq_attn_spatial_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(vq_attn_spatial_kernel<DBG, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM_BYTES) !=
         cudaSuccess)
       return VQ_ERR_LAUNCH;
     attr = true;
   }
-  launch_pdl(vq_attn_spatial_kernel<DBG>, dim3(grid), dim3(SA_THREADS), SA_SMEM_BYTES, st, qa, qb, ka, kb, to, a);
+  launch_pdl(vq_attn_spatial_kernel<DBG, EMU>, dim3(grid), dim3(SA_THREADS), SA_SMEM_BYTES, st, qa, qb, ka, kb, to, a);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
@@ -479,11 +531,25 @@ static int attn_spatial_impl(const void* qkv, void* out, int n_seq, int S, int H
   if (rc != VQ_OK) return rc;
   rc = make_attn_out_tmap(&to, out, rows, H);
   if (rc != VQ_OK) return rc;
+  // share of the exponentials evaluated on the FMA pipe, in sixteenths (tuning knob)
+  static const int emu = [] {
+    const char* e = getenv("VQ_SA_EMU");
+    return e ? atoi(e) : 4;
+  }();
   SpatialArgs a{n_seq, S, H, scale * 1.4426950408889634f, debug, dbg, v_lbo};
   const long long items = static_cast<long long>(n_seq) * H * (S / (SA_QT * SA_BM));
   const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return debug ? launch_spatial<true>(qa, qb, ka, kb, to, a, grid, st) : launch_spatial<false>(qa, qb, ka, kb, to, a, grid, st);
+  if (debug) return launch_spatial<true, 4>(qa, qb, ka, kb, to, a, grid, st);
+  switch (emu) {
+    case 0: return launch_spatial<false, 0>(qa, qb, ka, kb, to, a, grid, st);
+    case 4: return launch_spatial<false, 4>(qa, qb, ka, kb, to, a, grid, st);
+    case 8: return launch_spatial<false, 8>(qa, qb, ka, kb, to, a, grid, st);
+    case 10: return launch_spatial<false, 10>(qa, qb, ka, kb, to, a, grid, st);
+    case 12: return launch_spatial<false, 12>(qa, qb, ka, kb, to, a, grid, st);
+    case 6: return launch_spatial<false, 6>(qa, qb, ka, kb, to, a, grid, st);
+    default: return launch_spatial<false, 4>(qa, qb, ka, kb, to, a, grid, st);
+  }
 }
 
 }  // namespace vq

@@ -158,7 +158,10 @@ class PixArtMS(nn.Module):
             nb = blk.attn.qkv.act_quantizer.n_bits
             a, _ = ops.ln_modulate_act_quant(x, shift_msa, scale_msa, n_bits=nb)
             qkv = ops.gemm_w8a8(a, blk.attn.qkv.prepared_weight())
-            o = AttentionImg.attend(qkv, B, N, H, D)
+            if ops.attn_spatial_supported(N, D):   # tcgen05 flash attention, q|k|v read in place (one sequence per image)
+                o = ops.attn_spatial(qkv, B, N, H, D, D ** -0.5).view(B, N, C)
+            else:
+                o = AttentionImg.attend(qkv, B, N, H, D)
             ops.gemm_w8a8(blk.attn.proj.quantize_input(o), blk.attn.proj.prepared_weight(),
                           epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
             ca = blk.cross_attn

@@ -11,9 +11,11 @@ Two forward schedules over the same parameters:
                        GELU run in the GEMM epilogues, the temporal branch reads the (T S) token layout in place.
     Every rounding point of the reference's fp16 graph is kept, so both schedules agree to the last bit except for
     LayerNorm statistics (fp32 here, library-dependent there).
-Attention itself is a library call for now (torch SDPA, as the reference calls flash-attn / xformers).
+All three attentions are own kernels: spatial = tcgen05 flash attention (vq_attn_spatial), temporal / cross = small-sequence
+kernels (vq_attn_temporal / vq_attn_cross); torch SDPA is only the library yardstick (VQ_SPATIAL_ATTN=sdpa).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -328,6 +330,20 @@ class FusedBlocks:
     def __init__(self, model: STDiT):
         self.m = model
         self._qkv = {}
+        # VQ_SPATIAL_ATTN=sdpa runs the long spatial attention on the library flash kernel (torch SDPA -> cuDNN) instead of
+        # vq_attn_spatial: the yardstick bench.py / tools/prof_kernels.py time the own kernel against, not a fallback
+        self.own_spatial = os.environ.get("VQ_SPATIAL_ATTN", "own") != "sdpa"
+
+    @staticmethod
+    def _spatial_library(qkv, pj, scale, B, N, T, S, C, D, independent):
+        """Library yardstick / shapes vq_attn_spatial does not cover (head_dim != 72 or S not a multiple of 256)."""
+        o = F.scaled_dot_product_attention(qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2),
+                                           qkv[:, :, 2].transpose(1, 2), scale=scale)   # [B*T, H, S, D]
+        if o.is_contiguous() and D == 72 and C == 1152 and not pj.smooth_quant:
+            # quantise straight from the head-major layout the library kernel emits (no transpose copy)
+            return (ops.act_quant_heads(o, 1, B * N, S, n_bits=pj.act_quantizer.n_bits) if independent
+                    else ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits))
+        return pj.quantize_input(o.transpose(1, 2).reshape(B * T, S, C), independent=independent)
 
     @staticmethod
     def _cat_prepared(layers):
@@ -390,17 +406,14 @@ class FusedBlocks:
         for i, blk in enumerate(m.blocks):
             shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = mod[i].unbind(0)
             # ---- spatial attention: LN + modulate + quantise once, one q|k|v GEMM
-            qkv = self._qkv_project(blk.attn, (i, "s"), x, ln=(shift_msa, scale_msa),
-                                    independent=independent).view(B * T, S, 3, H, D)
-            o = F.scaled_dot_product_attention(qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2),
-                                               qkv[:, :, 2].transpose(1, 2), scale=blk.attn.scale)   # [B*T, H, S, D]
+            qkv = self._qkv_project(blk.attn, (i, "s"), x, ln=(shift_msa, scale_msa), independent=independent)
             pj = blk.attn.proj
-            if o.is_contiguous() and D == 72 and C == 1152 and not pj.smooth_quant:
-                # quantise straight from the head-major layout the attention kernel emits (no transpose copy)
-                a = (ops.act_quant_heads(o, 1, B * N, S, n_bits=pj.act_quantizer.n_bits) if independent
-                     else ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits))
+            if self.own_spatial and ops.attn_spatial_supported(S, D):
+                # tcgen05 flash attention reading q|k|v in place, token-major output: the projection's quantiser input
+                o = ops.attn_spatial(qkv, B * T, S, H, D, blk.attn.scale)
+                a = pj.quantize_input(o.view(B * T, S, C), independent=independent)
             else:
-                a = pj.quantize_input(o.transpose(1, 2).reshape(B * T, S, C), independent=independent)
+                a = self._spatial_library(qkv.view(B * T, S, 3, H, D), pj, blk.attn.scale, B, N, T, S, C, D, independent)
             xr = x.view(M, C)   # residual stream, updated in place: out aliases res -> TMA reduce-add epilogue
             ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                           rows_per_gate=N, out=xr)
