@@ -120,9 +120,11 @@ int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S, int H, int
 int vq_attn_spatial(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale, void* stream);
 
 /* (a9) cross attention (blocks.py:292-310, xformers BlockDiagonalMask.from_seqlens([N]*B, y_lens)): q fp16
- * [B*N, H*head_dim]; kv fp16 [sum(len), 2*H*head_dim] (k | v); kv_start / kv_len: device int32 [B]; max_len <= 128. */
+ * [B*N, H*head_dim]; kv fp16 [kv_rows, 2*H*head_dim] (k | v), kv_rows = sum(len) = the rows actually allocated (the
+ * TMA tensor map is bounded by it); kv_start / kv_len: device int32 [B]; max_len <= 128.  N a multiple of 256 runs on
+ * the tcgen05 flash-attention kernel (keys past a sample's length masked), other N on a small mma.sync kernel.          */
 int vq_attn_cross(const void* q, const void* kv, void* out, const int32_t* kv_start, const int32_t* kv_len, int B,
-                  int N, int H, int head_dim, int max_len, float scale, void* stream);
+                  int N, int H, int head_dim, int max_len, int64_t kv_rows, float scale, void* stream);
 
 /* (a10 + N1) the sampler update of one denoise step for cfg_split models, fused: forward_with_cfg's combine
  * (iddpm/__init__.py:166-184: model_out / (1 + ptqd_k); eps = u + s (c - u) on channels [:3] (sic), the rest from the

@@ -282,7 +282,8 @@ def test_spatial_attention_rejects_unsupported_shapes(ops):
         ops.attn_spatial(qkv, 1, 100, 16, 72, 72 ** -0.5)      # S not a multiple of 256: no silent fallback
 
 
-@pytest.mark.parametrize("B,N,lens", [(1, 256, [109]), (2, 200, [77, 120]), (1, 130, [1]), (3, 48, [128, 5, 64])])
+@pytest.mark.parametrize("B,N,lens", [(1, 256, [109]), (2, 200, [77, 120]), (1, 130, [1]), (3, 48, [128, 5, 64]),
+                                      (3, 512, [128, 5, 64]), (2, 1024, [1, 120]), (5, 768, [64, 65, 63, 2, 127])])
 def test_cross_attention_matches_fp32_reference(ops, B, N, lens):
     H, D = 16, 72
     C = H * D

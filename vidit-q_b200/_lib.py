@@ -45,7 +45,7 @@ def lib():
     f32 = ctypes.c_float
     L.vq_attn_temporal.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp]
     L.vq_attn_spatial.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
-    L.vq_attn_cross.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
+    L.vq_attn_cross.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, f32, vp]
     L.vq_cfg_ddim_step.argtypes = [vp, vp, vp, vp, f32, ctypes.c_double, i32, i32, i32, i64, vp, vp]
     L.vq_status_read.argtypes = [vp, vp, vp]
     for name in EXPORTS:

@@ -299,10 +299,18 @@ extern "C" int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S,
 }
 
 extern "C" int vq_attn_cross(const void* q, const void* kv, void* out, const int32_t* kv_start, const int32_t* kv_len,
-                             int B, int N, int H, int head_dim, int max_len, float scale, void* stream) {
+                             int B, int N, int H, int head_dim, int max_len, int64_t kv_rows, float scale, void* stream) {
   using namespace vq;
   if (!q || !kv || !out || !kv_start || !kv_len || B <= 0 || N <= 0 || H <= 0) return VQ_ERR_ARG;
   if (head_dim != HD || max_len <= 0 || max_len > CROSS_KT * 16) return VQ_ERR_UNSUPPORTED;
+  // image-sized query sets: the tcgen05 flash-attention kernel (two 64-key tiles, ragged prompt masked); the mma.sync
+  // kernel below keeps the small / odd shapes (and is the bring-up reference: VQ_CROSS_TC=0)
+  static const bool allow_tc = [] {
+    const char* e = getenv("VQ_CROSS_TC");
+    return !(e && e[0] == '0');
+  }();
+  if (allow_tc && kv_rows > 0 && (N % 256) == 0)
+    return attn_cross_tc(q, kv, out, kv_start, kv_len, B, N, H, head_dim, kv_rows, scale, stream);
   CrossArgs a{static_cast<const __half*>(q), static_cast<const __half*>(kv), static_cast<__half*>(out), kv_start,
               kv_len, B, N, H, scale * 1.4426950408889634f};
   const int smem = (2 * CROSS_KT * 16 + 2 * CROSS_WARPS * 16) * PITCH * 2;

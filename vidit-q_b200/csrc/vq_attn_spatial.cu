@@ -68,6 +68,12 @@ struct SpatialArgs {
   int debug;        // 0 = attention; 1 = P := 1; 2 = P := identity on the first key tile; 3 = also dump S of key tile 0
   float* dbg;       // debug 3: [items][2][128][128] raw scores of the first key tile
   uint32_t v_lbo;   // leading byte offset written into the MN-major V descriptors (unused by the hardware when N fits one atom)
+  // cross attention (vq_attn_cross_tc): sequence = sample, S = image tokens per sample (queries), keys / values = that
+  // sample's prompt rows [kv_start[b], kv_start[b] + kv_len[b]) of a separate packed k|v tensor, at most 128 of them
+  int cross;
+  const int* kv_start;
+  const int* kv_len;
+  int k_which, v_which;   // index of k / v along the {q,k,v} (self) or {k,v} (cross) dimension of the K/V tensor map
 };
 
 __device__ __forceinline__ float sa_exp2(float x) {
@@ -125,7 +131,7 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nqp = a.S / (SA_QT * SA_BM);       // 256-query groups per sequence
-  const int nkv = a.S / SA_BN;                 // key tiles per sequence (even, >= 4)
+  const int nkv = a.cross ? 2 : a.S / SA_BN;   // key tiles per sequence (even)
   const int num_items = a.n_seq * a.H * nqp;
 
   if (warp == 0 && lane == 0) {
@@ -173,7 +179,7 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
         const int h = (item / nqp) % a.H;
         const int seq = item / (nqp * a.H);
         const int row_q0 = seq * a.S + qp * (SA_QT * SA_BM);
-        const int row_kv0 = seq * a.S;
+        const int row_kv0 = a.cross ? a.kv_start[seq] : seq * a.S;
         mbar_wait(q_empty, (it & 1) ^ 1);
         mbar_arrive_expect_tx(q_full, SA_QT * SA_TILE);
         for (int t = 0; t < SA_QT; ++t) {
@@ -186,12 +192,12 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
           // K / V tiles of a (sequence, head) are re-read by the other query groups of that head: keep them in L2
           mbar_wait(&k_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[s], SA_KV);
-          tma_load_4d_hint(smem_k + s * SA_KV, &tmap_ka, &k_full[s], 0, h, 1, row_kv0 + j * SA_BN, kEvictLast);
-          tma_load_4d_hint(smem_k + s * SA_KV + SA_KV_A, &tmap_kb, &k_full[s], 64, h, 1, row_kv0 + j * SA_BN, kEvictLast);
+          tma_load_4d_hint(smem_k + s * SA_KV, &tmap_ka, &k_full[s], 0, h, a.k_which, row_kv0 + j * SA_BN, kEvictLast);
+          tma_load_4d_hint(smem_k + s * SA_KV + SA_KV_A, &tmap_kb, &k_full[s], 64, h, a.k_which, row_kv0 + j * SA_BN, kEvictLast);
           mbar_wait(&v_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[s], SA_KV);
-          tma_load_4d_hint(smem_v + s * SA_KV, &tmap_ka, &v_full[s], 0, h, 2, row_kv0 + j * SA_BN, kEvictLast);
-          tma_load_4d_hint(smem_v + s * SA_KV + SA_KV_A, &tmap_kb, &v_full[s], 64, h, 2, row_kv0 + j * SA_BN, kEvictLast);
+          tma_load_4d_hint(smem_v + s * SA_KV, &tmap_ka, &v_full[s], 0, h, a.v_which, row_kv0 + j * SA_BN, kEvictLast);
+          tma_load_4d_hint(smem_v + s * SA_KV + SA_KV_A, &tmap_kb, &v_full[s], 64, h, a.v_which, row_kv0 + j * SA_BN, kEvictLast);
         }
       }
     }
@@ -299,6 +305,7 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
     float m_used = 0.f, l = 0.f;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int klen = a.cross ? a.kv_len[item / (nqp * a.H)] : a.S;   // keys of this item's sequence
       for (int j = 0; j < nkv; ++j) {
         const int b = j & 1;
         const uint32_t sa = s_addr + b * SA_BN;
@@ -309,6 +316,16 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
         tmem_ld_32x32b_x32(sa, v0);
         tmem_ld_32x32b_x32(sa + 32, v1);
         tmem_ld_wait();
+        const int n_valid = klen - j * SA_BN;
+        if (n_valid < SA_BN) {
+          // ragged prompt (cross attention): keys past the sample's length are other samples' rows or TMA zero fill —
+          // score -inf, so that they neither raise the maximum nor get a probability
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= n_valid) v0[i] = 0xff800000u;
+            if (32 + i >= n_valid) v1[i] = 0xff800000u;
+          }
+        }
         // ---- row maximum of the 64 scores (four independent chains)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -469,13 +486,13 @@ static PFN_encodeTiledSA sa_encode_fn() {
 
 // q|k|v as a 4-D tensor (dim 72, head H, {q,k,v} 3, token rows): box = box_d dims x 128 tokens of one (head, which).
 // Dims past 72 are outside the innermost extent: the TMA unit fills them with zeros.
-static int make_qkv_tmap(CUtensorMap* out, const void* base, uint64_t rows, int H, uint32_t box_d, uint32_t box_rows,
-                         CUtensorMapSwizzle sw) {
+static int make_qkv_tmap(CUtensorMap* out, const void* base, uint64_t rows, int H, int n_which, uint32_t box_d,
+                         uint32_t box_rows, CUtensorMapSwizzle sw) {
   PFN_encodeTiledSA enc = sa_encode_fn();
   if (!enc) return VQ_ERR_DRIVER;
   const uint64_t C = static_cast<uint64_t>(H) * SA_D;
-  cuuint64_t gdim[4] = {SA_D, static_cast<cuuint64_t>(H), 3, rows};
-  cuuint64_t gstride[3] = {SA_D * 2, C * 2, 3 * C * 2};
+  cuuint64_t gdim[4] = {SA_D, static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(n_which), rows};
+  cuuint64_t gstride[3] = {SA_D * 2, C * 2, static_cast<cuuint64_t>(n_which) * C * 2};
   cuuint32_t box[4] = {box_d, 1u, 1u, box_rows};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -513,21 +530,27 @@ static int launch_spatial(const CUtensorMap& qa, const CUtensorMap& qb, const CU
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
-static int attn_spatial_impl(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale, int debug,
-                             float* dbg, uint32_t v_lbo, void* stream) {
-  if (!qkv || !out || n_seq <= 0 || S <= 0 || H <= 0) return VQ_ERR_ARG;
+// self attention: q_base = kv_base = fused q|k|v [n_seq * S, 3C]; cross attention: q [n_seq * S, C], kv [kv_rows, 2C]
+static int attn_tc_impl(const void* q_base, const void* kv_base, void* out, int n_seq, int S, int H, int head_dim,
+                        float scale, int cross, uint64_t kv_rows, const int* kv_start, const int* kv_len, int debug,
+                        float* dbg, uint32_t v_lbo, void* stream) {
+  if (!q_base || !kv_base || !out || n_seq <= 0 || S <= 0 || H <= 0) return VQ_ERR_ARG;
   if (head_dim != SA_D || (S % (SA_QT * SA_BM)) != 0 || S < 4 * SA_BN) return VQ_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return VQ_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(q_base) & 15) || (reinterpret_cast<uintptr_t>(kv_base) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15))
+    return VQ_ERR_ARG;
   const uint64_t rows = static_cast<uint64_t>(n_seq) * S;
   if (rows * 3 * H * SA_D >= (1ull << 40)) return VQ_ERR_UNSUPPORTED;
+  const int nq = cross ? 1 : 3, nk = cross ? 2 : 3;
+  if (!cross) kv_rows = rows;
   CUtensorMap qa, qb, ka, kb, to;
-  int rc = make_qkv_tmap(&qa, qkv, rows, H, 64, SA_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_qkv_tmap(&qa, q_base, rows, H, nq, 64, SA_BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VQ_OK) return rc;
-  rc = make_qkv_tmap(&qb, qkv, rows, H, 16, SA_BM, CU_TENSOR_MAP_SWIZZLE_32B);
+  rc = make_qkv_tmap(&qb, q_base, rows, H, nq, 16, SA_BM, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != VQ_OK) return rc;
-  rc = make_qkv_tmap(&ka, qkv, rows, H, 64, SA_BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_qkv_tmap(&ka, kv_base, kv_rows, H, nk, 64, SA_BN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VQ_OK) return rc;
-  rc = make_qkv_tmap(&kb, qkv, rows, H, 16, SA_BN, CU_TENSOR_MAP_SWIZZLE_32B);
+  rc = make_qkv_tmap(&kb, kv_base, kv_rows, H, nk, 16, SA_BN, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != VQ_OK) return rc;
   rc = make_attn_out_tmap(&to, out, rows, H);
   if (rc != VQ_OK) return rc;
@@ -536,31 +559,36 @@ static int attn_spatial_impl(const void* qkv, void* out, int n_seq, int S, int H
     const char* e = getenv("VQ_SA_EMU");
     return e ? atoi(e) : 4;
   }();
-  SpatialArgs a{n_seq, S, H, scale * 1.4426950408889634f, debug, dbg, v_lbo};
+  SpatialArgs a{n_seq, S, H, scale * 1.4426950408889634f, debug, dbg, v_lbo, cross, kv_start, kv_len, cross ? 0 : 1,
+                cross ? 1 : 2};
   const long long items = static_cast<long long>(n_seq) * H * (S / (SA_QT * SA_BM));
   const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (debug) return launch_spatial<true, 4>(qa, qb, ka, kb, to, a, grid, st);
   switch (emu) {
     case 0: return launch_spatial<false, 0>(qa, qb, ka, kb, to, a, grid, st);
-    case 4: return launch_spatial<false, 4>(qa, qb, ka, kb, to, a, grid, st);
     case 8: return launch_spatial<false, 8>(qa, qb, ka, kb, to, a, grid, st);
-    case 10: return launch_spatial<false, 10>(qa, qb, ka, kb, to, a, grid, st);
-    case 12: return launch_spatial<false, 12>(qa, qb, ka, kb, to, a, grid, st);
-    case 6: return launch_spatial<false, 6>(qa, qb, ka, kb, to, a, grid, st);
     default: return launch_spatial<false, 4>(qa, qb, ka, kb, to, a, grid, st);
   }
+}
+
+// cross attention on the same kernel (declared in vq_internal.h, called by vq_attn_cross in vq_attention.cu)
+int attn_cross_tc(const void* q, const void* kv, void* out, const int* kv_start, const int* kv_len, int B, int N, int H,
+                  int head_dim, long long kv_rows, float scale, void* stream) {
+  if (!kv_start || !kv_len || kv_rows <= 0) return VQ_ERR_ARG;
+  return attn_tc_impl(q, kv, out, B, N, H, head_dim, scale, 1, static_cast<uint64_t>(kv_rows), kv_start, kv_len, 0,
+                      nullptr, 16, stream);
 }
 
 }  // namespace vq
 
 extern "C" int vq_attn_spatial(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale,
                                void* stream) {
-  return vq::attn_spatial_impl(qkv, out, n_seq, S, H, head_dim, scale, 0, nullptr, 16, stream);
+  return vq::attn_tc_impl(qkv, qkv, out, n_seq, S, H, head_dim, scale, 0, 0, nullptr, nullptr, 0, nullptr, 16, stream);
 }
 
 // bring-up / bisection entry used by tools/attn_selftest.cu only (not part of the C ABI in include/viditq_b200.h)
 extern "C" int vq_attn_spatial_debug(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale,
                                      int debug, float* dbg, unsigned v_lbo, void* stream) {
-  return vq::attn_spatial_impl(qkv, out, n_seq, S, H, head_dim, scale, debug, dbg, v_lbo, stream);
+  return vq::attn_tc_impl(qkv, qkv, out, n_seq, S, H, head_dim, scale, 0, 0, nullptr, nullptr, debug, dbg, v_lbo, stream);
 }

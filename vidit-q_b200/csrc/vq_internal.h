@@ -72,6 +72,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// cross attention on the tcgen05 flash-attention kernel of vq_attn_spatial.cu (N a multiple of 256, prompts <= 128 rows)
+int attn_cross_tc(const void* q, const void* kv, void* out, const int* kv_start, const int* kv_len, int B, int N, int H,
+                  int head_dim, long long kv_rows, float scale, void* stream);
 int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch,
                         uint32_t box_rows);
 }  // namespace vq

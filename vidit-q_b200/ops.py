@@ -261,7 +261,7 @@ def attn_cross(q, kv, kv_start, kv_len, B, N, H, head_dim, max_len, scale, out=N
     if out is None:
         out = torch.empty((B * N, C), dtype=torch.float16, device=q.device)
     rc = _lib.lib().vq_attn_cross(_ptr(q), _ptr(kv), _ptr(out), _ptr(kv_start), _ptr(kv_len), B, N, H, head_dim,
-                                  int(max_len), float(scale), _stream())
+                                  int(max_len), int(kv.shape[0]), float(scale), _stream())
     _lib.check(rc, "vq_attn_cross")
     _count()
     return out
