@@ -74,6 +74,15 @@ int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, in
 int vq_act_quant_static(const void* x, int M, int K, int64_t ld, const void* delta, const void* zp, int period,
                         const void* smooth, int n_bits, uint8_t* codes, int32_t* rowsum, void* stream);
 
+/* (a1) on h(x + addv[(r / rows_per_add) % add_period]): the temporal position embedding added in front of block 0's
+ * temporal attention (stdit.py:113-115, `x + self.pos_embed_temporal` on the "(B S) T C" view; in the (T S) token order the
+ * embedding of frame t belongs to rows [t S, (t + 1) S): rows_per_add = S, add_period = T), an fp16 add, fused into the
+ * quantiser of attn_temp's q|k|v input instead of a separate pass over the hidden tensor.  x fp16 [G*rows, K] contiguous,
+ * addv fp16 [add_period, K]; K = 1152.  Outputs as vq_act_quant.                                                     */
+int vq_add_act_quant(const void* x, const void* addv, int rows_per_add, int add_period, int G, int rows, int K,
+                     const void* smooth, int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum,
+                     uint32_t* status, void* stream);
+
 /* nn.GELU(approximate="tanh") + (a1), one pass: the activation between Mlp.fc1 and Mlp.fc2 (reference
  * opensora/models/stdit/stdit.py:109-111 timm Mlp with approx_gelu; PixArt_blocks / PixArtMS.py:60 likewise) applied to
  * the fp16 fc1 output x on its way into fc2's DynamicActQuantizer (quant_layer.py:137-140: smooth division, then
@@ -136,6 +145,13 @@ int vq_attn_cross(const void* q, const void* kv, void* out, const int32_t* kv_st
  * fp32 reciprocal of the Python scalar).                                              */
 int vq_cfg_ddim_step(const float* out_cond, const float* out_uncond, const float* x, const float* coef,
                      float cfg_scale, double ptqd_k, int n, int c_out, int c, int64_t inner, float* x_new, void* stream);
+
+/* (N2) patch embedding fused with the spatial position embedding: STDiT `x_embedder` (PatchEmbed3D, Conv3d kernel = stride =
+ * (1, ph, pw), blocks.py:60-110) + rearrange + `x + pos_embed` (stdit.py:255-258); PixArt's Conv2d patchify is the T = 1
+ * case.  latent fp32 [B, Cin, T, Hh, Ww] (rounded to fp16 like x.to(dtype)); weight fp16 [C, Cin*ph*pw]; bias fp16 [C] or
+ * NULL; pos fp16 [S, C] (S = Hh/ph * Ww/pw) or NULL; out fp16 [B, T*S, C].  Cin*ph*pw <= 16, C % 4 == 0, C <= 1280.      */
+int vq_patch_embed(const float* latent, const void* weight, const void* bias, const void* pos, int B, int Cin, int T,
+                   int Hh, int Ww, int ph, int pw, int C, void* out, void* stream);
 
 /* status word helpers (host side; the only calls here that synchronise) */
 int vq_status_read(const uint32_t* status_dev, uint32_t* host_out, void* stream);

@@ -407,3 +407,43 @@ def test_static_quant_layer_module_path(ops, golden_static):
     ref = c["out"].astype(np.float32)
     assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-3
     assert np.abs(y - ref).max() / np.abs(ref).max() <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------- patch embedding
+@pytest.mark.parametrize("B,T,H,W", [(2, 16, 64, 64), (1, 3, 6, 10), (3, 1, 8, 8)])
+def test_patch_embed_matches_conv3d_plus_pos(ops, B, T, H, W):
+    """vq_patch_embed == Conv3d(kernel = stride = (1,2,2)) on the fp16-rounded latent + transpose + pos_embed add
+    (stdit.py:255-258), up to the summation order inside the 16-term dot product (last fp16 bit)."""
+    C, Cin = 1152, 4
+    torch.manual_seed(5)
+    conv = torch.nn.Conv3d(Cin, C, kernel_size=(1, 2, 2), stride=(1, 2, 2)).cuda().half()
+    S = (H // 2) * (W // 2)
+    pos = (torch.randn(S, C, device="cuda") * 0.5).half()
+    z = torch.randn(B, Cin, T, H, W, device="cuda")
+    out = ops.patch_embed(z, conv.weight, conv.bias, pos, (2, 2))
+    # reference in fp32 on the fp16-rounded operands, rounded to fp16 where the fp16 graph rounds
+    y = torch.nn.functional.conv3d(z.half().float(), conv.weight.float(), conv.bias.float(), stride=(1, 2, 2))
+    y = y.half().flatten(2).transpose(1, 2).reshape(B, T, S, C)
+    ref = (y + pos).reshape(B, T * S, C)           # fp16 add
+    assert out.shape == ref.shape
+    diff = (out.float() - ref.float()).abs()
+    # one fp16 ulp of the larger of (conv output, position embedding, sum): the add can cancel
+    mag = torch.maximum(torch.maximum(y.float().abs(), pos.float().abs().expand_as(y)).reshape(B, T * S, C), ref.float().abs())
+    ulp = torch.clamp(mag, min=1e-3) * 2.0 ** -10
+    assert bool((diff <= 2.02 * ulp).all()), float((diff / ulp).max())   # 1 ulp of the conv output, then 1 of the sum
+    assert float((out != ref).float().mean()) < 2e-2     # and almost always bit-identical
+
+
+@pytest.mark.parametrize("G,T,S,smooth", [(1, 16, 40, False), (2, 4, 33, True)])
+def test_add_act_quant_equals_add_then_quant(ops, G, T, S, smooth):
+    """vq_add_act_quant == the fp16 add of the temporal position embedding followed by the plain quantiser, bit for bit."""
+    K = 1152
+    torch.manual_seed(7)
+    x = (torch.randn(G, T * S, K, device="cuda") * 2).half()
+    tpe = torch.randn(T, K, device="cuda").half()
+    sm = (torch.rand(K, device="cuda") + 0.5).half() if smooth else None
+    a = ops.add_act_quant(x, tpe, S, smooth=sm)
+    xt = (x.view(G, T, S, K) + tpe.view(1, T, 1, K)).view(G, T * S, K).contiguous()
+    b = ops.act_quant(xt, smooth=sm)
+    for u, v in ((a.codes, b.codes), (a.delta, b.delta), (a.zp, b.zp), (a.rowsum, b.rowsum)):
+        assert torch.equal(u, v)

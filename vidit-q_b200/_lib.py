@@ -13,8 +13,8 @@ VQ_EPI_BIAS, VQ_EPI_GELU_TANH, VQ_EPI_GATE_RESIDUAL = 0, 1, 2
 VQ_STATUS_EPS_DEGENERATE = 1
 _ERR = {-1: "VQ_ERR_ARG", -2: "VQ_ERR_DRIVER", -3: "VQ_ERR_TMAP", -4: "VQ_ERR_LAUNCH", -5: "VQ_ERR_UNSUPPORTED"}
 
-EXPORTS = ["vq_version", "vq_num_sms", "vq_prep_weight", "vq_act_quant", "vq_act_quant_static", "vq_gelu_act_quant", "vq_act_quant_heads", "vq_ln_modulate_act_quant", "vq_gemm_w8a8",
-           "vq_attn_temporal", "vq_attn_cross", "vq_attn_spatial", "vq_cfg_ddim_step", "vq_status_read"]
+EXPORTS = ["vq_version", "vq_num_sms", "vq_prep_weight", "vq_act_quant", "vq_act_quant_static", "vq_add_act_quant", "vq_gelu_act_quant", "vq_act_quant_heads", "vq_ln_modulate_act_quant", "vq_gemm_w8a8",
+           "vq_attn_temporal", "vq_attn_cross", "vq_attn_spatial", "vq_cfg_ddim_step", "vq_patch_embed", "vq_status_read"]
 
 _lib = None
 
@@ -37,6 +37,7 @@ def lib():
     L.vq_num_sms.restype = i32
     L.vq_prep_weight.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
     L.vq_act_quant.argtypes = [vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.vq_add_act_quant.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     L.vq_act_quant_static.argtypes = [vp, i32, i32, i64, vp, vp, i32, vp, i32, vp, vp, vp]
     L.vq_gelu_act_quant.argtypes = [vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp]
     L.vq_act_quant_heads.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
@@ -47,6 +48,7 @@ def lib():
     L.vq_attn_spatial.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
     L.vq_attn_cross.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, f32, vp]
     L.vq_cfg_ddim_step.argtypes = [vp, vp, vp, vp, f32, ctypes.c_double, i32, i32, i32, i64, vp, vp]
+    L.vq_patch_embed.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.vq_status_read.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name).restype = i32

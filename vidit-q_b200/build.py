@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libviditq_b200.so")
-SOURCES = ["vq_gemm_w8a8.cu", "vq_quant.cu", "vq_attention.cu", "vq_attn_spatial.cu", "vq_sampler.cu"]
+SOURCES = ["vq_gemm_w8a8.cu", "vq_quant.cu", "vq_attention.cu", "vq_attn_spatial.cu", "vq_sampler.cu", "vq_embed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",

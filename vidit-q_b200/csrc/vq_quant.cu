@@ -377,6 +377,8 @@ struct ActQuantArgs {
   int rows_per_mod;      // LN mode: row (g, r) uses modulation vector (g * rows + r) / rows_per_mod
   __half* y_out;         // optional [G*rows, K] transformed input (LN mode)
   int head_S;            // > 0: x is head-major [G*rows / head_S, H, head_S, 72] (attention output), H = K / 72
+  const __half* addv;    // optional [add_period, K]: row r is quantised as h(x + addv[(r / rows_per_add) % add_period])
+  int rows_per_add, add_period;
   float qmax;
   uint8_t* codes;
   __half* delta;
@@ -477,8 +479,22 @@ __device__ __forceinline__ void uload_any(UnitRegs<U>& regs, const ActQuantArgs&
   }
 }
 
+template <int U>
+__device__ __forceinline__ void uapply_add(UnitRegs<U>& r, const __half* addrow, int lane) {
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const uint2 av = __ldg(reinterpret_cast<const uint2*>(addrow) + lane + 32 * i);
+    __half2* x = reinterpret_cast<__half2*>(&r.u[i]);
+    const __half2* ad = reinterpret_cast<const __half2*>(&av);
+    x[0] = __hadd2_rn(x[0], ad[0]);
+    x[1] = __hadd2_rn(x[1], ad[1]);
+  }
+}
+
 template <int U, bool LN>
 __device__ __forceinline__ void utransform(UnitRegs<U>& regs, const ActQuantArgs& a, int g, int r, int lane) {
+  if (!LN && a.addv)   // the temporal position embedding of block 0 (stdit.py:113-115: x + tpe, an fp16 add), fused
+    uapply_add<U>(regs, a.addv + static_cast<size_t>((r / a.rows_per_add) % a.add_period) * a.K, lane);
   if (LN) {
     uapply_ln_modulate<U>(regs, a.shift + mod_offset(a, g, r), a.scale + mod_offset(a, g, r), a.K, lane);
     if (a.smooth) uapply_smooth<U>(regs, a.smooth, lane);
@@ -530,6 +546,8 @@ __global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuan
       if (a.G > 1) {  // G == 1: the transformed row is still in registers
         uload_any<U, HEADS>(regs, a, g, r, lane);
         UnitRegs<U>& rr = regs;
+        if (!LN && a.addv)
+          uapply_add<U>(rr, a.addv + static_cast<size_t>((r / a.rows_per_add) % a.add_period) * a.K, lane);
         if (LN) {
           uapply_ln_modulate<U>(rr, a.shift + mod_offset(a, g, r), a.scale + mod_offset(a, g, r), a.K, lane);
           if (a.smooth) uapply_smooth<U>(rr, a.smooth, lane);
@@ -786,6 +804,30 @@ extern "C" int vq_act_quant(const void* x, int G, int rows, int K, int64_t group
   a.G = G; a.rows = rows; a.K = K;
   a.group_stride = group_stride; a.ld = ld;
   a.smooth = static_cast<const __half*>(smooth);
+  a.qmax = static_cast<float>((1 << n_bits) - 1);
+  a.codes = codes;
+  a.delta = static_cast<__half*>(delta);
+  a.zp = static_cast<__half*>(zp);
+  a.rowsum = rowsum;
+  a.status = status;
+  return launch_act_quant<false>(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vq_add_act_quant(const void* x, const void* addv, int rows_per_add, int add_period, int G, int rows, int K,
+                                const void* smooth, int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum,
+                                uint32_t* status, void* stream) {
+  using namespace vq;
+  if (!x || !addv || !codes || !delta || !zp || !rowsum || G <= 0 || rows <= 0) return VQ_ERR_ARG;
+  if (rows_per_add <= 0 || add_period <= 0 || n_bits < 2 || n_bits > 8) return VQ_ERR_ARG;
+  if (K != 9 * 128) return VQ_ERR_UNSUPPORTED;   // the branch-free K = 1152 kernel only
+  ActQuantArgs a{};
+  a.x = static_cast<const __half*>(x);
+  a.G = G; a.rows = rows; a.K = K;
+  a.group_stride = static_cast<long long>(rows) * K; a.ld = K;
+  a.smooth = static_cast<const __half*>(smooth);
+  a.addv = static_cast<const __half*>(addv);
+  a.rows_per_add = rows_per_add;
+  a.add_period = add_period;
   a.qmax = static_cast<float>((1 << n_bits) - 1);
   a.codes = codes;
   a.delta = static_cast<__half*>(delta);

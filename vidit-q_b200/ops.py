@@ -63,6 +63,35 @@ def cfg_ddim_step(out_cond, out_uncond, x, coef, cfg_scale, ptqd_k=0.0, out=None
     return out
 
 
+def patch_embed(latent, weight, bias, pos, patch_hw, T=None):
+    """Fused patchify + position embedding. latent: fp32 CUDA [B, Cin, T, H, W] (or [B, Cin, H, W]); weight: fp16 conv
+    weight [C, Cin, (1,) ph, pw]; bias fp16 [C] or None; pos fp16 [S, C] or None -> fp16 [B, T*S, C]."""
+    if not (latent.is_cuda and latent.dtype == torch.float32 and latent.is_contiguous()):
+        raise _lib.VqError("patch_embed: latent must be a contiguous CUDA fp32 tensor (no CPU fallback)")
+    if latent.dim() == 4:
+        latent = latent.unsqueeze(2)
+    B, Cin, T_, Hh, Ww = latent.shape
+    ph, pw = patch_hw
+    C = weight.shape[0]
+    w2 = weight.reshape(C, -1)
+    _need_cuda_f16(w2, "weight")
+    if w2.shape[1] != Cin * ph * pw:
+        raise _lib.VqError(f"patch_embed: weight {tuple(weight.shape)} is not a depth-1 ({ph}, {pw}) patch kernel")
+    if bias is not None:
+        _need_cuda_f16(bias, "bias")
+    S = (Hh // ph) * (Ww // pw)
+    if pos is not None:
+        _need_cuda_f16(pos, "pos")
+        if pos.numel() != S * C:
+            raise _lib.VqError(f"patch_embed: pos has {pos.numel()} elements, expected {S * C}")
+    out = torch.empty((B, T_ * S, C), dtype=torch.float16, device=latent.device)
+    rc = _lib.lib().vq_patch_embed(_ptr(latent), _ptr(w2), _ptr(bias), _ptr(pos), B, Cin, T_, Hh, Ww, ph, pw, C, _ptr(out),
+                                   _stream())
+    _lib.check(rc, "vq_patch_embed")
+    _count()
+    return out
+
+
 def check_status(device=None):
     """Poll the sticky device status word (synchronises; call outside the hot loop). Raises on the reference's
     degenerate-eps quirk (base_quantizer.py:220-223), whose fp16 result is non-finite garbage in the reference."""
@@ -135,6 +164,24 @@ def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None, gelu=Fal
     rc = fn(_ptr(x), G, rows, K, rows * K, K, _ptr(smooth), n_bits, _ptr(a.codes), _ptr(a.delta),
             _ptr(a.zp), _ptr(a.rowsum), _ptr(status_word(x.device)), _stream())
     _lib.check(rc, "vq_gelu_act_quant" if gelu else "vq_act_quant")
+    _count()
+    return a
+
+
+def add_act_quant(x, addv, rows_per_add, n_bits=8, smooth=None) -> ActCodes:
+    """Quantise h(x + addv[(r // rows_per_add) % len(addv)]) per token: x fp16 [G, rows, K], addv fp16 [period, K]."""
+    _need_cuda_f16(x, "x")
+    _need_cuda_f16(addv, "addv")
+    G, rows, K = x.shape
+    if addv.dim() != 2 or addv.shape[1] != K:
+        raise _lib.VqError(f"add_act_quant: addv {tuple(addv.shape)} does not match K={K}")
+    a = _alloc_act(G, rows, K, x.device)
+    if smooth is not None:
+        _need_cuda_f16(smooth, "smooth")
+    rc = _lib.lib().vq_add_act_quant(_ptr(x), _ptr(addv), int(rows_per_add), addv.shape[0], G, rows, K, _ptr(smooth), n_bits,
+                                     _ptr(a.codes), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum), _ptr(status_word(x.device)),
+                                     _stream())
+    _lib.check(rc, "vq_add_act_quant")
     _count()
     return a
 

@@ -253,14 +253,21 @@ class STDiT(nn.Module):
         return (torch.tensor(starts, dtype=torch.int32, device=device),
                 torch.tensor(list(y_lens), dtype=torch.int32, device=device))
 
-    def embed(self, x, timestep, y, mask, plan=None):
-        x = x.to(self.dtype)
+    def embed(self, x, timestep, y, mask, plan=None, fused=False):
         timestep = timestep.to(self.dtype)
         y = y.to(self.dtype)
         B = x.shape[0]
         T, S, C = self.num_temporal, self.num_spatial, self.hidden_size
-        x = self.x_embedder(x).view(B, T, S, C) + self.pos_embed
-        x = x.view(B, T * S, C)
+        proj = self.x_embedder.proj
+        if fused and self.patch_size[0] == 1 and proj.weight.dtype == torch.float16:
+            # one pass: patchify + bias + "B (T S) C" layout + pos_embed (vq_patch_embed) instead of conv3d, two layout
+            # conversions, a transposing add
+            x = ops.patch_embed(x.float().contiguous(), proj.weight, proj.bias, self.pos_embed.to(torch.float16).reshape(S, C),
+                                self.patch_size[1:])
+        else:
+            x = x.to(self.dtype)
+            x = self.x_embedder(x).view(B, T, S, C) + self.pos_embed
+            x = x.view(B, T * S, C)
         t = self.t_embedder(timestep, dtype=x.dtype)
         t0 = self.t_block(t)
         y = self.y_embedder(y)
@@ -303,7 +310,7 @@ class STDiT(nn.Module):
         cond / uncond halves of cfg_split=True (iddpm/__init__.py:156-157 calls the model twice with batch n_prompts = 1).
         Their per-token statistics are not pooled (each row is quantised on its own, which is what two batch-1 calls do);
         results are identical to calling forward_fused once per entry, at half the launches and better-filled GEMM waves."""
-        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan)
+        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan, fused=True)
         eng = getattr(self, "_engine", None)
         if eng is None:
             eng = self._engine = FusedBlocks(self)
@@ -365,10 +372,12 @@ class FusedBlocks:
             pw = self._qkv[key] = self._cat_prepared(layers)
         return pw
 
-    def _qkv_project(self, attn, tag, x, ln=None, independent=False):
+    def _qkv_project(self, attn, tag, x, ln=None, independent=False, add=None):
         """q|k|v of one attention as one [M, 3C] tensor. ln = (shift, scale) fuses LayerNorm+modulate in front.
         Without smooth-quant: one quantise pass + one N=3C GEMM. With it (w4a8_timestep_aware_cb.yaml): each layer has
-        its own channel scale, hence its own codes; the three GEMMs write column slices of the same output."""
+        its own channel scale, hence its own codes; the three GEMMs write column slices of the same output.
+        add = (vectors [period, C], rows_per_add): an fp16 row-broadcast add fused in front of the quantiser (block 0's
+        temporal position embedding) when K = 1152."""
         pw = self._qkv_weight(attn, tag)
         nb = attn.q.act_quantizer.n_bits
         rpm = None
@@ -376,8 +385,12 @@ class FusedBlocks:
             rpm = x.shape[1]
             x = x.view(1, -1, x.shape[2])
         if pw is not None:
-            a = (ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, rows_per_mod=rpm)[0] if ln is not None
-                 else ops.act_quant(x, n_bits=nb))
+            if ln is not None:
+                a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, rows_per_mod=rpm)[0]
+            elif add is not None:
+                a = ops.add_act_quant(x, add[0], add[1], n_bits=nb)
+            else:
+                a = ops.act_quant(x, n_bits=nb)
             return ops.gemm_w8a8(a, pw)
         B, N, C = x.shape
         out = torch.empty(B * N, 3 * C, dtype=x.dtype, device=x.device)
@@ -386,6 +399,8 @@ class FusedBlocks:
             sm = getattr(lw, "smooth", None)
             if ln is not None:
                 a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, smooth=sm, rows_per_mod=rpm)[0]
+            elif add is not None:
+                a = ops.add_act_quant(x, add[0], add[1], n_bits=nb, smooth=sm)
             else:
                 a = ops.act_quant(x, n_bits=nb, smooth=sm)
             ops.gemm_w8a8(a, lw, out=out[:, j * C:(j + 1) * C], ldo=3 * C)
@@ -418,8 +433,11 @@ class FusedBlocks:
             ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                           rows_per_gate=N, out=xr)
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
-            xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
-            qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt, independent=independent)
+            if i == 0 and C == 1152:   # x + tpe rides in the quantise pass (vq_add_act_quant): frame t = (row // S) % T
+                qkv = self._qkv_project(blk.attn_temp, (i, "t"), x, independent=independent, add=(tpe.view(T, C), S))
+            else:
+                xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
+                qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt, independent=independent)
             if T <= 16 and D == 72:      # own kernel: reads the (T S) layout in place, no permute copies
                 o = ops.attn_temporal(qkv, B, T, S, H, D, blk.attn_temp.scale).view(B, N, C)
             else:                        # library path for shapes the kernel does not cover
