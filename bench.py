@@ -193,6 +193,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cfg-mode", default="stacked", choices=["stacked", "split"],
                     help="cfg_split's cond / uncond forwards as one stacked launch sequence (default) or two calls")
+    ap.add_argument("--parallelism", default="samples", choices=["samples", "cfg-branch"],
+                    help="samples: one sample per rank, no data-path collective (the metric, weak scaling). cfg-branch: "
+                         "two ranks per sample, one CFG branch each, model outputs exchanged every step (latency / "
+                         "strong scaling of one sample; needs an even --gpus)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -208,15 +212,20 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from viditq_b200 import ops
+    from viditq_b200 import ops, shard
     from viditq_b200.sampler import SpacedDDIM
-    torch.manual_seed(1234 + rank)
+    pairs = args.parallelism == "cfg-branch"
+    if pairs and (world < 2 or world % 2):
+        raise SystemExit("--parallelism cfg-branch needs an even number of ranks")
+    pair_group = shard.cfg_pair_groups() if pairs else None
+    sample_id = rank // 2 if pairs else rank          # both ranks of a pair hold the same sample and the same weights
+    torch.manual_seed(1234 + sample_id)
     torch.set_grad_enabled(False)
     qnn, model = build_model(dev, args.depth)
     ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
 
     # host (pinned) inputs of one step of this rank's sample; static device buffers the graph reads
-    g = torch.Generator().manual_seed(99 + rank)
+    g = torch.Generator().manual_seed(99 + sample_id)
     h_z = torch.randn(1, 4, T_FRAMES, 64, 64, generator=g).pin_memory()
     h_yc = torch.randn(1, 1, PROMPT_LEN, 4096, generator=g).pin_memory()
     h_yu = torch.randn(1, 1, PROMPT_LEN, 4096, generator=g).pin_memory()
@@ -245,7 +254,10 @@ def main():
         """The denoise step on device-resident inputs (iddpm forward_with_cfg + ddim_sample, cfg_split): the cond and
         uncond forwards of cfg_split run as one stacked launch sequence with un-pooled statistics (== two batch-1 calls,
         tests/test_gpu_stdit.py::test_stacked_cfg_split_equals_two_separate_forwards)."""
-        if args.cfg_mode == "stacked":
+        if pairs:   # this rank's branch only; the 2 MB outputs cross NVLink, then both ranks apply the same update
+            mine = model.forward_fused(d_z, d_t, d_yu if shard.cfg_branch() else d_yc, plan=plan1, segments=segments1)
+            out_c, out_u = shard.exchange_cfg_branches(mine, pair_group)
+        elif args.cfg_mode == "stacked":
             out = model.forward_fused(torch.cat([d_z, d_z]), d_t.expand(2), d_y, plan=plan, segments=segments,
                                       independent=True)
             out_c, out_u = out[:1], out[1:]
@@ -288,7 +300,7 @@ def main():
 
 
     graph = None
-    if not args.no_graph:
+    if not args.no_graph and not pairs:    # the pair exchange is an NCCL call per step: launched eagerly
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -360,16 +372,21 @@ def main():
     peak_tops = 2.0 * bf16_sus
     achieved = gemm_ops / (gemm_ms * 1e-3) / 1e12
     if rank == 0:
-        value = world * args.steps / (ms * 1e-3)
-        e2e_value = world * args.steps / (ms_e2e * 1e-3)
+        n_samples = world // 2 if pairs else world
+        value = n_samples * args.steps / (ms * 1e-3)
+        e2e_value = n_samples * args.steps / (ms_e2e * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if pairs else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "STDiT-XL/2 16x512x512 (T=16,S=1024 -> 16384 tokens, 28 blocks) W8A8 per-token "
                                    "dynamic (w8a8_dynamic.yaml), cfg_split: cond + uncond forwards (one stacked launch sequence, "
                                    "un-pooled statistics == two batch-1 calls) + CFG + DDIM per step",
-                       "samples_per_gpu": 1, "parallelism": f"sample-sharded x{world} (no data-path collective)",
+                       "samples_per_gpu": 0.5 if pairs else 1,
+                       "parallelism": (f"cfg-branch pairs x{world // 2}: one CFG branch per rank, all_gather of the model "
+                                       f"outputs (2 MB) per step" if pairs else
+                                       f"sample-sharded x{world} (no data-path collective)"),
                        "cuda_graph": graph is not None, "depth": args.depth, "cfg_mode": args.cfg_mode,
                        "l2": "working set per step (0.74 GB weight codes + >1 GB activations) exceeds the 126 MB L2",
                        "linear_TOP_per_step": 2 * linear_ops_per_forward() / 1e12 * args.depth / DEPTH},

@@ -49,3 +49,30 @@ def test_single_process_is_identity():
     x = torch.randn(3, 2)
     assert shard.gather_latents(x, 3) is x
     assert shard.max_over_ranks([1.5], "cpu") == [1.5]
+
+
+def _cfg_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from viditq_b200 import shard
+    grp = shard.cfg_pair_groups()
+    branch = shard.cfg_branch()
+    pair = rank // 2
+    out_local = torch.full((1, 8, 2, 3), 100.0 * pair + branch)     # what this rank's forward would return
+    oc, ou = shard.exchange_cfg_branches(out_local, grp)
+    ret[rank] = (branch, float(oc.flatten()[0]), float(ou.flatten()[0]))
+    dist.destroy_process_group()
+
+
+def test_cfg_branch_pairs_four_ranks():
+    """Two samples x two CFG branches on four gloo ranks: each pair exchanges only inside the pair, cond first."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    world = 4
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cfg_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for rank in range(world):
+        branch, oc, ou = ret[rank]
+        assert branch == rank % 2
+        assert (oc, ou) == (100.0 * (rank // 2), 100.0 * (rank // 2) + 1.0)

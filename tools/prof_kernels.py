@@ -67,10 +67,16 @@ timeit("gemm N=1152 K=4608 gate+res (fc2)", lambda: ops.gemm_w8a8(a4, w_fc2, epi
        ops_=2.0 * M * C * 4 * C)
 timeit("attn_temporal T=16 S=1024", lambda: ops.attn_temporal(qkv, 1, 16, 1024, 16, 72, 72 ** -0.5, out=o1),
        algo_bytes=M * C * 2 * 4)
+timeit("attn_spatial (tcgen05) 16 x 1024", lambda: ops.attn_spatial(qkv, 16, 1024, 16, 72, 72 ** -0.5, out=o1),
+       ops_=4.0 * 16 * 16 * 1024 * 1024 * 72)
 kv = torch.randn(109, 2 * C, device=dev).half()
 st, ln = torch.zeros(1, dtype=torch.int32, device=dev), torch.full((1,), 109, dtype=torch.int32, device=dev)
-timeit("attn_cross L=109", lambda: ops.attn_cross(xr, kv, st, ln, 1, M, 16, 72, 109, 72 ** -0.5, out=o1),
+timeit("attn_cross L=109 (tcgen05)", lambda: ops.attn_cross(xr, kv, st, ln, 1, M, 16, 72, 109, 72 ** -0.5, out=o1),
        algo_bytes=M * C * 2 * 2)
+z = torch.randn(1, 4, 16, 64, 64, device=dev)
+conv_w = (torch.randn(C, 4, 1, 2, 2, device=dev) * 0.1).half()
+pos = torch.randn(1024, C, device=dev).half()
+timeit("patch_embed + pos_embed", lambda: ops.patch_embed(z, conv_w, shift.view(-1), pos, (2, 2)), algo_bytes=M * C * 2)
 import torch.nn.functional as F
 q5 = qkv.view(16, 1024, 3, 16, 72)
 for name, be in (("cudnn", torch.nn.attention.SDPBackend.CUDNN_ATTENTION),

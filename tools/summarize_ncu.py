@@ -24,6 +24,7 @@ KEYS = [
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
 ]
 
 
@@ -91,7 +92,7 @@ def main():
     launches(tag)
     for rep in sorted(glob.glob(os.path.join(SRC, "*.ncu-rep"))):
         report(tag, rep)
-    for log in ("selftest.log", "prof_kernels.log", "bench.log", "smi.txt"):
+    for log in ("selftest.log", "attn_selftest.log", "prof_kernels.log", "bench.log", "timeline.log", "smi.txt"):
         p = os.path.join(SRC, log)
         if os.path.exists(p):
             with open(p) as fi, open(os.path.join(OUT, f"{tag}_{log}"), "w") as fo:

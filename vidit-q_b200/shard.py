@@ -4,6 +4,11 @@ One process per GPU, a full weight replica each, no collective on the data path.
 barrier / max-over-ranks reduction and one all_gather of the final latents (1 MB per sample) before VAE decode.
 Per-token activation statistics are pooled over the per-rank batch (quirk Q1), so an N-way sharded run equals the
 reference executed once per prompt with batch_size = 1 — not one batch-N run.
+
+A second, exact split for latency (strong scaling of ONE sample): with cfg_split the conditional and unconditional forwards
+of a denoise step are independent model calls (iddpm/__init__.py:156-157), so a pair of ranks runs one branch each and
+exchanges the model outputs (2 MB per rank per step) before both apply the identical CFG + DDIM update.  Nothing else
+crosses ranks; the result is bit-identical to the two calls made on one GPU (tests/test_gpu_multi.py).
 """
 import torch
 import torch.distributed as dist
@@ -50,3 +55,38 @@ def max_over_ranks(values, device):
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.tolist()
+
+
+# ------------------------------------------------------------------------------------------------ cfg-branch pairs
+def cfg_branch(rank=None):
+    """0 = conditional, 1 = unconditional branch of the pair this rank belongs to."""
+    if rank is None:
+        _, rank = world()
+    return rank % 2
+
+
+def cfg_pair_groups():
+    """Process groups of consecutive rank pairs (2i, 2i+1); every rank must call this (collective). Returns this rank's
+    group (None when running single-process)."""
+    world_size, rank = world()
+    if world_size == 1:
+        return None
+    if world_size % 2:
+        raise ValueError("cfg-branch split needs an even number of ranks (two per sample)")
+    mine = None
+    for i in range(0, world_size, 2):
+        g = dist.new_group([i, i + 1])
+        if rank in (i, i + 1):
+            mine = g
+    return mine
+
+
+def exchange_cfg_branches(out_local, group=None):
+    """out_local: this rank's model output [n, c_out, ...] for its branch. Returns (out_cond, out_uncond), both complete
+    on both ranks of the pair, in that order regardless of the caller's branch."""
+    world_size, rank = world()
+    if world_size == 1:
+        raise ValueError("exchange_cfg_branches needs an initialised process group")
+    parts = [torch.empty_like(out_local) for _ in range(2)]
+    dist.all_gather(parts, out_local.contiguous(), group=group)
+    return parts[0], parts[1]     # group rank 0 = even global rank = conditional branch
