@@ -508,19 +508,21 @@ __device__ __forceinline__ void utransform(UnitRegs<U>& regs, const ActQuantArgs
   }
 }
 
-// Persistent: every warp walks rows r, r + W, r + 2W, ... and (for G == 1, the hot case) keeps the NEXT row's loads
-// in flight while it quantises the current one, so HBM requests are outstanding all the time.
-template <int U, bool LN, bool HEADS>
-__global__ void __launch_bounds__(256, 3) vq_act_quant_unit_kernel(const ActQuantArgs a) {
+// Persistent: every warp walks rows r, r + W, r + 2W, ...  PF = true (for G == 1) keeps the NEXT row's loads in flight
+// while the current one is quantised; PF = false spends those registers on a fourth resident block per SM instead (the
+// default, see launch_act_quant).
+template <int U, bool LN, bool HEADS, bool PF = true>
+__global__ void __launch_bounds__(256, PF ? 3 : 4) vq_act_quant_unit_kernel(const ActQuantArgs a) {
   grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int wstride = gridDim.x * (blockDim.x >> 5);
   int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= a.rows) return;
   UnitRegs<U> regs, nxt;
-  if (a.G == 1) uload_any<U, HEADS>(regs, a, 0, r, lane);
+  if (PF && a.G == 1) uload_any<U, HEADS>(regs, a, 0, r, lane);
   for (; r < a.rows; r += wstride) {
-    const bool has_next = a.G == 1 && r + wstride < a.rows;
+    const bool has_next = PF && a.G == 1 && r + wstride < a.rows;
+    if (!PF && a.G == 1) uload_any<U, HEADS>(regs, a, 0, r, lane);
     if (has_next) uload_any<U, HEADS>(nxt, a, 0, r + wstride, lane);   // prefetch
     __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
     if (a.G == 1) {
@@ -658,10 +660,19 @@ static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
   // K = 4608 is 18 full chunk rounds, where the chunk mapping is already branch-free and lighter on registers.
   if (a.K == 9 * 128) {
     const int blocks_needed = (a.rows + warps - 1) / warps;
-    const int persistent = num_sms() * 3;   // 3 resident 8-warp blocks per SM (80 registers), rows strided across them
+    // Register prefetch of the next row (3 blocks per SM, 80 registers) against no prefetch and 4 blocks per SM (64
+    // registers): inside the replayed step the extra warps win — plain 20.6 -> 18.1 us, LN 39.4 -> 36.8 us per launch at
+    // M = 32768 (profiles/r01_s22_*).  VQ_AQ_NOPF selects per kernel (bit 0: plain, bit 1: LN; default both).
+    static const int nopf = [] {
+      const char* e = getenv("VQ_AQ_NOPF");
+      return e ? atoi(e) : 3;
+    }();
+    const bool pf = !((nopf >> (LN ? 1 : 0)) & 1) || a.head_S > 0;
+    const int persistent = num_sms() * (pf ? 3 : 4);   // resident 8-warp blocks per SM, rows strided across them
     const int g2 = blocks_needed < persistent ? blocks_needed : persistent;
     if (a.head_S > 0) launch_pdl(vq_act_quant_unit_kernel<9, LN, true>, g2, block, 0, st, a);
-    else launch_pdl(vq_act_quant_unit_kernel<9, LN, false>, g2, block, 0, st, a);
+    else if (pf) launch_pdl(vq_act_quant_unit_kernel<9, LN, false>, g2, block, 0, st, a);
+    else launch_pdl(vq_act_quant_unit_kernel<9, LN, false, false>, g2, block, 0, st, a);
   }
   else if (maxc <= 5) launch_pdl(vq_act_quant_kernel<5, LN>, grid, block, 0, st, a);
   else if (maxc <= 9) launch_pdl(vq_act_quant_kernel<9, LN>, grid, block, 0, st, a);
