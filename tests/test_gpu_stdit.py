@@ -269,3 +269,61 @@ def test_w4a8_timestep_aware_smooth_quant_model(small):  # noqa: F811
         print("W4A8 smooth t=%g: layerwise %.3e %.3e | fused %.3e %.3e" % (tval, i1, l1, i2, l2))
         # end-to-end distances live in the re-quantisation noise band (see the W8A8 test); W4 weights: wider band
         assert l1 <= 6e-3 and l2 <= 6e-3
+
+
+def test_own_attention_kernels_inside_the_model():
+    """Image-sized token counts (S = 256 per frame, 4 frames): the fused schedule with the tcgen05 flash-attention kernel
+    for the spatial AND cross attention and the fused patch embedding, against (a) the same schedule on the library flash
+    kernel (VQ_SPATIAL_ATTN=sdpa yardstick) and (b) the layer-by-layer reference schedule (QuantLayer calls, torch SDPA,
+    Conv3d patch embedding).  The golden-vector models are too small (S = 64) to reach these kernels."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from test_stdit_graph_cpu import Cfg
+    from viditq_b200.qdiff import QuantModel
+    from viditq_b200.stdit import STDiT
+    T, S = 4, 256
+    model = STDiT(input_size=(T, 32, 32), depth=2)
+    model.init_synthetic(seed=3)
+    model.eval()
+    sq = Cfg(enable=False, channel_wise_scale_type="momentum_act_max", momentum=0.95, alpha=0.625)
+    wq = Cfg(n_bits=8, per_group="channel", channel_dim=0, scale_method="min_max", round_mode="nearest",
+             mixed_precision=[4, 6, 8])
+    aq = Cfg(n_bits=8, per_group="token", scale_method="min_max", round_mode="nearest_ste", running_stat=False,
+             dynamic=True, sym=False, n_spatial_token=S, n_temporal_token=T, n_prompt=120, smooth_quant=sq)
+    qnn = QuantModel(model, wq, aq)
+    qnn.cuda()
+    qnn.half()
+    model.dtype = torch.float16
+    qnn.set_module_name_for_quantizer(module=qnn.model)
+    qnn.fp_layer_list = FP_LAYERS
+    qnn.init_weight_quant_params()
+    qnn.set_quant_init_done("weight")
+    qnn.set_quant_init_done("activation")
+    qnn.set_quant_state(True, True)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 4, T, 32, 32, generator=g).cuda()
+    y = torch.randn(1, 1, 120, 4096, generator=g).cuda()
+    mask = torch.zeros(1, 120, dtype=torch.int64)
+    mask[0, :93] = 1
+    mask = mask.cuda()
+    t = torch.tensor([500.0], device="cuda")
+    from viditq_b200 import ops
+    with torch.no_grad():
+        model.forward_fused(x, t, y, mask=mask)      # first call prepares the weights (extra launches)
+        n0 = ops.launch_count()
+        own = model.forward_fused(x, t, y, mask=mask).cpu().numpy()
+        assert model._engine.own_spatial
+        launches_own = ops.launch_count() - n0
+        model._engine.own_spatial = False
+        n0 = ops.launch_count()
+        lib = model.forward_fused(x, t, y, mask=mask).cpu().numpy()
+        launches_lib = ops.launch_count() - n0
+        model._engine.own_spatial = True
+        ref = qnn(x, t, y, mask=mask).cpu().numpy()
+    assert np.isfinite(own).all()
+    assert launches_own == launches_lib + 2          # one vq_attn_spatial launch per block replaces the library call
+    i1, l1 = _rel(own, lib)
+    i2, l2 = _rel(own, ref)
+    print("own attention vs library-attention schedule: %.3e %.3e | vs layerwise reference schedule: %.3e %.3e" % (i1, l1, i2, l2))
+    # distances between two correct fp16 implementations of a re-quantising network: inside the band of the W8A8 test
+    assert l1 <= 4e-3 and l2 <= 4e-3, (l1, l2)
