@@ -54,3 +54,30 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert "UTMALDG.4D" in sass    # 4-D q|k|v tensor maps of the attention
     assert "STTM" in sass          # tcgen05.st: P written to TMEM as the A operand of P V
     assert "IMMA." not in sass.replace("UTCIMMA", "")   # no legacy mma.sync integer path
+
+
+def test_argument_validation_returns_error_codes_without_touching_the_device():
+    """Error behaviour of the boundary: bad pointers / shapes are refused with VQ_ERR_ARG (-1) or VQ_ERR_UNSUPPORTED (-5)
+    before any CUDA call is made, so this runs on a machine without a GPU."""
+    import viditq_b200
+    lib = ctypes.CDLL(viditq_b200.build_library())
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    lib.vq_attn_spatial.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.vq_attn_cross.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, f32, vp]
+    lib.vq_patch_embed.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.vq_add_act_quant.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.vq_gemm_w8a8.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
+    fake = 0x10000   # never dereferenced: every call below is rejected by its argument checks
+    assert lib.vq_attn_spatial(None, fake, 1, 1024, 16, 72, 0.1, None) == -1          # null q|k|v
+    assert lib.vq_attn_spatial(fake, fake, 1, 1000, 16, 72, 0.1, None) == -5          # S not a multiple of 256
+    assert lib.vq_attn_spatial(fake, fake, 1, 1024, 16, 64, 0.1, None) == -5          # head_dim != 72
+    assert lib.vq_attn_spatial(fake + 2, fake, 1, 1024, 16, 72, 0.1, None) == -1      # misaligned tensor
+    assert lib.vq_attn_cross(fake, fake, fake, None, fake, 1, 256, 16, 72, 120, 120, 0.1, None) == -1   # null kv_start
+    assert lib.vq_attn_cross(fake, fake, fake, fake, fake, 1, 256, 16, 72, 200, 200, 0.1, None) == -5   # prompt > 128 rows
+    assert lib.vq_patch_embed(None, fake, None, None, 1, 4, 16, 64, 64, 2, 2, 1152, fake, None) == -1
+    assert lib.vq_patch_embed(fake, fake, None, None, 1, 4, 16, 64, 64, 4, 4, 1152, fake, None) == -5   # 64-element patches
+    assert lib.vq_patch_embed(fake, fake, None, None, 1, 4, 16, 63, 64, 2, 2, 1152, fake, None) == -5   # ragged grid
+    assert lib.vq_add_act_quant(fake, None, 1024, 16, 1, 64, 1152, None, 8, fake, fake, fake, fake, None, None) == -1
+    assert lib.vq_add_act_quant(fake, fake, 1024, 16, 1, 64, 4608, None, 8, fake, fake, fake, fake, None, None) == -5
+    assert lib.vq_gemm_w8a8(fake, fake, fake, fake, 64, fake, fake, 64, 100, 1152, 0, None, 0, None, 0, fake, 100, None) == -1  # N % 8
+    assert lib.vq_gemm_w8a8(fake, fake, fake, fake, 64, fake, fake, 64, 1152, 1152, 2, None, 0, None, 0, fake, 1152, None) == -1  # residual epilogue without res
