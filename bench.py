@@ -193,10 +193,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cfg-mode", default="stacked", choices=["stacked", "split"],
                     help="cfg_split's cond / uncond forwards as one stacked launch sequence (default) or two calls")
-    ap.add_argument("--parallelism", default="samples", choices=["samples", "cfg-branch"],
+    ap.add_argument("--parallelism", default="samples", choices=["samples", "cfg-branch", "frames"],
                     help="samples: one sample per rank, no data-path collective (the metric, weak scaling). cfg-branch: "
                          "two ranks per sample, one CFG branch each, model outputs exchanged every step (latency / "
-                         "strong scaling of one sample; needs an even --gpus)")
+                         "strong scaling of one sample; needs an even --gpus). frames: ONE sample, its 16 frames sharded "
+                         "over all ranks, codes all-to-all around the temporal attention of every block (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -218,7 +219,8 @@ def main():
     if pairs and (world < 2 or world % 2):
         raise SystemExit("--parallelism cfg-branch needs an even number of ranks")
     pair_group = shard.cfg_pair_groups() if pairs else None
-    sample_id = rank // 2 if pairs else rank          # both ranks of a pair hold the same sample and the same weights
+    fsh = args.parallelism == "frames" and world > 1
+    sample_id = rank // 2 if pairs else (0 if fsh else rank)   # ranks sharing a sample hold the same inputs and weights
     torch.manual_seed(1234 + sample_id)
     torch.set_grad_enabled(False)
     qnn, model = build_model(dev, args.depth)
@@ -234,6 +236,10 @@ def main():
     h_t = torch.zeros(1).pin_memory()
     h_coef = torch.zeros(4).pin_memory()
     h_out = torch.empty(1, 4, T_FRAMES, 64, 64).pin_memory()
+    if fsh:   # this rank's frames of the latent (it stays frame-sharded through the whole sampling loop)
+        f0, f1 = shard.frame_slice(T_FRAMES)
+        h_z = h_z[:, :, f0:f1].contiguous().pin_memory()
+        h_out = torch.empty_like(h_z).pin_memory()
     d_z = h_z.to(dev)
     d_y = torch.cat([h_yc, h_yu]).to(dev)                 # cond | uncond captions, one stacked device buffer
     d_yc, d_yu = d_y[:1], d_y[1:]
@@ -254,7 +260,11 @@ def main():
         """The denoise step on device-resident inputs (iddpm forward_with_cfg + ddim_sample, cfg_split): the cond and
         uncond forwards of cfg_split run as one stacked launch sequence with un-pooled statistics (== two batch-1 calls,
         tests/test_gpu_stdit.py::test_stacked_cfg_split_equals_two_separate_forwards)."""
-        if pairs:   # this rank's branch only; the 2 MB outputs cross NVLink, then both ranks apply the same update
+        if fsh:
+            out = model.forward_fused(torch.cat([d_z, d_z]), d_t.expand(2), d_y, plan=plan, segments=segments,
+                                      independent=True, frames=(None, world, rank))
+            out_c, out_u = out[:1], out[1:]
+        elif pairs:   # this rank's branch only; the 2 MB outputs cross NVLink, then both ranks apply the same update
             mine = model.forward_fused(d_z, d_t, d_yu if shard.cfg_branch() else d_yc, plan=plan1, segments=segments1)
             out_c, out_u = shard.exchange_cfg_branches(mine, pair_group)
         elif args.cfg_mode == "stacked":
@@ -300,7 +310,9 @@ def main():
 
 
     graph = None
-    if not args.no_graph and not pairs:    # the pair exchange is an NCCL call per step: launched eagerly
+    # steps with NCCL calls inside (cfg-branch / frames) are launched eagerly: capturing the torch.distributed calls in
+    # the step graph deadlocked on the 2-GPU box (both ranks hung in capture; measured once, not pursued)
+    if not args.no_graph and not (pairs or fsh):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -372,20 +384,22 @@ def main():
     peak_tops = 2.0 * bf16_sus
     achieved = gemm_ops / (gemm_ms * 1e-3) / 1e12
     if rank == 0:
-        n_samples = world // 2 if pairs else world
+        n_samples = world // 2 if pairs else (1 if fsh else world)
         value = n_samples * args.steps / (ms * 1e-3)
         e2e_value = n_samples * args.steps / (ms_e2e * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if pairs else "weak",
+            "scaling": "strong" if (pairs or fsh) else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "STDiT-XL/2 16x512x512 (T=16,S=1024 -> 16384 tokens, 28 blocks) W8A8 per-token "
                                    "dynamic (w8a8_dynamic.yaml), cfg_split: cond + uncond forwards (one stacked launch sequence, "
                                    "un-pooled statistics == two batch-1 calls) + CFG + DDIM per step",
-                       "samples_per_gpu": 0.5 if pairs else 1,
+                       "samples_per_gpu": 0.5 if pairs else (1.0 / world if fsh else 1),
                        "parallelism": (f"cfg-branch pairs x{world // 2}: one CFG branch per rank, all_gather of the model "
                                        f"outputs (2 MB) per step" if pairs else
+                                       f"frame-sharded x{world}: {T_FRAMES // world} frames per rank, all-to-all of the "
+                                       f"temporal branch's u8 codes per block" if fsh else
                                        f"sample-sharded x{world} (no data-path collective)"),
                        "cuda_graph": graph is not None, "depth": args.depth, "cfg_mode": args.cfg_mode,
                        "l2": "working set per step (0.74 GB weight codes + >1 GB activations) exceeds the 126 MB L2",

@@ -76,3 +76,48 @@ def test_cfg_branch_pairs_four_ranks():
         branch, oc, ou = ret[rank]
         assert branch == rank % 2
         assert (oc, ou) == (100.0 * (rank // 2), 100.0 * (rank // 2) + 1.0)
+
+
+def _frames_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from viditq_b200 import shard
+    B, T, S, F = 2, 4, 6, 3
+    P = world
+    t0, t1 = shard.frame_slice(T)
+    T_loc = t1 - t0
+    # global tensor g[b, t, s, f] = unique id; this rank holds frames [t0, t1)
+    g = torch.arange(B * T * S * F, dtype=torch.int32).view(B, T, S, F)
+    local = g[:, t0:t1].reshape(B * T_loc * S, F).contiguous()
+    sp = shard.frames_to_spatial(local, B, T_loc, S, P)
+    Sp = S // P
+    want_sp = g[:, :, rank * Sp:(rank + 1) * Sp].reshape(B * T * Sp, F)
+    back = shard.spatial_to_frames(sp, B, T_loc, S, P)
+
+    class A:                                  # stand-in for ops.ActCodes (same constructor signature)
+        def __init__(self, codes, delta, zp, rowsum, G, rows, K):
+            self.codes, self.delta, self.zp, self.rowsum, self.G, self.rows, self.K = codes, delta, zp, rowsum, G, rows, K
+    rows = B * T_loc * S
+    ids = g[:, t0:t1, :, 0].reshape(rows)
+    a = A(local.to(torch.uint8), (ids.float() * 0.5).half(), (ids % 7).half(), ids * 3, 1, rows, F)
+    a_sp = shard.exchange_act_codes(a, B, T_loc, S, P, True)
+    ids_sp = g[:, :, rank * Sp:(rank + 1) * Sp, 0].reshape(-1)
+    meta_ok = (torch.equal(a_sp.delta, (ids_sp.float() * 0.5).half()) and torch.equal(a_sp.zp, (ids_sp % 7).half())
+               and torch.equal(a_sp.rowsum, ids_sp * 3) and torch.equal(a_sp.codes, want_sp.to(torch.uint8)))
+    a_fr = shard.exchange_act_codes(a_sp, B, T_loc, S, P, False)
+    rt_ok = (torch.equal(a_fr.codes, a.codes) and torch.equal(a_fr.delta, a.delta) and torch.equal(a_fr.rowsum, a.rowsum))
+    ret[rank] = (torch.equal(sp, want_sp), torch.equal(back, local), meta_ok, rt_ok, a_sp.rows == B * T * Sp)
+    dist.destroy_process_group()
+
+
+def test_frame_sharding_layout_exchange_two_ranks():
+    """frames <-> positions all-to-all (viditq_b200.shard) on gloo: every rank ends up with all frames of its S / P
+    positions, the inverse restores the frame-sharded layout, and the per-token scales travel with their codes."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_frames_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for rank in range(world):
+        assert all(ret[rank]), (rank, ret[rank])

@@ -9,6 +9,14 @@ A second, exact split for latency (strong scaling of ONE sample): with cfg_split
 of a denoise step are independent model calls (iddpm/__init__.py:156-157), so a pair of ranks runs one branch each and
 exchanges the model outputs (2 MB per rank per step) before both apply the identical CFG + DDIM update.  Nothing else
 crosses ranks; the result is bit-identical to the two calls made on one GPU (tests/test_gpu_multi.py).
+
+A third split, for one 16-frame video on P GPUs: frame (T) sharding.  Every per-token linear, LayerNorm, per-token
+quantiser, the spatial attention and the cross attention are frame-local; only the temporal attention couples frames.  A
+rank keeps T/P frames of the residual stream; per block the *quantised* input of attn_temp's q|k|v (u8 codes + 8 bytes of
+scales per token — a quarter of the fp16 bytes, and per-token quantisation does not care where a token lives) goes through
+one all-to-all into the (all frames, S/P positions) layout, the temporal q|k|v GEMM + attention + the projection's
+quantiser run there, and a second all-to-all brings the codes back for the projection GEMM with the local residual.
+Bit-identical to the single-GPU schedule (every kernel is row-, sequence- or sample-local).
 """
 import torch
 import torch.distributed as dist
@@ -90,3 +98,59 @@ def exchange_cfg_branches(out_local, group=None):
     parts = [torch.empty_like(out_local) for _ in range(2)]
     dist.all_gather(parts, out_local.contiguous(), group=group)
     return parts[0], parts[1]     # group rank 0 = even global rank = conditional branch
+
+
+# ------------------------------------------------------------------------------------------------ frame (T) sharding
+def frame_slice(T, world_size=None, rank=None):
+    """Frames [t0, t1) owned by this rank (T must divide evenly: the reference's 16 frames over 2 / 4 / 8 / 16 ranks)."""
+    if world_size is None:
+        world_size, rank = world()
+    if T % world_size:
+        raise ValueError(f"{T} frames do not divide over {world_size} ranks")
+    per = T // world_size
+    return rank * per, (rank + 1) * per
+
+
+def _all_to_all(send, group):
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv
+
+
+def frames_to_spatial(t, B, T_loc, S, P, group=None):
+    """t: [B * T_loc * S, F] rows in (b, local frame, position) order on every rank -> [B * T * (S / P), F] rows in
+    (b, frame, local position) order: all T = P * T_loc frames of this rank's S / P positions."""
+    Sp, F = S // P, t.shape[-1]
+    send = t.view(B, T_loc, P, Sp, F).permute(2, 0, 1, 3, 4).contiguous()          # [dst rank, b, t_loc, s', F]
+    recv = _all_to_all(send, group)                                                # [src rank = frame chunk, b, t_loc, s', F]
+    return recv.permute(1, 0, 2, 3, 4).reshape(B * P * T_loc * Sp, F)
+
+
+def spatial_to_frames(t, B, T_loc, S, P, group=None):
+    """Inverse of frames_to_spatial: [B * T * (S / P), F] -> [B * T_loc * S, F]."""
+    Sp, F = S // P, t.shape[-1]
+    send = t.view(B, P, T_loc, Sp, F).permute(1, 0, 2, 3, 4).contiguous()          # [dst rank = frame owner, b, t_loc, s', F]
+    recv = _all_to_all(send, group)                                                # [src rank = position chunk, b, t_loc, s', F]
+    return recv.permute(1, 2, 0, 3, 4).reshape(B * T_loc * S, F)
+
+
+def _pack_meta(delta, zp, rowsum):
+    """(delta fp16, zp fp16, rowsum i32) per row -> int32 [rows, 2] so that the scales travel in one exchange."""
+    dz = torch.stack([delta, zp], dim=-1).contiguous().view(torch.int32)          # [rows, 1]
+    return torch.cat([dz, rowsum.view(-1, 1)], dim=1).contiguous()
+
+
+def _unpack_meta(meta):
+    dz = meta[:, :1].contiguous().view(torch.float16)                              # [rows, 2]
+    return dz[:, 0].contiguous(), dz[:, 1].contiguous(), meta[:, 1].contiguous()
+
+
+def exchange_act_codes(a, B, T_loc, S, P, to_spatial, group=None):
+    """Move per-token quantised activations (ops.ActCodes with one scale pair per row: G == 1) between the frame-sharded
+    and the position-sharded layout. Two all-to-alls: codes (1 byte / element) and 8 bytes of (delta, zp, rowsum) per row."""
+    if a.G != 1:
+        raise ValueError("frame sharding moves per-token codes: batch-pooled statistics (G > 1) are not supported")
+    fn = frames_to_spatial if to_spatial else spatial_to_frames
+    codes = fn(a.codes, B, T_loc, S, P, group)
+    delta, zp, rowsum = _unpack_meta(fn(_pack_meta(a.delta, a.zp, a.rowsum), B, T_loc, S, P, group))
+    return type(a)(codes, delta, zp, rowsum, 1, codes.shape[0], a.K)

@@ -257,7 +257,7 @@ class STDiT(nn.Module):
         timestep = timestep.to(self.dtype)
         y = y.to(self.dtype)
         B = x.shape[0]
-        T, S, C = self.num_temporal, self.num_spatial, self.hidden_size
+        T, S, C = x.shape[2] // self.patch_size[0], self.num_spatial, self.hidden_size   # T: this rank's frames
         proj = self.x_embedder.proj
         if fused and self.patch_size[0] == 1 and proj.weight.dtype == torch.float16:
             # one pass: patchify + bias + "B (T S) C" layout + pos_embed (vq_patch_embed) instead of conv3d, two layout
@@ -292,6 +292,7 @@ class STDiT(nn.Module):
         B = x.shape[0]
         Nt, Nh, Nw = [self.input_size[i] // self.patch_size[i] for i in range(3)]
         Tp, Hp, Wp = self.patch_size
+        Nt = x.shape[1] // (Nh * Nw)      # frame-sharded forward: only this rank's frames
         x = x.view(B, Nt, Nh, Nw, Tp, Hp, Wp, self.out_channels)
         return x.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(B, self.out_channels, Nt * Tp, Nh * Hp, Nw * Wp)
 
@@ -304,19 +305,21 @@ class STDiT(nn.Module):
         return self.unpatchify(x).to(torch.float32)
 
     # ---- fused B200 schedule ----------------------------------------------------------------------------------------
-    def forward_fused(self, x, timestep, y, mask=None, plan=None, segments=None, independent=False):
+    def forward_fused(self, x, timestep, y, mask=None, plan=None, segments=None, independent=False, frames=None):
         """plan / segments: host-precomputed mask_select_plan(mask) and kv_segments(y_lens) make the call sync-free.
         independent=True: the batch entries are SEPARATE reference forward calls stacked into one launch sequence — the
         cond / uncond halves of cfg_split=True (iddpm/__init__.py:156-157 calls the model twice with batch n_prompts = 1).
         Their per-token statistics are not pooled (each row is quantised on its own, which is what two batch-1 calls do);
-        results are identical to calling forward_fused once per entry, at half the launches and better-filled GEMM waves."""
+        results are identical to calling forward_fused once per entry, at half the launches and better-filled GEMM waves.
+        frames = (process group, P, rank in group): frame-sharded forward of one video — x holds this rank's T / P frames
+        of the latent, the returned tensor the same frames of the output (viditq_b200.shard)."""
         x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan, fused=True)
         eng = getattr(self, "_engine", None)
         if eng is None:
             eng = self._engine = FusedBlocks(self)
         if segments is None:
             segments = self.kv_segments(y_lens, x.device)
-        x = eng.run(x, y, t0, y_lens, segments, independent)
+        x = eng.run(x, y, t0, y_lens, segments, independent, frames)
         # final layer (FP, remain_fp.txt): LayerNorm + modulate in one pass of the fused kernel (its codes are unused)
         fl = self.final_layer
         shift, scale = (fl.scale_shift_table[None] + t[:, None]).chunk(2, dim=1)
@@ -406,12 +409,31 @@ class FusedBlocks:
             ops.gemm_w8a8(a, lw, out=out[:, j * C:(j + 1) * C], ldo=3 * C)
         return out
 
-    def run(self, x, y, t0, y_lens, segments, independent=False):
+    def run(self, x, y, t0, y_lens, segments, independent=False, frames=None):
         m = self.m
         B, N, C = x.shape
-        T, S, H = m.num_temporal, m.num_spatial, m.num_heads
+        S, H = m.num_spatial, m.num_heads
+        T = N // S                       # frames held by this rank (all of them unless frame-sharded)
         D = C // H
         M = B * N
+        t_first = 0
+        if frames is not None:
+            from . import shard
+            grp, P, prank = frames
+            if not (independent or B == 1):
+                raise NotImplementedError("frame sharding moves per-token codes: needs un-pooled statistics")
+            if T * P != m.num_temporal or S % P:
+                raise ValueError(f"frame sharding: {T} local frames x {P} ranks != {m.num_temporal} or {S} % {P} != 0")
+            t_first = prank * T
+
+        def qi(layer, t, gelu=False):
+            """The layer's activation quantiser. Frame-sharded: a rank holds T / P frames, which the reference layers'
+            (B, T*S) pooling views do not describe — every row is quantised on its own (un-pooled, as checked above)."""
+            if frames is None:
+                return layer.quantize_input(t, gelu=gelu, independent=independent)
+            if layer.smooth_quant:
+                raise NotImplementedError("frame sharding with smooth-quant channel scales")
+            return ops.act_quant(t.reshape(1, -1, t.shape[-1]), n_bits=layer.act_quantizer.n_bits, gelu=gelu)
         x = x.contiguous()   # fresh tensor from embed(): the residual stream is updated in place below
         ones = torch.ones(1, C, dtype=x.dtype, device=x.device)
         tpe = m.pos_embed_temporal.to(x.dtype)
@@ -426,38 +448,56 @@ class FusedBlocks:
             if self.own_spatial and ops.attn_spatial_supported(S, D):
                 # tcgen05 flash attention reading q|k|v in place, token-major output: the projection's quantiser input
                 o = ops.attn_spatial(qkv, B * T, S, H, D, blk.attn.scale)
-                a = pj.quantize_input(o.view(B * T, S, C), independent=independent)
+                a = qi(pj, o.view(B * T, S, C))
             else:
                 a = self._spatial_library(qkv.view(B * T, S, 3, H, D), pj, blk.attn.scale, B, N, T, S, C, D, independent)
             xr = x.view(M, C)   # residual stream, updated in place: out aliases res -> TMA reduce-add epilogue
             ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                           rows_per_gate=N, out=xr)
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
-            if i == 0 and C == 1152:   # x + tpe rides in the quantise pass (vq_add_act_quant): frame t = (row // S) % T
+            if frames is not None:
+                # frame-sharded: quantise locally, all-to-all the CODES into the (all frames, S / P positions) layout,
+                # q|k|v GEMM + attention + the projection's quantiser there, all-to-all the codes back
+                pw_t = self._qkv_weight(blk.attn_temp, (i, "t"))
+                if pw_t is None or blk.attn_temp.proj.smooth_quant or C != 1152:
+                    raise NotImplementedError("frame sharding with per-layer smooth-quant scales")
+                nb = blk.attn_temp.q.act_quantizer.n_bits
+                x1 = x.view(1, M, C)
+                a = (ops.add_act_quant(x1, tpe.view(-1, C)[t_first:t_first + T].contiguous(), S, n_bits=nb) if i == 0
+                     else ops.act_quant(x1, n_bits=nb))
+                a = shard.exchange_act_codes(a, B, T, S, P, True, grp)
+                qkv = ops.gemm_w8a8(a, pw_t)
+                o = ops.attn_temporal(qkv, B, T * P, S // P, H, D, blk.attn_temp.scale)
+                a = ops.act_quant(o.view(1, -1, C), n_bits=blk.attn_temp.proj.act_quantizer.n_bits)
+                a = shard.exchange_act_codes(a, B, T, S, P, False, grp)
+                ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
+                              rows_per_gate=N, out=xr)
+            elif i == 0 and C == 1152:   # x + tpe rides in the quantise pass (vq_add_act_quant): frame t = (row // S) % T
                 qkv = self._qkv_project(blk.attn_temp, (i, "t"), x, independent=independent, add=(tpe.view(T, C), S))
             else:
                 xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
                 qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt, independent=independent)
-            if T <= 16 and D == 72:      # own kernel: reads the (T S) layout in place, no permute copies
-                o = ops.attn_temporal(qkv, B, T, S, H, D, blk.attn_temp.scale).view(B, N, C)
-            else:                        # library path for shapes the kernel does not cover
-                q5 = qkv.view(B, T, S, 3, H, D)
-                qt, kt, vt = (q5[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
-                o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)
-                o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
-            # per-token statistics: row order irrelevant
-            a = blk.attn_temp.proj.quantize_input(o.view(B * S, T, C), independent=independent)
-            ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
-                          rows_per_gate=N, out=xr)
+            if frames is None:
+                if T <= 16 and D == 72:      # own kernel: reads the (T S) layout in place, no permute copies
+                    o = ops.attn_temporal(qkv, B, T, S, H, D, blk.attn_temp.scale).view(B, N, C)
+                else:                        # library path for shapes the kernel does not cover
+                    q5 = qkv.view(B, T, S, 3, H, D)
+                    qt, kt, vt = (q5[:, :, :, j].permute(0, 2, 3, 1, 4).reshape(B * S, H, T, D) for j in range(3))
+                    o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)
+                    o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
+                # per-token statistics: row order irrelevant
+                a = blk.attn_temp.proj.quantize_input(o.view(B * S, T, C), independent=independent)
+                ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
+                              rows_per_gate=N, out=xr)
             # ---- cross attention
             ca = blk.cross_attn
-            q = ops.gemm_w8a8(ca.q_linear.quantize_input(x, independent=independent), ca.q_linear.prepared_weight())
+            q = ops.gemm_w8a8(qi(ca.q_linear, x), ca.q_linear.prepared_weight())
             kv = ops.gemm_w8a8(ca.kv_linear.quantize_input(y), ca.kv_linear.prepared_weight())
             if D == 72 and max(y_lens) <= 128:
                 o = ops.attn_cross(q, kv, segments[0], segments[1], B, N, H, D, max(y_lens), D ** -0.5).view(B, N, C)
             else:
                 o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
-            ops.gemm_w8a8(ca.proj.quantize_input(o, independent=independent), ca.proj.prepared_weight(),
+            ops.gemm_w8a8(qi(ca.proj, o), ca.proj.prepared_weight(),
                           epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=ones, rows_per_gate=M, out=xr)
             # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
             fc1w = blk.mlp.fc1.prepared_weight()
@@ -466,7 +506,7 @@ class FusedBlocks:
                                              smooth=getattr(fc1w, "smooth", None), rows_per_mod=N if independent else None)
             # GELU rides in fc2's quantise pass (HBM-bound, idle MUFU) instead of fc1's epilogue (epilogue-bound)
             h = ops.gemm_w8a8(a, fc1w).view(B, N, -1)
-            a = blk.mlp.fc2.quantize_input(h, gelu=True, independent=independent)
+            a = qi(blk.mlp.fc2, h, gelu=True)
             ops.gemm_w8a8(a, blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp,
                           rows_per_gate=N, out=xr)
         return x
