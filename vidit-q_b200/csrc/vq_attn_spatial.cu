@@ -10,26 +10,28 @@
 // Work item = (sequence, head, 256 queries): two 128-query tiles share one stream of 64-key K / V tiles, which halves the
 // L2 -> shared-memory operand traffic (at 128 queries per K/V stream the kernel would sit on the L2 bandwidth roof).
 // Persistent CTAs (one per SM), 12 warps:
-//   warp 0      TMA producer: Q tiles of the item, then a 4-stage ring of K tiles and one of V tiles.  head_dim 72 is
+//   warp 0      TMA producer: Q tiles of the item, then a 4-stage ring of K tiles and one of V tiles.  head_dim 72 of Q / K is
 //               stored as a 64-dim SWIZZLE_128B tile plus a 16-dim SWIZZLE_32B tile whose dims 72..79 lie outside the
-//               tensor map's innermost extent and are zero-filled by the TMA unit (so K = 80 for the MMA, no padded copy).
+//               tensor map's innermost extent and are zero-filled by the TMA unit (K = 80 for the MMA, no padded copy);
+//               V as five 16-dim SWIZZLE_32B boxes = one MN-major operand of N = 80.
 //   warp 1      MMA issuer (warp-uniform control flow, one elected lane issues; descriptors live in uniform registers).
-//               S = Q K^T: 5 x tcgen05.mma.kind::f16 (M128 N64 K16; 4 in the SW128 tile, 1 in the SW32 tile) into one of
-//               TWO score buffers per query tile, so the scores run two key tiles ahead of the softmax.  O += P V: P is
-//               read from TMEM as the A operand (it overwrites S in place, two fp16 per column), V is the MN-major B
-//               operand straight from the TMA tile: per 16 keys one N=64 and one N=16 instruction.
-//   warp 2      TMEM allocation (512 columns: S/P 2 tiles x 2 buffers x 64, O 2 x 128).
+//               S = Q K^T: 5 x tcgen05.mma.kind::f16 (M128 N64 K16) with **Q read from TMEM** as the A operand (copied
+//               there once per item by the softmax warps: from shared memory every N = 64 instruction re-read 4 KB of Q
+//               and was bound by the shared-memory port) into one of TWO score buffers per query tile, so the scores run
+//               two key tiles ahead of the softmax.  O += P V: P is read from TMEM as the A operand too (it overwrites S in
+//               place, two fp16 per column), V is the MN-major B operand straight from the TMA tile: one N = 80
+//               instruction per 16 keys.
+//   warp 2      TMEM allocation (512 columns: S/P 2 tiles x 2 buffers x 64, O 2 x 80, Q 2 x 40).
 //   warps 4-7   softmax of query tile 0, one thread per query row (tcgen05.ld 32x32b: lane = row, no shuffles);
 //   warps 8-11  softmax of query tile 1.
 // Online softmax with a lazy rescale: the running maximum is only raised (and O / the row sum rescaled in TMEM) when a
 // row's new maximum exceeds the one in use by more than 2^8 — after the first K tiles that is rare, so the O round trip
 // through registers disappears from the steady state.  exp2 on MUFU with the log2(e) / sqrt(d) factor folded into one
 // FFMA; a quarter of the exponentials take an FMA-pipe polynomial instead.
-// Measured (B200, 32 sequences x 16 heads x 1024^2): 222 us = 700 TFLOP/s at d = 72; the MUFU pipe is
-// 56 % busy, the tensor pipe 35 %.  What bounds it is the per-iteration dependency chain of a softmax warp (TMEM load ->
-// max -> exp -> TMEM store -> fence -> barrier, ~900 cycles of latency per 64 keys against ~1000 cycles of MUFU issue), with
-// only two softmax warps per scheduler to overlap it; the bring-up variants that tried to hide it (16 softmax warps with
-// split columns, optimistic max + prefetch, staggered tiles, 0..75 % polynomial exp2) all land within 5 % of this one.
+// Measured (B200, 32 sequences x 16 heads x 1024^2): 215 us = 718 TFLOP/s at d = 72.  ncu: MUFU pipe
+// 45 % busy, tensor-core pipe 53 % — the two add up to the whole kernel: softmax and MMA phases of the two tiles do not
+// overlap (both tiles run in lock-step, and a softmax warp spends ~850 cycles per 64 keys in its TMEM / barrier dependency
+// chain).  Bring-up variants that tried to break this are listed in DESIGN.md; all land within 5 % of each other.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -60,6 +62,7 @@ constexpr int SA_SMEM_BYTES = SA_SMEM_BAR + 512 + 1024;   // barriers + alignmen
 constexpr int SA_THREADS = 384;
 constexpr uint32_t SA_TMEM_COLS = 512;
 constexpr uint32_t SA_O_COL = 256;         // O accumulators start here; S/P buffer b of tile t at t * 128 + b * 64
+constexpr uint32_t SA_Q_COL = SA_O_COL + 80;   // Q of tile t (fp16 pairs, 40 columns) behind its O accumulator (80 columns)
 constexpr float SA_RESCALE_LOG2 = 8.0f;    // lazy-rescale threshold (log2 units): P stays <= 2^8 in fp16
 
 struct SpatialArgs {
@@ -126,7 +129,8 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
   // between two waits of its consumer (with one barrier per tile the parity wait aliases: deadlock / early pass).
   uint64_t* p_full = s_full + 2 * SA_QT;       // [2 tiles][2 buffers] P is in TMEM (and O rescaled if needed)
   uint64_t* o_full = p_full + 2 * SA_QT;       // [2 tiles][2 buffers] the P V reading that buffer has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2 * SA_QT);
+  uint64_t* qt_full = o_full + 2 * SA_QT;      // [2 tiles] Q of tile t has been copied into TMEM (A operand of S = Q K^T)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qt_full + SA_QT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,7 +147,9 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    mbar_init(q_empty, 8);   // all eight softmax warps have copied their Q rows out of shared memory
+    mbar_init(&qt_full[0], 4);
+    mbar_init(&qt_full[1], 4);
     for (int s = 0; s < SA_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -196,8 +202,12 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
           tma_load_4d_hint(smem_k + s * SA_KV + SA_KV_A, &tmap_kb, &k_full[s], 64, h, a.k_which, row_kv0 + j * SA_BN, kEvictLast);
           mbar_wait(&v_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[s], SA_KV);
-          tma_load_4d_hint(smem_v + s * SA_KV, &tmap_ka, &v_full[s], 0, h, a.v_which, row_kv0 + j * SA_BN, kEvictLast);
-          tma_load_4d_hint(smem_v + s * SA_KV + SA_KV_A, &tmap_kb, &v_full[s], 64, h, a.v_which, row_kv0 + j * SA_BN, kEvictLast);
+          // V: five 16-dim SWIZZLE_32B boxes (2 KB each) = one MN-major operand of N = 80 for a single P V instruction
+          // per 16 keys (dims 72..79 of the last box are zero fill)
+#pragma unroll
+          for (int db = 0; db < 5; ++db)
+            tma_load_4d_hint(smem_v + s * SA_KV + db * SA_KV_B, &tmap_kb, &v_full[s], 16 * db, h, a.v_which,
+                             row_kv0 + j * SA_BN, kEvictLast);
         }
       }
     }
@@ -209,43 +219,42 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
     // the loop inside a single-lane branch every tcgen05.mma cost four R2UR round trips and the issuing thread, not the
     // tensor pipe or the MUFU, bounded the kernel (26 small MMAs per key-tile pair).
     constexpr uint32_t idesc_s = make_idesc_f16(SA_BM, SA_BN, 0, 0);
-    constexpr uint32_t idesc_pv64 = make_idesc_f16(SA_BM, 64, 0, 1);   // B = V, MN-major
-    constexpr uint32_t idesc_pv16 = make_idesc_f16(SA_BM, 16, 0, 1);
+    constexpr uint32_t idesc_pv80 = make_idesc_f16(SA_BM, 80, 0, 1);   // B = V, MN-major
+    constexpr uint64_t v_lbo_word = static_cast<uint64_t>((SA_KV_B >> 4) & 0x3FFFu) << 16;
     // descriptor = lo | hi << 32: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14 | layout << 29
     constexpr uint64_t hi_sw128 = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
     constexpr uint64_t hi_sw32 = static_cast<uint64_t>((256u >> 4) | (1u << 14) | (6u << 29)) << 32;
     const uint32_t lbo = (a.v_lbo >> 4) << 16;
-    const uint32_t q_lo = ((smem_u32(smem_q) & 0x3FFFFu) >> 4) | lbo;
     const uint32_t k_lo = ((smem_u32(smem_k) & 0x3FFFFu) >> 4) | lbo;
-    const uint32_t v_lo = ((smem_u32(smem_v) & 0x3FFFFu) >> 4) | lbo;
+    const uint32_t v_lo = (smem_u32(smem_v) & 0x3FFFFu) >> 4;
     // S[t][b] = Q[t] K^T: K dimension 80 = 4 steps of 16 inside the 128-byte swizzle rows + 1 step in the 32-byte tile
     auto issue_s = [&](int t, int b, int ks) {
-      const uint32_t qa = q_lo + t * (SA_TILE >> 4), ka = k_lo + ks * (SA_KV >> 4);
+      const uint32_t ka = k_lo + ks * (SA_KV >> 4);
       const uint32_t d = tmem_base + t * 128 + b * SA_BN;
+      const uint32_t qt = tmem_base + SA_Q_COL + t * 128;   // Q[t] in TMEM: 40 columns, 8 per 16-dim step
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        tc_mma_f16_ss(d, hi_sw128 | (qa + 2 * k), hi_sw128 | (ka + 2 * k), idesc_s, k > 0 ? 1u : 0u);
-      tc_mma_f16_ss(d, hi_sw32 | (qa + (SA_TILE_A >> 4)), hi_sw32 | (ka + (SA_KV_A >> 4)), idesc_s, 1u);
+      for (int k = 0; k < 4; ++k) tc_mma_f16_ts(d, qt + 8 * k, hi_sw128 | (ka + 2 * k), idesc_s, k > 0 ? 1u : 0u);
+      tc_mma_f16_ts(d, qt + 32, hi_sw32 | (ka + (SA_KV_A >> 4)), idesc_s, 1u);
       tc_commit(&s_full[2 * t + b]);
     };
-    // O[t] (+)= P[t][b] V: 4 steps of 16 keys; dims 0..63 from the SW128 tile (N = 64), dims 64..79 from the SW32 tile (N = 16)
+    // O[t] (+)= P[t][b] V: 4 steps of 16 keys
     auto issue_pv = [&](int t, int b, int vs, uint32_t acc) {
       const uint32_t va = v_lo + vs * (SA_KV >> 4);
       const uint32_t p = tmem_base + t * 128 + b * SA_BN;
       const uint32_t o = tmem_base + SA_O_COL + t * 128;
+      // one N = 80 instruction per 16 keys: V is MN-major in five 16-dim SWIZZLE_32B atoms, 2 KB apart (leading byte
+      // offset), 8-key groups 256 B apart (stride byte offset); a key step advances by 16 keys x 32 B
 #pragma unroll
-      for (int k = 0; k < SA_BN / 16; ++k) {
-        const uint32_t ak = (acc | static_cast<uint32_t>(k > 0)) ? 1u : 0u;
-        const uint32_t pk = p + 8 * k;
-        tc_mma_f16_ts(o, pk, hi_sw128 | (va + k * (2048 >> 4)), idesc_pv64, ak);
-        tc_mma_f16_ts(o + 64, pk, hi_sw32 | (va + ((SA_KV_A + k * 512) >> 4)), idesc_pv16, ak);
-      }
+      for (int k = 0; k < SA_BN / 16; ++k)
+        tc_mma_f16_ts(o, p + 8 * k, hi_sw32 | v_lbo_word | (va + k * (512 >> 4)), idesc_pv80,
+                      (acc | static_cast<uint32_t>(k > 0)) ? 1u : 0u);
       tc_commit(&o_full[2 * t + b]);
     };
     uint32_t kc = 0, vc = 0;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      mbar_wait(q_full, it & 1);
+      mbar_wait(&qt_full[0], it & 1);
+      mbar_wait(&qt_full[1], it & 1);
       // the score buffers run two key tiles ahead of the softmax: S_0 and S_1 first
       for (int i = 0; i < 2; ++i) {
         const int ks = kc % SA_STAGES;
@@ -255,7 +264,6 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
           issue_s(0, i, ks);
           issue_s(1, i, ks);
           tc_commit(&k_empty[ks]);
-          if (i == nkv - 1) tc_commit(q_empty);
         }
         __syncwarp();
         ++kc;
@@ -280,10 +288,7 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
         }
         if (elect_one()) {
           tc_commit(&v_empty[vs]);
-          if (more) {
-            tc_commit(&k_empty[ks]);
-            if (j + 3 == nkv) tc_commit(q_empty);   // the item's last S MMAs are issued: Q may be overwritten
-          }
+          if (more) tc_commit(&k_empty[ks]);
         }
         __syncwarp();
         ++vc;
@@ -306,6 +311,35 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int klen = a.cross ? a.kv_len[item / (nqp * a.H)] : a.S;   // keys of this item's sequence
+      {
+        // Q[t] -> TMEM (the A operand of every S = Q K^T of this item): with Q read from shared memory each N = 64 score
+        // MMA re-read 4 KB of it and sat on the shared-memory port; from TMEM the instruction is compute-bound.  The rows
+        // are un-swizzled by hand (SWIZZLE_128B tile: 16-byte chunk c of row r sits at c ^ (r & 7); SWIZZLE_32B tile: at
+        // c ^ ((r >> 2) & 1)).  The previous item's score MMAs have retired (this thread consumed their last result).
+        mbar_wait(q_full, it & 1);
+        const uint32_t qa = smem_u32(smem_q + t * SA_TILE), qb = qa + SA_TILE_A;
+        uint32_t w[32], w8[8];
+#pragma unroll
+        for (int cch = 0; cch < 8; ++cch) {
+          const int4 v = lds_v4_addr(qa + row * 128 + ((cch ^ (row & 7)) << 4));
+          w[4 * cch] = v.x; w[4 * cch + 1] = v.y; w[4 * cch + 2] = v.z; w[4 * cch + 3] = v.w;
+        }
+#pragma unroll
+        for (int cch = 0; cch < 2; ++cch) {
+          const int4 v = lds_v4_addr(qb + row * 32 + ((cch ^ ((row >> 2) & 1)) << 4));
+          w8[4 * cch] = v.x; w8[4 * cch + 1] = v.y; w8[4 * cch + 2] = v.z; w8[4 * cch + 3] = v.w;
+        }
+        const uint32_t qt = tmem_base + lane_off + SA_Q_COL + t * 128;
+        tmem_st_32x32b_x32(qt, w);
+        tmem_st_32x32b_x8(qt + 32, w8);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&qt_full[t]);
+          mbar_arrive(q_empty);      // shared-memory Q may be refilled for the next item
+        }
+      }
       for (int j = 0; j < nkv; ++j) {
         const int b = j & 1;
         const uint32_t sa = s_addr + b * SA_BN;
