@@ -27,11 +27,11 @@ FP_LAYERS = ["x_embedder", "t_block", "t_embedder", "y_embedder", "final_layer"]
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE vq_gemm_w8a8_kernel launch at M = 16384, from the `ncu --set full`
-# captures of the four block shapes (profiles/r01_s21_gemm_16384_<N>_<K>_<epi>.md), in MB keyed by (N, K).  Below the
+# captures of the four block shapes (profiles/r01_s22_gemm_16384_<N>_<K>_<epi>.md), in MB keyed by (N, K).  Below the
 # algorithmic bytes (136 / 96 / 175 / 156 MB) because inputs written by the previous kernel still sit in the 126 MB L2
 # and part of the output is still there when the kernel ends.
-NCU_GEMM_DRAM_MB = {(3 * HIDDEN, HIDDEN): 85.0, (HIDDEN, HIDDEN): 64.0, (4 * HIDDEN, HIDDEN): 124.1,
-                    (HIDDEN, 4 * HIDDEN): 226.7}
+NCU_GEMM_DRAM_MB = {(3 * HIDDEN, HIDDEN): 86.4, (HIDDEN, HIDDEN): 64.3, (4 * HIDDEN, HIDDEN): 126.6,
+                    (HIDDEN, 4 * HIDDEN): 226.3}
 
 
 def gemm_dram_bytes_per_step(depth):
@@ -411,7 +411,7 @@ def main():
                          "frac": achieved / peak_tops,
                          "traffic": gemm_dram_bytes_per_step(args.depth) / max(1, len(gemm_events)),
                          "traffic_unit": "bytes per launch (ncu dram read+write of the 4 block shapes at M=16384, "
-                                         "profiles/r01_s21_gemm_*.md, averaged over this step's launches)",
+                                         "profiles/r01_s22_gemm_*.md, averaged over this step's launches)",
                          "algorithmic_bytes_per_launch": 2 * args.depth * (2 * 136e6 + 3 * 95.6e6 + 57.9e6 + 175e6 + 156e6)
                                                          / max(1, len(gemm_events)),
                          "kernel": "vq_gemm_w8a8_kernel (all QuantLinear GEMMs of a step)",
