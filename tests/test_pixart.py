@@ -130,3 +130,51 @@ def test_pixart_w8a8_on_gpu(pix):
     # the quantisation error itself is 1.0e-2 on this model. Per-layer parity (<= 1e-3) is asserted on the layer cases.
     assert a[1] <= 8e-3 and b[1] <= 8e-3, (a, b)
     assert c[1] <= 1e-2 and d[1] <= 1e-2, (c, d)
+
+
+@pytest.mark.gpu
+def test_pixart_512_fused_schedule_uses_the_attention_kernels():
+    """BASELINE config 2 shape (PixArt 512x512: 64x64 latent -> 1024 tokens, CFG batch 2), two blocks of synthetic weights:
+    the fused schedule (fused patch embedding, tcgen05 self- and cross-attention) against the layer-by-layer schedule
+    (QuantLayer calls, Conv2d, torch SDPA) on the same GPU."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from viditq_b200 import ops
+    from viditq_b200.pixart import PixArtMS
+    from viditq_b200.qdiff import QuantModel
+    model = PixArtMS(input_size=64, depth=2)
+    model.init_synthetic(seed=2)
+    model.eval()
+    sq = Cfg(enable=False, channel_wise_scale_type="momentum_act_max", momentum=0.95, alpha=0.625)
+    wq = Cfg(n_bits=8, per_group="channel", channel_dim=0, scale_method="min_max", round_mode="nearest",
+             mixed_precision=[4, 6, 8])
+    aq = Cfg(n_bits=8, per_group="token", scale_method="min_max", round_mode="nearest_ste", running_stat=False,
+             dynamic=True, sym=False, n_spatial_token=1024, n_temporal_token=1, n_prompt=120, smooth_quant=sq)
+    qnn = QuantModel(model, wq, aq, model_type="pixart")
+    qnn.cuda()
+    qnn.half()
+    model.dtype = torch.float16
+    qnn.set_module_name_for_quantizer(module=qnn.model)
+    qnn.init_weight_quant_params()
+    qnn.set_quant_init_done("weight")
+    qnn.set_quant_init_done("activation")
+    qnn.set_quant_state(True, True)
+    qnn.set_layer_quant(model=qnn, module_name_list=FP_LAYERS, quant_level="per_layer", weight_quant=False,
+                        act_quant=False, prefix="")
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 4, 64, 64, generator=g).cuda()
+    t = torch.tensor([500.0, 500.0], device="cuda")
+    y = torch.randn(2, 1, 120, 4096, generator=g).cuda()
+    mask = torch.zeros(2, 120, dtype=torch.int64)
+    mask[0, :57] = 1
+    mask[1, :120] = 1
+    mask = mask.cuda()
+    with torch.no_grad():
+        ref = qnn(x, t, y, mask=mask).float().cpu().numpy()
+        n0 = ops.launch_count()
+        fused = model.forward_fused(x, t, y, mask=mask).float().cpu().numpy()
+    assert np.isfinite(fused).all() and ops.check_status() == 0
+    assert ops.launch_count() - n0 >= 2 * 18
+    inf, l2 = _rel(fused, ref)
+    print("pixart-512 fused (own attention, fused patch embed) vs layerwise schedule: %.3e %.3e" % (inf, l2))
+    assert l2 <= 8e-3, (inf, l2)

@@ -70,7 +70,7 @@ struct SpatialArgs {
   float scale_log2e;
   int debug;        // 0 = attention; 1 = P := 1; 2 = P := identity on the first key tile; 3 = also dump S of key tile 0
   float* dbg;       // debug 3: [items][2][128][128] raw scores of the first key tile
-  uint32_t v_lbo;   // leading byte offset written into the MN-major V descriptors (unused by the hardware when N fits one atom)
+  uint32_t k_lbo;   // leading byte offset written into the K-major K descriptors (ignored by the hardware for swizzled K-major tiles)
   // cross attention (vq_attn_cross_tc): sequence = sample, S = image tokens per sample (queries), keys / values = that
   // sample's prompt rows [kv_start[b], kv_start[b] + kv_len[b]) of a separate packed k|v tensor, at most 128 of them
   int cross;
@@ -224,7 +224,7 @@ vq_attn_spatial_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid
     // descriptor = lo | hi << 32: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14 | layout << 29
     constexpr uint64_t hi_sw128 = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
     constexpr uint64_t hi_sw32 = static_cast<uint64_t>((256u >> 4) | (1u << 14) | (6u << 29)) << 32;
-    const uint32_t lbo = (a.v_lbo >> 4) << 16;
+    const uint32_t lbo = (a.k_lbo >> 4) << 16;
     const uint32_t k_lo = ((smem_u32(smem_k) & 0x3FFFFu) >> 4) | lbo;
     const uint32_t v_lo = (smem_u32(smem_v) & 0x3FFFFu) >> 4;
     // S[t][b] = Q[t] K^T: K dimension 80 = 4 steps of 16 inside the 128-byte swizzle rows + 1 step in the 32-byte tile

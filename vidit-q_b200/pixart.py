@@ -102,13 +102,27 @@ class PixArtMS(nn.Module):
     mask_select_plan = staticmethod(STDiT.mask_select_plan)
     kv_segments = staticmethod(STDiT.kv_segments)
 
-    def embed(self, x, timestep, y, mask, plan=None):
-        x = x.to(self.dtype)
+    def _pos_embed(self, gh, gw, device):
+        """PixArtMS recomputes its sin-cos table on the host every forward (PixArtMS.py:150-156); it only depends on the
+        grid, so it is built once per (grid, device, dtype) and kept on the device."""
+        key = (gh, gw, str(device), self.dtype)
+        cache = self.__dict__.setdefault("_pe_cache", {})
+        if key not in cache:
+            pe = torch.from_numpy(pixart_pos_embed(self.hidden_size, gh, gw, self.pe_interpolation, self.base_size))
+            cache[key] = pe.to(device).to(self.dtype).contiguous()
+        return cache[key]
+
+    def embed(self, x, timestep, y, mask, plan=None, fused=False):
         timestep = timestep.to(self.dtype)
         y = y.to(self.dtype)
         gh, gw = x.shape[-2] // self.patch_size, x.shape[-1] // self.patch_size
-        pe = torch.from_numpy(pixart_pos_embed(self.hidden_size, gh, gw, self.pe_interpolation, self.base_size))
-        x = self.x_embedder(x) + pe.unsqueeze(0).to(x.device).to(self.dtype)
+        pe = self._pos_embed(gh, gw, x.device)
+        proj = self.x_embedder.proj
+        if fused and proj.weight.dtype == torch.float16:
+            # patchify + bias + position embedding in one pass (vq_patch_embed, the T = 1 case)
+            x = ops.patch_embed(x.float().contiguous(), proj.weight, proj.bias, pe, (self.patch_size, self.patch_size))
+        else:
+            x = self.x_embedder(x.to(self.dtype)) + pe.unsqueeze(0)
         t = self.t_embedder(timestep, dtype=x.dtype)
         t0 = self.t_block(t)
         y = self.y_embedder(y)
@@ -143,7 +157,7 @@ class PixArtMS(nn.Module):
         return self.forward(x, timestep, y, data_info=data_info, **kwargs).chunk(2, dim=1)[0]
 
     def forward_fused(self, x, timestep, y, mask=None, plan=None, segments=None):
-        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan)
+        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan, fused=True)
         if segments is None:
             segments = self.kv_segments(y_lens, x.device)
         B, N, C = x.shape
