@@ -174,7 +174,7 @@ def test_pixart_512_fused_schedule_uses_the_attention_kernels():
         n0 = ops.launch_count()
         fused = model.forward_fused(x, t, y, mask=mask).float().cpu().numpy()
     assert np.isfinite(fused).all() and ops.check_status() == 0
-    assert ops.launch_count() - n0 >= 2 * 18
+    assert ops.launch_count() - n0 >= 2 * 16 + 1      # 16 own launches per block + the fused patch embedding
     inf, l2 = _rel(fused, ref)
     print("pixart-512 fused (own attention, fused patch embed) vs layerwise schedule: %.3e %.3e" % (inf, l2))
     assert l2 <= 8e-3, (inf, l2)
