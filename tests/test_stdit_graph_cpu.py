@@ -128,3 +128,23 @@ def test_pattern_in_semantics():
     assert not pattern_in("model.blocks.7.attn.q", "blocks.[0-5].attn.q")
     assert pattern_in("blocks.0.mlp.fc1", "*.0.mlp")
     assert pattern_in("x_embedder", "x_embedder")
+
+
+def test_frame_sharding_host_helpers():
+    """Host-side pieces of the frame-sharded forward that need no process group: the frame ranges, the unpatchify of a
+    rank's frames, and the refusal of batch-pooled codes."""
+    from viditq_b200 import shard
+    from viditq_b200.stdit import STDiT
+    assert [shard.frame_slice(16, 4, r) for r in range(4)] == [(0, 4), (4, 8), (8, 12), (12, 16)]
+    with pytest.raises(ValueError):
+        shard.frame_slice(16, 3, 0)
+    model = STDiT(input_size=(4, 8, 8), depth=1, hidden_size=64, num_heads=4)
+    full = torch.randn(2, 4 * 16, 4 * 8)                       # [B, T*S, patch * out_channels]
+    whole = model.unpatchify(full)
+    part = model.unpatchify(full.view(2, 4, 16, 32)[:, 1:3].reshape(2, 2 * 16, 32))   # frames 1..2 only
+    assert part.shape == (2, 8, 2, 8, 8) and torch.equal(part, whole[:, :, 1:3])
+
+    class A:
+        G = 2
+    with pytest.raises(ValueError):
+        shard.exchange_act_codes(A(), 1, 2, 16, 2, True)
