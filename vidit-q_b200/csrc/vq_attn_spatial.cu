@@ -50,7 +50,7 @@ constexpr int SA_STAGES = 4;               // K ring and V ring depth
 constexpr int SA_TILE_A = SA_BM * 128;     // Q: dims 0..63: 128-byte rows, SWIZZLE_128B
 constexpr int SA_TILE_B = SA_BM * 32;      // Q: dims 64..79: 32-byte rows, SWIZZLE_32B (72..79 zero)
 constexpr int SA_TILE = SA_TILE_A + SA_TILE_B;
-constexpr int SA_KV_A = SA_BN * 128;       // K / V tile: same two pieces with 64 rows
+constexpr int SA_KV_A = SA_BN * 128;       // K tile: same two pieces with 64 rows; V tile: five 32-byte-row boxes, same bytes
 constexpr int SA_KV_B = SA_BN * 32;
 constexpr int SA_KV = SA_KV_A + SA_KV_B;
 constexpr int SA_OSTAGE = 128 * SA_D * 2;  // dense [128][72] fp16 staging tile of the output

@@ -583,8 +583,8 @@ __device__ __forceinline__ void uapply_gelu(UnitRegs<U>& r) {
   }
 }
 
-template <int WPR, bool GELU>
-__global__ void __launch_bounds__(256) vq_act_quant_seg_kernel(const ActQuantArgs a) {
+template <int WPR, bool GELU, int OCC = 4>
+__global__ void __launch_bounds__(256, OCC) vq_act_quant_seg_kernel(const ActQuantArgs a) {
   grid_dep_sync();
   constexpr int RPB = 8 / WPR;   // rows per block
   __shared__ float s_mn[8], s_mx[8];
@@ -643,7 +643,15 @@ static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
   if (!LN && a.G == 1 && a.head_S == 0 && (a.K == 4608 || a.K == 2304 || (GELU && a.K == 1152))) {
     const int wpr = a.K / 1152;
     dim3 g((a.rows * wpr + 7) / 8);
-    if (wpr == 4) launch_pdl(vq_act_quant_seg_kernel<4, GELU>, g, block, 0, st, a);
+    // resident blocks per SM of the K = 4608 kernel (registers capped at 62 / 48 / 40): 5 measured best (GELU variant
+    // 118.8 / 112.7 / 114.8 us, plain 86.0 / 79.9 / 77.9 us for 4 / 5 / 6 at M = 32768, cold L2); knob VQ_SEG_OCC
+    static const int occ = [] {
+      const char* e = getenv("VQ_SEG_OCC");
+      return e ? atoi(e) : 5;
+    }();
+    if (wpr == 4 && occ == 5) launch_pdl(vq_act_quant_seg_kernel<4, GELU, 5>, g, block, 0, st, a);
+    else if (wpr == 4 && occ == 6) launch_pdl(vq_act_quant_seg_kernel<4, GELU, 6>, g, block, 0, st, a);
+    else if (wpr == 4) launch_pdl(vq_act_quant_seg_kernel<4, GELU>, g, block, 0, st, a);
     else if (wpr == 2) launch_pdl(vq_act_quant_seg_kernel<2, GELU>, g, block, 0, st, a);
     else launch_pdl(vq_act_quant_seg_kernel<1, GELU>, g, block, 0, st, a);
     return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
