@@ -116,6 +116,33 @@ int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const void* a_zp, 
                  int a_rows_period, const uint8_t* w_codes, const VqColParam* col, int M, int N, int K, int epi, const void* res,
                  int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* stream);
 
+/* Per-channel activation maxima for smooth-quant: `input.abs().max(dim=-2)[0]` of quant_layer.py:116,119 (same lines in
+ * stdit_quant_layer.py:31,34 / :122,125 / :235,238) — the live statistic of channel_wise_scale_type "dynamic" and of the
+ * running-stat EMA that PixArt keeps switched on at inference (quirk Q17, t2i/scripts/quant_txt2img.py:297-300).
+ * x fp16 [G, n, K] contiguous; out_bits u32 [G, K], ZERO-FILLED by the caller: on return out_bits[g,k] holds the fp16 bit
+ * pattern of max_r |x[g,r,k]| (exact).  gelu != 0: statistics of h(gelu_tanh(x)) instead (fused schedules pass fc2 the
+ * pre-activation).                                                                                                     */
+int vq_col_absmax(const void* x, int G, int n, int K, int gelu, uint32_t* out_bits, void* stream);
+
+/* (a3-a7, SURVEY.md section 8b entry 3) ONE call per QuantLayer-family forward: dynamic per-token activation quantiser
+ * (a1) -> integer GEMM on prepared weight codes -> per-token x per-channel dequant -> bias | GELU | gated residual
+ * epilogue; replaces quant_layer.py:185-211 / stdit_quant_layer.py:68-96 / dit_quant_layer.py:18-29.
+ * x fp16 [G*rows, K] contiguous (statistics of token r pooled over the G batch entries, quirk Q1); smooth fp16 [K] or NULL;
+ * ln_shift / ln_scale: fp16 [G*rows / rows_per_mod, K] or both NULL — when given, LayerNorm(eps 1e-6, no affine) +
+ * t2i_modulate (blocks.py:51) run in front of the quantiser (the producers of the q|k|v and fc1 inputs, stdit.py:104,125).
+ * K == 1152 with G in {1, 2, 4} (rows a multiple of 128 / G when G > 1) and G * rows <= 8192 (VQ_LINEAR_FUSED_MAX_M) runs as
+ * ONE kernel launch (vq_linear_fused_kernel: producer warps quantise the 128-row activation panel straight into the
+ * swizzled shared-memory operand of tcgen05.mma; no codes ever reach HBM); other shapes run the two-launch sequence
+ * vq_act_quant | vq_ln_modulate_act_quant -> vq_gemm_w8a8 through `workspace` — vq_linear_launch_count says which.
+ * workspace: device scratch of at least vq_linear_workspace_bytes(G, rows, K) bytes (the library never allocates).
+ * out_delta / out_zp (optional, may be NULL): fp16 [rows] per-token parameters, the DynamicActQuantizer side state.     */
+int64_t vq_linear_workspace_bytes(int G, int rows, int K);
+int vq_linear_launch_count(int G, int rows, int K);   /* 1 = fused kernel, 2 = quantise pass + GEMM */
+int vq_linear_w8a8(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift, const void* ln_scale,
+                   int rows_per_mod, int n_bits, const uint8_t* w_codes, const VqColParam* col, int N, int epi,
+                   const void* res, int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* out_delta,
+                   void* out_zp, void* workspace, int64_t workspace_bytes, uint32_t* status, void* stream);
+
 /* (a9) temporal self-attention of STDiT (stdit.py:112-118, blocks.py:151-195 on "(B S) T C"), reading q|k|v in place
  * from the fused GEMM output qkv fp16 [B*T*S, 3*H*head_dim] in the (T S) token layout; out fp16 [B*T*S, H*head_dim].
  * head_dim must be 72, T <= 16. scale = head_dim^-0.5.                                                             */

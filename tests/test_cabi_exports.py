@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     hdr = open(os.path.join(ROOT, "include", "viditq_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(vq_[a-z0-9_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(?:int|int64_t)\s+(vq_[a-z0-9_]+)\s*\(", hdr)))
 
 
 def test_header_declares_the_hot_path_entry_points():

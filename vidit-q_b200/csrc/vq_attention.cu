@@ -287,7 +287,8 @@ extern "C" int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S,
   TemporalArgs a{static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, S, H, scale * 1.4426950408889634f};
   const long long units = static_cast<long long>(B) * S * H;
   const int smem = TEMPORAL_WARPS * 3 * 16 * PITCH * 2;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};   // per-device function attribute (one process may drive several GPUs)
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     if (cudaFuncSetAttribute(vq_attn_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return VQ_ERR_LAUNCH;
@@ -314,7 +315,8 @@ extern "C" int vq_attn_cross(const void* q, const void* kv, void* out, const int
   CrossArgs a{static_cast<const __half*>(q), static_cast<const __half*>(kv), static_cast<__half*>(out), kv_start,
               kv_len, B, N, H, scale * 1.4426950408889634f};
   const int smem = (2 * CROSS_KT * 16 + 2 * CROSS_WARPS * 16) * PITCH * 2;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};   // per-device function attribute (one process may drive several GPUs)
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     if (cudaFuncSetAttribute(vq_attn_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return VQ_ERR_LAUNCH;

@@ -553,7 +553,8 @@ static int make_attn_out_tmap(CUtensorMap* out, const void* base, uint64_t rows,
 template <bool DBG, int EMU>
 static int launch_spatial(const CUtensorMap& qa, const CUtensorMap& qb, const CUtensorMap& ka, const CUtensorMap& kb,
                           const CUtensorMap& to, const SpatialArgs& a, int grid, cudaStream_t st) {
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};   // per-device function attribute (one process may drive several GPUs)
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     if (cudaFuncSetAttribute(vq_attn_spatial_kernel<DBG, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM_BYTES) !=
         cudaSuccess)

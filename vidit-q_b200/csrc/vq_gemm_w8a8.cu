@@ -27,116 +27,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "vq_ptx.cuh"
-#include "vq_internal.h"
+#include "vq_gemm_common.cuh"
 
 namespace vq {
-
-constexpr int BM = 128;
-constexpr int BN = 192;
-constexpr int BK = 128;  // bytes == u8 elements per K block (one 128B swizzle row)
-constexpr int UMMA_K = 32;
-constexpr int STAGES = 4;        // single-CTA tiles: 4 x (16 KB A + 24 KB B)
-constexpr int PAIR_STAGES = 6;   // CTA pairs stage half a B tile each: 6 x (16 KB A + 12 KB B)
-constexpr int MAX_STAGES = 6;
-constexpr int B_PAIR_STAGE_BYTES = (BN / 2) * BK;   // cta_group::2: each CTA of the pair stages half of the B tile
-constexpr int A_STAGE_BYTES = BM * BK;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK;  // 24 KB
-constexpr int ACC_STAGES = 2;
-constexpr int ACC_COLS = 256;  // TMEM column stride between accumulator stages
-constexpr int TMEM_COLS = 512;
-constexpr int NUM_EPI_WARPS = 8;                      // warp%4 = TMEM lane quarter, (warp-4)/4 = column half
-constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
-constexpr int EPI_COLS = BN / 2;                      // 96 output columns per epilogue warp per tile
-constexpr int EPI_CHUNK = 32;                         // columns per TMEM load / staging sub-tile (64 B of fp16 per row)
-constexpr int EPI_NCHUNK = EPI_COLS / EPI_CHUNK;      // 3
-constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 2;     // one sub-tile: 32 rows x 64 B, SWIZZLE_64B
-constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_NCHUNK * EPI_BUF_BYTES;   // one 32 x 96 strip per warp
-constexpr int COLBUF_BYTES = 2 * BN * 16;                // per-tile {c1, zw, dw, bias} records, double-buffered
-constexpr int OPERAND_BYTES_SINGLE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-constexpr int OPERAND_BYTES_PAIR = PAIR_STAGES * (A_STAGE_BYTES + B_PAIR_STAGE_BYTES);
-constexpr int OPERAND_BYTES = OPERAND_BYTES_PAIR > OPERAND_BYTES_SINGLE ? OPERAND_BYTES_PAIR : OPERAND_BYTES_SINGLE;
-constexpr int SMEM_BYTES = OPERAND_BYTES + EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-
-struct GemmArgs {
-  int M, N, K;
-  const __half* a_delta;    // [M] per-token step size (fp16, as the reference's DynamicActQuantizer.delta)
-  const __half* a_zp;       // [M] per-token zero point (integer valued fp16)
-  const int32_t* a_rowsum;  // [M] sum_k xq[m,k]
-  int a_period;             // delta/zp row index = m % a_period (token statistics pooled over the batch, Q1)
-  const VqColParam* col;    // [N] {c1, zw, dw, bias}
-  __half* out;              // [M, ldo]
-  int ldo;
-  int epi;                  // VQ_EPI_*
-  const __half* res;        // [M, ldr] residual (VQ_EPI_GATE_RESIDUAL)
-  int ldr;
-  const __half* gate;       // [M / rows_per_gate, N]
-  int rows_per_gate;
-  uint64_t store_policy;    // L2 cache policy of the output stores (kEvictFirst unless VQ_STORE_POLICY=normal)
-};
-
-constexpr int VQ_EPI_DEBUG_MAINLOOP = 3;  // internal: discard accumulators (measures the TMA->MMA pipeline alone)
-constexpr int VQ_EPI_DEBUG_LOADS = 5;     // internal: + TMEM loads (no math, no stores)
-constexpr int VQ_EPI_DEBUG_MATH = 6;      // internal: + dequant math (no staging / stores)
-constexpr int VQ_EPI_DEBUG_STORES = 7;    // internal: TMEM loads + staging + TMA stores, no dequant math
-
-// Dequantise 32 consecutive output columns of one row (thread = row): int32 zero-point correction, one fp32 FMA with
-// dx * dw and the bias, one rounding to fp16, optional GELU. Results stay in registers (16 packed half2).
-template <int EPI>
-__device__ __forceinline__ void dequant_chunk(const uint32_t (&v)[32], int32_t zx, int32_t rs, float dx,
-                                              const int4* colp, uint32_t (&packed)[16]) {
-  // colp: this chunk's 16 column-PAIR records in shared memory, two int4 per pair (warp-uniform -> broadcast LDS.128):
-  //   [2j]   = {c1(n), c1(n+1), zw(n), zw(n+1)}      [2j+1] = {dw(n), dw(n+1), bias(n), bias(n+1)} (fp32 bits)
-  const float2 dx2 = make_float2(dx, dx);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int4 ci = lds_v4(colp + 2 * j);
-    const int4 cf = lds_v4(colp + 2 * j + 1);
-    const int32_t t0 = static_cast<int32_t>(v[2 * j]) - zx * ci.x - rs * ci.z;
-    const int32_t t1 = static_cast<int32_t>(v[2 * j + 1]) - zx * ci.y - rs * ci.w;
-    const float2 s2 = __fmul2_rn(dx2, make_float2(__int_as_float(cf.x), __int_as_float(cf.y)));
-    const float2 f2 = __ffma2_rn(make_float2(static_cast<float>(t0), static_cast<float>(t1)), s2,
-                                 make_float2(__int_as_float(cf.z), __int_as_float(cf.w)));
-    __half2 h2 = __floats2half2_rn(f2.x, f2.y);
-    if (EPI == VQ_EPI_GELU_TANH) {
-      const float2 g = gelu_tanh_pair(__half22float2(h2));
-      h2 = __floats2half2_rn(g.x, g.y);
-    }
-    packed[j] = *reinterpret_cast<uint32_t*>(&h2);
-  }
-}
-
-// Write one chunk (32 columns of this thread's row) into its staging sub-tile: row-major 64-byte rows, 16-byte piece
-// index XOR ((row >> 1) & 3) == CU_TENSOR_MAP_SWIZZLE_64B (conflict-free). For the gated residual the sub-tile already
-// holds the residual (TMA load, same swizzle): x_new = res + gate * y with the reference's two fp16 roundings.
-template <int EPI>
-__device__ __forceinline__ void stage_chunk(const GemmArgs& p, uint32_t (&packed)[16], int row, bool row_ok, int col0,
-                                            uint8_t* sub, int lane) {
-  const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
-  const uint32_t base = smem_u32(sub) + lane * (EPI_CHUNK * 2);
-  if (EPI == VQ_EPI_GATE_RESIDUAL) {
-    const __half* gate_row = p.gate + static_cast<size_t>((row_ok ? row : 0) / p.rows_per_gate) * p.N;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int n = col0 + g * 8;
-      uint4 gv = make_uint4(0, 0, 0, 0);
-      if (n < p.N) gv = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
-      const int4 rv = lds_v4_addr(base + ((g ^ sw) << 4));
-      const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
-      const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __half2 y = *reinterpret_cast<__half2*>(&packed[g * 4 + e]);
-        __half2 o = __hadd2_rn(r2[e], __hmul2_rn(g2[e], y));   // _rn: two roundings, never one fp16 FMA
-        packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&o);
-      }
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < 4; ++g)
-    sts_v4_addr(base + ((g ^ sw) << 4), packed[g * 4 + 0], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
-}
 
 // PAIR = true: launched as 2-CTA clusters; one output tile is 256 rows (128 per CTA) x 192 columns, the leader CTA
 // (cluster rank 0) issues tcgen05.mma.cta_group::2 for both, every CTA TMA-loads its own 128 A rows and HALF of the
@@ -224,8 +117,10 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       constexpr uint32_t kStageBytes = PAIR ? 2 * (A_STAGE_BYTES + B_PAIR_STAGE_BYTES) : (A_STAGE_BYTES + B_STAGE_BYTES);
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int m_idx = (tile % num_m_tiles) * TILE_M + m_cta;
-        const int n_idx = (tile / num_m_tiles) * BN + (PAIR ? static_cast<int>(cta_rank) * (BN / 2) : 0);
+        int tm, tn;
+        tile_to_mn(tile, num_m_tiles, num_n_tiles, p.group_m, tm, tn);
+        const int m_idx = tm * TILE_M + m_cta;
+        const int n_idx = tn * BN + (PAIR ? static_cast<int>(cta_rank) * (BN / 2) : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           // operand tiles are re-read by other CTAs (A by every n-tile, B by every m-tile): keep them in L2
@@ -288,7 +183,9 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
       const int b = local & 1;
       mbar_wait(&colempty_bar[b], ((local >> 1) & 1) ^ 1);
-      const int n0 = (tile / num_m_tiles) * BN;
+      int tm, tn;
+      tile_to_mn(tile, num_m_tiles, num_n_tiles, p.group_m, tm, tn);
+      const int n0 = tn * BN;
 #pragma unroll
       for (int i = 0; i < BN / 64; ++i) {   // 96 column pairs per tile, 3 per lane
         const int pr = lane + 32 * i;
@@ -315,7 +212,9 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     struct RowP { float dx; int32_t zx, rs; };
     auto load_rowp = [&](int tile_) {
       RowP r;
-      const int row_ = (tile_ % num_m_tiles) * TILE_M + m_cta + q * 32 + lane;
+      int tm_, tn_;
+      tile_to_mn(tile_, num_m_tiles, num_n_tiles, p.group_m, tm_, tn_);
+      const int row_ = tm_ * TILE_M + m_cta + q * 32 + lane;
       const int rc = row_ < p.M ? row_ : p.M - 1;
       const int sr = p.a_period >= p.M ? rc : rc % p.a_period;
       r.dx = __half2float(p.a_delta[sr]);
@@ -327,8 +226,10 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int m_idx = (tile % num_m_tiles) * TILE_M + m_cta;
-      const int n_idx = (tile / num_m_tiles) * BN;
+      int tm, tn;
+      tile_to_mn(tile, num_m_tiles, num_n_tiles, p.group_m, tm, tn);
+      const int m_idx = tm * TILE_M + m_cta;
+      const int n_idx = tn * BN;
       const int row0 = m_idx + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
@@ -473,25 +374,29 @@ int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
+int num_sms() {   // per device ordinal: one process may drive several GPUs
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 template <int EPI, bool PAIR>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                             const GemmArgs& args, int grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // the > 48 KB dynamic shared memory opt-in is a per-device function attribute
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SMEM_BYTES);
     if (e != cudaSuccess) return VQ_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -528,7 +433,11 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   if (M <= 0 || N <= 0 || K <= 0 || a_rows_period <= 0) return VQ_ERR_ARG;
   if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0 || !out) return VQ_ERR_ARG;
   if (epi == VQ_EPI_GATE_RESIDUAL && (!res || !gate || rows_per_gate <= 0 || (ldr % 8) != 0)) return VQ_ERR_ARG;
+#ifdef VQ_DEBUG_EPI
   if (epi < 0 || epi > VQ_EPI_DEBUG_STORES || epi == 4) return VQ_ERR_ARG;
+#else
+  if (epi < 0 || epi > VQ_EPI_GATE_RESIDUAL) return VQ_ERR_ARG;   // the bisection epilogues exist in the -DVQ_DEBUG_EPI build only
+#endif
   // CTA pairs (cta_group::2) whenever there is more than one 128-row tile; VQ_GEMM_PAIR=0 forces single-CTA tiles
   static const bool allow_pair = [] {
     const char* e = getenv("VQ_GEMM_PAIR");
@@ -566,7 +475,17 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
     return (e && e[0] == 'n') ? kEvictNormal : kEvictFirst;
   }();
   args.store_policy = store_policy;
+  // Rasterisation: groups of `group_m` m-panels, m fastest inside a group, then n (tile_to_mn).  A wave of CTAs then covers
+  // few m-panels x several n-tiles: an A panel is fetched from HBM once and its other n-tiles hit L2 (with m fastest over ALL
+  // panels, K = 4608 re-streamed the whole A operand once per n-tile column as soon as it exceeded the L2, and the first wave
+  // of a K = 1152 GEMM pulled every A panel at once).  VQ_GEMM_GROUP_M=0 restores m-fastest order (A/B knob).
+  static const int group_m_env = [] {
+    const char* e = getenv("VQ_GEMM_GROUP_M");
+    return e ? atoi(e) : 8;
+  }();
   const int tile_m = pair ? 2 * BM : BM;
+  const int m_tiles = (M + tile_m - 1) / tile_m;
+  args.group_m = group_m_env <= 0 ? m_tiles : (group_m_env < m_tiles ? group_m_env : m_tiles);
   const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
   const int workers = pair ? num_sms() / 2 : num_sms();
   const int grid = (tiles < workers ? tiles : workers) * (pair ? 2 : 1);
@@ -575,9 +494,12 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
     case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, tr, args, grid, pair, st);
     case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, tr, args, grid, pair, st);
     case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, tr, args, grid, pair, st);
+#ifdef VQ_DEBUG_EPI
     case VQ_EPI_DEBUG_LOADS: return launch_gemm<VQ_EPI_DEBUG_LOADS>(ta, tb, to, tr, args, grid, pair, st);
     case VQ_EPI_DEBUG_MATH: return launch_gemm<VQ_EPI_DEBUG_MATH>(ta, tb, to, tr, args, grid, pair, st);
     case VQ_EPI_DEBUG_STORES: return launch_gemm<VQ_EPI_DEBUG_STORES>(ta, tb, to, tr, args, grid, pair, st);
-    default: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, tr, args, grid, pair, st);
+    case VQ_EPI_DEBUG_MAINLOOP: return launch_gemm<VQ_EPI_DEBUG_MAINLOOP>(ta, tb, to, tr, args, grid, pair, st);
+#endif
+    default: return VQ_ERR_ARG;
   }
 }

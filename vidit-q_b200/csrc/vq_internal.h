@@ -11,7 +11,9 @@
 #include <utility>
 
 namespace vq {
-int num_sms();
+constexpr int kMaxDevices = 64;
+int current_device();   // ordinal of the calling thread's current device, clamped to [0, kMaxDevices)
+int num_sms();          // SM count of the current device
 
 // Programmatic dependent launch (opt-in, VQ_PDL=1): every kernel of this library starts with `griddepcontrol.wait`
 // (nothing before it touches global memory) followed by `griddepcontrol.launch_dependents`, so the next kernel's CTA
@@ -77,4 +79,6 @@ int attn_cross_tc(const void* q, const void* kv, void* out, const int* kv_start,
                   int head_dim, long long kv_rows, float scale, void* stream);
 int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch,
                         uint32_t box_rows);
+// rows x cols fp16 matrix (row pitch ld elements), box 32 rows x 32 columns, SWIZZLE_64B: the epilogue staging sub-tile
+int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
 }  // namespace vq

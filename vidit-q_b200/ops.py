@@ -111,6 +111,7 @@ class PreparedWeight:
     N: int
     K: int
     n_bits: int
+    smooth: Optional[torch.Tensor] = None   # fp16 [K] smooth-quant channel scale folded into the codes (or None)
 
 
 @dataclass
@@ -123,6 +124,7 @@ class ActCodes:
     G: int
     rows: int
     K: int
+    pw: Optional[PreparedWeight] = None   # set by QuantLayer.quantize_input: the weight these codes were scaled for
 
 
 def prep_weight(w, delta, zp, n_bits=8, smooth=None, bias=None) -> PreparedWeight:
@@ -184,6 +186,18 @@ def add_act_quant(x, addv, rows_per_add, n_bits=8, smooth=None) -> ActCodes:
     _lib.check(rc, "vq_add_act_quant")
     _count()
     return a
+
+
+def col_absmax(x, gelu=False):
+    """input.abs().max(dim=-2)[0] of the smooth-quant statistics (quant_layer.py:116,119): x fp16 [G, n, K] -> fp16 [G, K]
+    (exact).  gelu=True: maxima of h(gelu_tanh(x))."""
+    _need_cuda_f16(x, "x")
+    G, n, K = x.shape
+    bits = torch.zeros((G, K), dtype=torch.int32, device=x.device)
+    rc = _lib.lib().vq_col_absmax(_ptr(x), G, n, K, 1 if gelu else 0, _ptr(bits), _stream())
+    _lib.check(rc, "vq_col_absmax")
+    _count()
+    return bits.to(torch.int16).view(torch.float16)
 
 
 def act_quant_static(x, delta, zp, n_bits=8, smooth=None) -> ActCodes:
@@ -264,6 +278,65 @@ def gemm_w8a8(a: ActCodes, w: PreparedWeight, epi=VQ_EPI_BIAS, res=None, gate=No
                                  w.N if ldo is None else ldo, _stream())
     _lib.check(rc, "vq_gemm_w8a8")
     _count()
+    return out
+
+
+_workspaces = {}       # (device index, stream handle) -> uint8 scratch of vq_linear_w8a8's two-launch path
+
+
+def _workspace(nbytes, device):
+    key = (device.index, _stream())
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _workspaces[key] = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+    return buf
+
+
+def linear_launch_count(G, rows, K):
+    """1 when vq_linear_w8a8 runs this shape as the single fused kernel, 2 for quantise pass + GEMM."""
+    return _lib.lib().vq_linear_launch_count(G, rows, K)
+
+
+def linear_w8a8(x, w: PreparedWeight, n_bits=8, smooth=None, ln=None, rows_per_mod=None, epi=VQ_EPI_BIAS, res=None,
+                gate=None, rows_per_gate=0, out=None, ldo=None):
+    """One QuantLayer-family forward in ONE call (vq_linear_w8a8): x fp16 [G, rows, K] (per-token statistics pooled over G)
+    -> dynamic activation quantiser -> INT8 GEMM on the prepared weight -> dequant + epilogue -> fp16 [G*rows, N].
+    ln = (shift, scale): LayerNorm + t2i_modulate in front (rows_per_mod as in ln_modulate_act_quant).  Shapes the fused
+    kernel covers (K = 1152, small M) are a single launch; the rest is quantise pass + GEMM through a cached workspace."""
+    _need_cuda_f16(x, "x")
+    G, rows, K = x.shape
+    if K != w.K:
+        raise _lib.VqError(f"linear_w8a8: K mismatch {K} vs {w.K}")
+    M = G * rows
+    if out is None:
+        out = torch.empty((M, w.N), dtype=torch.float16, device=x.device)
+    shift = scale = None
+    rpm = 0
+    if ln is not None:
+        shift, scale = ln
+        _need_cuda_f16(shift, "shift")
+        _need_cuda_f16(scale, "scale")
+        rpm = rows if rows_per_mod is None else int(rows_per_mod)
+        if shift.numel() != (M // rpm) * K or scale.numel() != shift.numel() or (rpm != rows and G != 1):
+            raise _lib.VqError(f"linear_w8a8: shift/scale of {shift.numel()} elements do not match G={G} rows={rows} "
+                               f"rows_per_mod={rpm} K={K}")
+    if smooth is not None:
+        _need_cuda_f16(smooth, "smooth")
+    if epi == VQ_EPI_GATE_RESIDUAL:
+        _need_cuda_f16(res, "res")
+        _need_cuda_f16(gate, "gate")
+    L = _lib.lib()
+    n_launch = L.vq_linear_launch_count(G, rows, K)
+    ws, ws_bytes = None, 0
+    if n_launch != 1:
+        ws_bytes = L.vq_linear_workspace_bytes(G, rows, K)
+        ws = _workspace(ws_bytes, x.device)
+    rc = L.vq_linear_w8a8(_ptr(x), G, rows, K, _ptr(smooth), _ptr(shift), _ptr(scale), rpm, n_bits, _ptr(w.codes),
+                          _ptr(w.col), w.N, epi, _ptr(res), w.N, _ptr(gate), rows_per_gate, _ptr(out),
+                          w.N if ldo is None else ldo, None, None, _ptr(ws), ws_bytes, _ptr(status_word(x.device)),
+                          _stream())
+    _lib.check(rc, "vq_linear_w8a8")
+    _count(n_launch)
     return out
 
 

@@ -156,6 +156,28 @@ class PixArtMS(nn.Module):
     def forward_with_dpmsolver(self, x, timestep, y, data_info=None, **kwargs):
         return self.forward(x, timestep, y, data_info=data_info, **kwargs).chunk(2, dim=1)[0]
 
+    def check_fused_state(self):
+        """The fused schedule hard-wires dynamic per-token W+A quantisation of the 7 block linears (w8a8.yaml); LN-fused
+        quantisers (qkv, fc1) cannot take smooth-quant scales.  Checked on every call; anything else -> forward()."""
+        from .qdiff import QuantLayer, _is_dynamic
+        for i, blk in enumerate(self.blocks):
+            for path in ("attn.qkv", "attn.proj", "cross_attn.q_linear", "cross_attn.kv_linear", "cross_attn.proj",
+                         "mlp.fc1", "mlp.fc2"):
+                l = blk.get_submodule(path)
+                if not (isinstance(l, QuantLayer) and l.weight_quant and l.act_quant and not l.disable_act_quant
+                        and _is_dynamic(l.act_quantizer) and l.act_quantizer.per_group == "token"):
+                    raise NotImplementedError(f"forward_fused: blocks.{i}.{path} is not dynamic per-token W+A quantised; "
+                                              "use forward()")
+                if path in ("attn.qkv", "mlp.fc1") and l.smooth_mode() is not None:
+                    raise NotImplementedError(f"forward_fused: smooth-quant on the LN-fused blocks.{i}.{path}; use forward()")
+
+    @staticmethod
+    def _linear(layer, x, **kw):
+        """One quantised linear of the fused schedule through vq_linear_w8a8 (pooled per-token statistics, quirk Q1)."""
+        pw = layer._weight_for(x)
+        x3 = x if x.dim() == 3 else x.reshape(1, -1, x.shape[-1])
+        return ops.linear_w8a8(x3.contiguous(), pw, n_bits=layer.act_quantizer.n_bits, smooth=getattr(pw, "smooth", None), **kw)
+
     def forward_fused(self, x, timestep, y, mask=None, plan=None, segments=None):
         x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan, fused=True)
         if segments is None:
@@ -166,31 +188,33 @@ class PixArtMS(nn.Module):
         x = x.contiguous()
         xr = x.view(M, C)
         ones = torch.ones(1, C, dtype=x.dtype, device=x.device)
+        self.check_fused_state()
         for blk in self.blocks:
             shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = (
                 v.reshape(B, C).contiguous() for v in blk.modulation(t0))
             nb = blk.attn.qkv.act_quantizer.n_bits
-            a, _ = ops.ln_modulate_act_quant(x, shift_msa, scale_msa, n_bits=nb)
-            qkv = ops.gemm_w8a8(a, blk.attn.qkv.prepared_weight())
+            # every K = 1152 linear is ONE call (vq_linear_w8a8): at M = 2048 a single fused kernel each — LayerNorm +
+            # modulate + quantise in the producer warps, dequant + bias / gated residual in the epilogue
+            qkv = ops.linear_w8a8(x, blk.attn.qkv.prepared_weight(), n_bits=nb, ln=(shift_msa, scale_msa))
             if ops.attn_spatial_supported(N, D):   # tcgen05 flash attention, q|k|v read in place (one sequence per image)
                 o = ops.attn_spatial(qkv, B, N, H, D, D ** -0.5).view(B, N, C)
             else:
                 o = AttentionImg.attend(qkv, B, N, H, D)
-            ops.gemm_w8a8(blk.attn.proj.quantize_input(o), blk.attn.proj.prepared_weight(),
-                          epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
+            self._linear(blk.attn.proj, o, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
             ca = blk.cross_attn
-            q = ops.gemm_w8a8(ca.q_linear.quantize_input(x), ca.q_linear.prepared_weight())
-            kv = ops.gemm_w8a8(ca.kv_linear.quantize_input(y), ca.kv_linear.prepared_weight())
+            q = self._linear(ca.q_linear, x)
+            kv = self._linear(ca.kv_linear, y)
             if D == 72 and max(y_lens) <= 128:
                 o = ops.attn_cross(q, kv, segments[0], segments[1], B, N, H, D, max(y_lens), D ** -0.5).view(B, N, C)
             else:
                 o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
-            ops.gemm_w8a8(ca.proj.quantize_input(o), ca.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr,
-                          gate=ones, rows_per_gate=M, out=xr)
-            a, _ = ops.ln_modulate_act_quant(x, shift_mlp, scale_mlp, n_bits=nb)
-            h = ops.gemm_w8a8(a, blk.mlp.fc1.prepared_weight()).view(B, N, -1)   # GELU fused into fc2's quantise pass
-            ops.gemm_w8a8(blk.mlp.fc2.quantize_input(h, gelu=True), blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL,
-                          res=xr, gate=gate_mlp, rows_per_gate=N, out=xr)
+            self._linear(ca.proj, o, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=ones, rows_per_gate=M, out=xr)
+            h = ops.linear_w8a8(x, blk.mlp.fc1.prepared_weight(), n_bits=nb, ln=(shift_mlp, scale_mlp)).view(B, N, -1)
+            # GELU rides in fc2's quantise pass (K = 4608: quantise pass + GEMM).  fc2 goes through its own
+            # quantize_input: the running-stat smooth-quant EMA of quirk Q17 (PixArt keeps it on for blocks.27.mlp.fc2
+            # at inference) sees gelu(h) there and re-quantises the weight for this call
+            a = blk.mlp.fc2.quantize_input(h, gelu=True)
+            ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp, rows_per_gate=N, out=xr)
         return self.unpatchify(self.final_layer(x, t))
 
 

@@ -95,6 +95,11 @@ class DynamicActQuantizer(ActQuantizer):
     pass
 
 
+def _is_dynamic(aq):
+    """DynamicActQuantizer of this module OR of the reference (accelerate() shares the reference's quantiser objects)."""
+    return isinstance(aq, DynamicActQuantizer) or type(aq).__name__ == "DynamicActQuantizer"
+
+
 class StraightThrough(nn.Module):
     def forward(self, x):
         return x
@@ -149,6 +154,8 @@ class QuantLayer(nn.Module):
             self.smooth_quant_alpha = _cfg_get(sq, "alpha", None)
             self.smooth_quant_running_stat = False
         self._prepared = {}  # (n_bits, timerange_id) -> ops.PreparedWeight
+        self._gen = 0        # bumped whenever cached weight codes become stale (model-level caches key on it)
+        self._wmax_pow = {}  # alpha -> (weight data_ptr, max_n |W|^(1-alpha)) for the smooth-quant channel scale
 
     # -- state -----------------------------------------------------------------------------------------------------
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
@@ -161,9 +168,13 @@ class QuantLayer(nn.Module):
     def invalidate_prepared(self):
         """Drop cached u8 weight codes (call after changing weights or weight-quantiser buffers)."""
         self._prepared.clear()
+        self._wmax_pow.clear()
+        self._gen += 1
 
     def _apply(self, fn, *a, **k):  # .cuda()/.half() move the source tensors: prepared codes are stale
         self._prepared = {}
+        self._wmax_pow = {}
+        self._gen = getattr(self, "_gen", 0) + 1
         return super()._apply(fn, *a, **k)
 
     # -- helpers ---------------------------------------------------------------------------------------------------
@@ -172,36 +183,106 @@ class QuantLayer(nn.Module):
             return 0
         return find_interval(self.timerange, self.cur_timestep_id)
 
-    def channel_wise_scale(self, tr_id):
-        """quant_layer.py:137: act_scale[tr]^alpha / max_n |W|^(1-alpha), evaluated with torch half ops exactly as the
-        reference does (load-time work, cached per timerange)."""
-        if "momentum" not in self.channel_wise_scale_type:
-            raise NotImplementedError("smooth-quant channel_wise_scale_type 'dynamic' (input-dependent) is not fused")
-        if getattr(self, "smooth_quant_running_stat", False):
-            raise NotImplementedError("smooth_quant_running_stat=True is a calibration-time mode")
+    def _alpha(self, tr_id):
         alpha = self.smooth_quant_alpha
         if isinstance(alpha, (list, tuple)) or type(alpha).__name__ == "ListConfig":
             alpha = alpha[tr_id]
+        return alpha
+
+    def _weight_colmax_pow(self, alpha):
+        """max_n |W[n, k]|^(1 - alpha) of quant_layer.py:116,137 — a function of the weight only: evaluated once (torch
+        half ops, as the reference evaluates it every call)."""
+        w = self.weight
+        hit = self._wmax_pow.get(alpha)
+        if hit is None or hit[0] != (w.data_ptr(), w.dtype):
+            hit = ((w.data_ptr(), w.dtype), w.abs().max(dim=0)[0].pow(1 - alpha))
+            self._wmax_pow[alpha] = hit
+        return hit[1]
+
+    def smooth_mode(self):
+        """None | 'cached' (momentum scale from the checkpoint's act_scale: a constant per timerange) | 'dynamic'
+        (quant_layer.py:115-116: from the live input) | 'running' (quant_layer.py:118-126 with
+        smooth_quant_running_stat=True: the act_scale EMA advances on every call — quirk Q17, what
+        t2i/scripts/quant_txt2img.py:297-300 leaves switched on for blocks.27.mlp.fc2 at inference)."""
+        if not self.smooth_quant:
+            return None
+        kind = self.channel_wise_scale_type
+        if kind == "dynamic":
+            return "dynamic"
+        if "momentum" in kind:
+            return "running" if getattr(self, "smooth_quant_running_stat", False) else "cached"
+        raise NotImplementedError(f"smooth-quant channel_wise_scale_type {kind!r}")
+
+    def channel_wise_scale(self, tr_id):
+        """quant_layer.py:137: act_scale[tr]^alpha / max_n |W|^(1-alpha), evaluated with torch half ops exactly as the
+        reference does (a constant per timerange once the checkpoint is loaded; cached with the prepared weight)."""
+        if "momentum" not in self.channel_wise_scale_type:
+            raise NotImplementedError("channel_wise_scale(tr) is the checkpoint-constant (momentum) scale; the 'dynamic' "
+                                      "type depends on the input: live_channel_scale(input)")
+        alpha = self._alpha(tr_id)
         act_scale = self.act_quantizer.act_scale[tr_id]
-        s = act_scale.pow(alpha) / self.weight.abs().max(dim=0)[0].pow(1 - alpha)
+        s = act_scale.pow(alpha) / self._weight_colmax_pow(alpha)
         return s.reshape(-1).contiguous()
 
-    def prepared_weight(self):
+    def _update_running_act_scale(self, cur_act_scale, tr_id):
+        """quant_layer.py:119-126 / :146-153: EMA of the per-channel |x| maxima, in the tensor's own dtype.  The
+        reference's `act_scale[tr].abs().mean() == 0` first-call test is a host sync; here both outcomes are computed on
+        the device and selected there, so the update can live inside a captured CUDA graph."""
+        aq = self.act_quantizer
+        if aq.act_scale is None:
+            aq.act_scale = torch.zeros([self.timerange_num, *cur_act_scale.shape]).to(cur_act_scale)
+        old = aq.act_scale[tr_id]
+        m = self.smooth_quant_momentum
+        ema = old * m + cur_act_scale * (1 - m)
+        aq.act_scale[tr_id] = torch.where(old.abs().mean() == 0, cur_act_scale, ema)
+
+    def live_channel_scale(self, input, gelu=False):
+        """Channel scale of the two input-dependent smooth-quant modes, [K] fp16.  The per-channel |x| maxima come from
+        vq_col_absmax (one pass, exact); the [G, K] -> [K] arithmetic behind it is the reference's, op for op, on tiny
+        tensors.  gelu=True: `input` is the pre-activation and the statistics are those of gelu_tanh(input)."""
+        tr = self._timerange_id()
+        alpha = self._alpha(tr)
+        x3 = input if input.dim() == 3 else input.reshape(1, -1, input.shape[-1])
+        colmax = ops.col_absmax(x3, gelu=gelu)                          # input.abs().max(dim=-2)[0]  -> [G, K]
+        if self.smooth_mode() == "dynamic":
+            s = colmax.pow(alpha).mean(dim=0, keepdim=True) / self._weight_colmax_pow(alpha)
+        else:
+            self._update_running_act_scale(colmax.mean(dim=0, keepdim=True), tr)
+            s = self.act_quantizer.act_scale[tr].pow(alpha) / self._weight_colmax_pow(alpha)
+        return s.reshape(-1).contiguous()
+
+    def _weight_src_key(self):
+        wq = self.weight_quantizer
+        d = wq.delta
+        return (self.weight.data_ptr(), self.weight.dtype, None if d is None else (d.data_ptr(), d._version, d.dtype))
+
+    def prepared_weight(self, live_smooth=None):
+        """u8 weight codes + per-channel records of the current (n_bits, timerange).  Cached unless `live_smooth` (the
+        input-dependent channel scale of this very call) is given: then the weight is re-quantised now, which is what
+        the reference does on every call anyway (quant_layer.py:178-185)."""
         wq = self.weight_quantizer
         tr = self._timerange_id() if self.smooth_quant else 0
         key = (wq.n_bits, tr)
-        pw = self._prepared.get(key)
-        if pw is None:
-            if wq.delta is None or not wq.init_done:
-                raise RuntimeError("weight quantiser has no parameters: load a PTQ ckpt (load_quant_params) or run "
-                                   "QuantModel.init_weight_quant_params() first")
-            if wq.sym or wq.per_group != "channel" or wq.n_bits > 8:
-                raise NotImplementedError("fused path supports asymmetric per-output-channel weights, <= 8 bits")
-            smooth = self.channel_wise_scale(tr) if self.smooth_quant else None
-            pw = ops.prep_weight(self.weight.data, wq.delta, wq.zero_point, n_bits=wq.n_bits, smooth=smooth,
-                                 bias=None if self.bias is None else self.bias.data)
-            pw.smooth = smooth
-            self._prepared[key] = pw
+        src = self._weight_src_key()
+        hit = None if live_smooth is not None else self._prepared.get(key)
+        if hit is not None and hit[0] == src:
+            return hit[1]
+        if wq.delta is None or not wq.init_done:
+            raise RuntimeError("weight quantiser has no parameters: load a PTQ ckpt (load_quant_params) or run "
+                               "QuantModel.init_weight_quant_params() first")
+        if wq.sym or wq.per_group != "channel" or wq.n_bits > 8:
+            raise NotImplementedError("fused path supports asymmetric per-output-channel weights, <= 8 bits")
+        if live_smooth is not None:
+            smooth = live_smooth
+        else:
+            smooth = self.channel_wise_scale(tr) if self.smooth_mode() == "cached" else None
+        pw = ops.prep_weight(self.weight.data, wq.delta, wq.zero_point, n_bits=wq.n_bits, smooth=smooth,
+                             bias=None if self.bias is None else self.bias.data)
+        pw.smooth = smooth
+        if live_smooth is None:
+            if hit is not None:      # the source tensors changed under a cached entry (reload / .to()): stale everywhere
+                self._gen += 1
+            self._prepared[key] = (src, pw)
         return pw
 
     def _pool_view(self, input):
@@ -212,7 +293,7 @@ class QuantLayer(nn.Module):
         aq = self.act_quantizer
         if aq.sym or aq.n_bits > 8:
             raise NotImplementedError("fused path supports asymmetric activations of <= 8 bits")
-        if isinstance(aq, DynamicActQuantizer):
+        if _is_dynamic(aq):
             if aq.per_group != "token":
                 raise NotImplementedError("dynamic activation quantisation is per-token (the ViDiT-Q W8A8 / W4A8 configs)")
         elif aq.per_group not in (False, None, "token") or aq.delta is None or not aq.init_done:
@@ -227,14 +308,26 @@ class QuantLayer(nn.Module):
         return (aq.delta.reshape(-1).to(dev, torch.float16).contiguous(),
                 aq.zero_point.reshape(-1).to(dev, torch.float16).contiguous())
 
+    def _weight_for(self, input, gelu=False, independent=False):
+        """The prepared weight of THIS call: cached, or re-quantised under the input-dependent smooth-quant scale."""
+        if self.smooth_mode() in ("dynamic", "running"):
+            if independent:
+                raise NotImplementedError("input-dependent smooth-quant scales with stacked independent calls (the EMA / "
+                                          "batch mean would mix the calls)")
+            return self.prepared_weight(live_smooth=self.live_channel_scale(input, gelu=gelu))
+        return self.prepared_weight()
+
     def quantize_input(self, input, gelu=False, independent=False):
-        """Per-token dynamic activation quantisation of a [*, n, C] fp16 tensor -> ops.ActCodes.
+        """Activation quantisation of a [*, n, C] fp16 tensor -> ops.ActCodes, with `.pw` = the prepared weight the codes
+        belong to (the cached one, or — for the input-dependent smooth-quant modes — the one re-quantised for this call).
         gelu=True: `input` is the pre-activation of the preceding nn.GELU(approximate="tanh"); the activation is applied
         inside the quantise pass (fused schedules only — the module graph applies GELU itself).
         independent=True: the batch entries are separate forward calls stacked along the batch (cfg_split's cond / uncond
         halves at one prompt each): nothing is pooled, every row gets its own statistics."""
         self._check_act_quantizer()
-        if not isinstance(self.act_quantizer, DynamicActQuantizer):
+        pw = self._weight_for(input, gelu, independent)
+        smooth = getattr(pw, "smooth", None)
+        if not _is_dynamic(self.act_quantizer):
             # static scales (base_quantizer.py:112-144 with init_done): nothing is computed from the live tensor
             if gelu:
                 raise NotImplementedError("GELU fused into a static-scale quantise pass")
@@ -244,25 +337,41 @@ class QuantLayer(nn.Module):
                 G, rows = self._pool_view(input)
                 if rows != delta.numel():
                     raise NotImplementedError(f"static per-token scales for {delta.numel()} tokens, input has {rows}")
-            return ops.act_quant_static(x, delta, zp, n_bits=self.act_quantizer.n_bits,
-                                        smooth=getattr(self.prepared_weight(), "smooth", None))
-        G, rows = self._pool_view(input)
-        if independent:
-            G, rows = 1, G * rows
-        x = input.reshape(G, rows, input.shape[-1])
-        if not x.is_contiguous():
-            x = x.contiguous()
-        pw = self.prepared_weight()
-        return ops.act_quant(x, n_bits=self.act_quantizer.n_bits, smooth=getattr(pw, "smooth", None), gelu=gelu)
+            a = ops.act_quant_static(x, delta, zp, n_bits=self.act_quantizer.n_bits, smooth=smooth)
+        else:
+            G, rows = self._pool_view(input)
+            if independent:
+                G, rows = 1, G * rows
+            x = input.reshape(G, rows, input.shape[-1])
+            if not x.is_contiguous():
+                x = x.contiguous()
+            a = ops.act_quant(x, n_bits=self.act_quantizer.n_bits, smooth=smooth, gelu=gelu)
+        a.pw = pw
+        return a
 
     # -- forward ---------------------------------------------------------------------------------------------------
     def forward(self, input: torch.Tensor, scale: float = 1.0, split: int = 0, smooth_quant_enable: bool = False):
         if split != 0 or self.split != 0:
             raise NotImplementedError("split quantisation (UNet skip-concat) does not occur in STDiT/PixArt")
         act_q = self.act_quant and not self.disable_act_quant
+        if (not self.smooth_quant and getattr(self, "smooth_quant_running_stat", False)
+                and "momentum" in getattr(self, "channel_wise_scale_type", "")):
+            # quant_layer.py:141-153: statistics collection without scaling (calibration-time; kept for API parity)
+            x3 = input if input.dim() == 3 else input.reshape(1, -1, input.shape[-1])
+            self._update_running_act_scale(ops.col_absmax(x3).mean(dim=0, keepdim=True), self._timerange_id())
         if self.weight_quant and act_q:
-            a = self.quantize_input(input)
-            out = ops.gemm_w8a8(a, self.prepared_weight())
+            if _is_dynamic(self.act_quantizer):
+                # the whole QuantLayer forward as ONE call (vq_linear_w8a8): a single fused kernel where the shape allows
+                self._check_act_quantizer()
+                pw = self._weight_for(input)
+                G, rows = self._pool_view(input)
+                x = input.reshape(G, rows, input.shape[-1])
+                if not x.is_contiguous():
+                    x = x.contiguous()
+                out = ops.linear_w8a8(x, pw, n_bits=self.act_quantizer.n_bits, smooth=getattr(pw, "smooth", None))
+            else:
+                a = self.quantize_input(input)
+                out = ops.gemm_w8a8(a, a.pw)
             return out.view(*input.shape[:-1], self.out_features)
         if not self.weight_quant and not act_q:
             if self.smooth_quant:
@@ -563,10 +672,23 @@ def load_quant_params(qnn, ckpt_path, dtype=torch.float32):
     qnn.set_quant_params_dict(ckpt, dtype=dtype)
 
 
+_LAYER_STATE = ("weight_quant", "act_quant", "disable_act_quant", "cur_timestep_id", "smooth_quant",
+                "smooth_quant_running_stat", "smooth_quant_alpha", "smooth_quant_momentum", "channel_wise_scale_type",
+                "timerange", "timerange_num", "split")
+
+
 def accelerate(qnn):
-    """Swap the forward of every *reference* QuantLayer inside `qnn` (an unmodified qdiff QuantModel, after
-    load_quant_params / .cuda() / .to(fp16)) for the fused kernels, in place. The reference module objects, their
-    quantiser buffers and all QuantModel methods stay as they are."""
+    """Swap the forward of every *reference* QuantLayer inside `qnn` (an unmodified qdiff QuantModel) for the fused
+    kernels, in place.  The reference module objects and all QuantModel methods stay as they are.
+
+    The twin layer built here owns nothing: it wraps the same `org_module` (weights), holds the reference layer's OWN
+    quantiser objects (so load_quant_params / set_quant_params_dict / load_bitwidth_config / set_quant_init_done keep
+    acting on the state the kernels read, whether they run before or after accelerate()), and copies the layer-level
+    switches the QuantModel API flips (set_quant_state, set_layer_quant, set_smooth_quant, set_layer_smooth_quant,
+    timestep propagation) from the reference layer at the top of every call.  Prepared u8 weight codes are cached per
+    (n_bits, timerange) and re-validated against the weight / delta tensors they were made from, so .cuda(), .half() and
+    a checkpoint reload after accelerate() are picked up.  The running-stat smooth-quant EMA (quirk Q17) writes the
+    reference quantiser's own `act_scale` buffer."""
     mapping = {"QuantLayer": QuantLayer, "QuantSpatialAttnLinear": QuantSpatialAttnLinear,
                "QuantTemporalAttnLinear": QuantTemporalAttnLinear, "QuantCrossAttnLinear": QuantCrossAttnLinear,
                "QuantAttnLinearImg": QuantAttnLinearImg, "QuantCrossAttnLinearImg": QuantCrossAttnLinearImg}
@@ -575,21 +697,20 @@ def accelerate(qnn):
         cls = mapping.get(type(mod).__name__)
         if cls is None or isinstance(mod, QuantLayer) or not hasattr(mod, "weight_quantizer"):
             continue
+        if not isinstance(mod.org_module, nn.Linear):
+            continue        # Conv QuantLayers (PixArt's x_embedder) stay on the reference path: FP list in every script
         ours = cls(mod.org_module, mod.weight_quant_params, mod.act_quant_params)
+        # share the reference's quantiser objects (plain attribute entries: no second registration as sub-modules)
         for qname in ("weight_quantizer", "act_quantizer"):
-            src, dst = getattr(mod, qname), getattr(ours, qname)
-            for bname, val in src._buffers.items():
-                setattr(dst, bname, val)
-            dst.n_bits, dst.bit_idx, dst.init_done = src.n_bits, src.bit_idx, src.init_done
-        ours.weight_quant, ours.act_quant = mod.weight_quant, mod.act_quant
-        ours.smooth_quant = getattr(mod, "smooth_quant", False)
+            ours._modules.pop(qname, None)
+            object.__setattr__(ours, qname, getattr(mod, qname))
 
         def fwd(input, scale=1.0, split=0, _ours=ours, _ref=mod, **kw):
-            _ours.cur_timestep_id = getattr(_ref, "cur_timestep_id", 0)
-            _ours.weight_quant, _ours.act_quant = _ref.weight_quant, _ref.act_quant
-            _ours.weight_quantizer.n_bits = _ref.weight_quantizer.n_bits
-            return _ours(input)
+            for name in _LAYER_STATE:
+                if hasattr(_ref, name):
+                    object.__setattr__(_ours, name, getattr(_ref, name))
+            return _ours(input, scale, split)
         mod.forward = fwd
-        mod._viditq_b200 = ours
+        object.__setattr__(mod, "_viditq_b200", ours)   # not a sub-module of the reference model (state_dict unchanged)
         n += 1
     return n

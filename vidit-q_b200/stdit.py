@@ -271,18 +271,26 @@ class STDiT(nn.Module):
         t = self.t_embedder(timestep, dtype=x.dtype)
         t0 = self.t_block(t)
         y = self.y_embedder(y)
+        aq = getattr(self.final_layer.linear, "act_quantizer", None)
+        mask_select = not (aq is not None and type(aq).__name__ != "DynamicActQuantizer" and aq.per_group == "token")
+        if not mask_select and (fused or plan is not None):
+            # static per-token scales are calibrated per position of each layer's own (pooled) view — the temporal
+            # layers' in (S T) order — which the fused schedule's in-place (T S) layout does not reproduce
+            raise NotImplementedError("static per-token activation scales (MASK_SELECT=False, quirk Q14): use forward()")
         if plan is not None:
             y_index, y_lens = plan
             y = y.squeeze(1).reshape(-1, C).index_select(0, y_index).view(1, -1, C)
-        elif mask is not None:  # MASK_SELECT branch of stdit.py:280-286 (dynamic activation quantiser)
-            aq = getattr(self.final_layer.linear, "act_quantizer", None)
-            if aq is not None and type(aq).__name__ != "DynamicActQuantizer" and aq.per_group == "token":
-                raise NotImplementedError("static per-token activation quantisation (MASK_SELECT=False, quirk Q14)")
+        elif mask is not None and mask_select:  # MASK_SELECT branch of stdit.py:280-286 (dynamic activation quantiser)
             if mask.shape[0] != y.shape[0]:
                 mask = mask.repeat(y.shape[0] // mask.shape[0], 1)
             mask = mask.squeeze(1).squeeze(1)
             y = y.squeeze(1).masked_select(mask.unsqueeze(-1) != 0).view(1, -1, C)
             y_lens = mask.sum(dim=1).tolist()
+        elif mask is not None:   # MASK_SELECT = False (stdit.py:287-300, quirk Q14): padded prompt rows are zeroed, not
+            # dropped, so every static per-token (delta, zp) keeps its position: always max_len rows per sample
+            mask_ = mask.repeat(y.shape[0] // mask.shape[0], 1) if mask.shape[0] != y.shape[0] else mask
+            y_lens = [y.shape[2]] * y.shape[0]
+            y = (y * mask_.unsqueeze(-1).unsqueeze(1).to(y.dtype)).squeeze(1).reshape(1, -1, C)
         else:
             y_lens = [y.shape[2]] * y.shape[0]
             y = y.squeeze(1).reshape(1, -1, C)
@@ -351,29 +359,51 @@ class FusedBlocks:
                                            qkv[:, :, 2].transpose(1, 2), scale=scale)   # [B*T, H, S, D]
         if o.is_contiguous() and D == 72 and C == 1152 and not pj.smooth_quant:
             # quantise straight from the head-major layout the library kernel emits (no transpose copy)
-            return (ops.act_quant_heads(o, 1, B * N, S, n_bits=pj.act_quantizer.n_bits) if independent
-                    else ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits))
+            a = (ops.act_quant_heads(o, 1, B * N, S, n_bits=pj.act_quantizer.n_bits) if independent
+                 else ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits))
+            a.pw = pj.prepared_weight()
+            return a
         return pj.quantize_input(o.transpose(1, 2).reshape(B * T, S, C), independent=independent)
 
-    @staticmethod
-    def _cat_prepared(layers):
-        pws = [l.prepared_weight() for l in layers]
-        codes = torch.cat([p.codes for p in pws], 0).contiguous()
-        col = torch.cat([p.col for p in pws], 0).contiguous()
-        return ops.PreparedWeight(codes, col, codes.shape[0], pws[0].K, pws[0].n_bits)
+    LN_FUSED = ("attn.q", "attn.k", "attn.v", "attn_temp.q", "attn_temp.k", "attn_temp.v", "mlp.fc1")
+
+    def check_state(self):
+        """The fused schedule hard-wires per-token DYNAMIC W+A quantisation of all 13 block linears (the ViDiT-Q W8A8 /
+        W4A8 configs).  Anything else — a layer switched to FP by set_layer_quant, static (calibrated) activation scales
+        of w8a8_naive.yaml, input-dependent smooth-quant scales in front of an LN-fused quantiser, q/k/v with different
+        activation widths — must go through STDiT.forward (one QuantLayer call per linear); checked on EVERY call."""
+        from .qdiff import _is_dynamic
+        for i, blk in enumerate(self.m.blocks):
+            for path in ("attn.q", "attn.k", "attn.v", "attn.proj", "attn_temp.q", "attn_temp.k", "attn_temp.v",
+                         "attn_temp.proj", "cross_attn.q_linear", "cross_attn.kv_linear", "cross_attn.proj", "mlp.fc1",
+                         "mlp.fc2"):
+                l = blk.get_submodule(path)
+                if not (isinstance(l, QuantLayer) and l.weight_quant and l.act_quant and not l.disable_act_quant):
+                    raise NotImplementedError(f"forward_fused: blocks.{i}.{path} is not in W+A quantised state; use forward()")
+                aq = l.act_quantizer
+                if not _is_dynamic(aq) or aq.per_group != "token":
+                    raise NotImplementedError(f"forward_fused: blocks.{i}.{path} has static / non-per-token activation "
+                                              "scales (w8a8_naive.yaml family); use forward()")
+                if path in self.LN_FUSED and l.smooth_mode() in ("dynamic", "running"):
+                    raise NotImplementedError(f"forward_fused: blocks.{i}.{path} uses an input-dependent smooth-quant scale "
+                                              "in front of a fused LayerNorm / add quantiser; use forward()")
+            for att in (blk.attn, blk.attn_temp):
+                if len({att.q.act_quantizer.n_bits, att.k.act_quantizer.n_bits, att.v.act_quantizer.n_bits}) != 1:
+                    raise NotImplementedError(f"forward_fused: blocks.{i} q/k/v activation widths differ (shared quantise "
+                                              "pass); use forward()")
 
     def _qkv_weight(self, attn, tag):
         layers = (attn.q, attn.k, attn.v)
-        key = (tag,) + tuple((l.weight_quantizer.n_bits, l._timerange_id() if l.smooth_quant else 0) for l in layers)
-        pw = self._qkv.get(key)
-        if pw is None:
-            for l in layers:
-                if not (isinstance(l, QuantLayer) and l.weight_quant and l.act_quant):
-                    raise NotImplementedError("forward_fused needs every block linear in W+A quantised state")
-            if any(l.smooth_quant for l in layers):
-                return None   # per-layer channel scales (quant_layer.py:137 depends on each weight): no shared input codes
-            pw = self._qkv[key] = self._cat_prepared(layers)
-        return pw
+        if any(l.smooth_quant for l in layers):
+            return None   # per-layer channel scales (quant_layer.py:137 depends on each weight): no shared input codes
+        pws = [l.prepared_weight() for l in layers]   # validates each layer's cache (bumps _gen when its source moved)
+        key = (tag,) + tuple((l.weight_quantizer.n_bits, l._gen) for l in layers)
+        hit = self._qkv.get(tag)
+        if hit is None or hit[0] != key:
+            codes = torch.cat([p.codes for p in pws], 0).contiguous()
+            col = torch.cat([p.col for p in pws], 0).contiguous()
+            hit = self._qkv[tag] = (key, ops.PreparedWeight(codes, col, codes.shape[0], pws[0].K, pws[0].n_bits))
+        return hit[1]
 
     def _qkv_project(self, attn, tag, x, ln=None, independent=False, add=None):
         """q|k|v of one attention as one [M, 3C] tensor. ln = (shift, scale) fuses LayerNorm+modulate in front.
@@ -411,6 +441,7 @@ class FusedBlocks:
 
     def run(self, x, y, t0, y_lens, segments, independent=False, frames=None):
         m = self.m
+        self.check_state()
         B, N, C = x.shape
         S, H = m.num_spatial, m.num_heads
         T = N // S                       # frames held by this rank (all of them unless frame-sharded)
@@ -433,7 +464,9 @@ class FusedBlocks:
                 return layer.quantize_input(t, gelu=gelu, independent=independent)
             if layer.smooth_quant:
                 raise NotImplementedError("frame sharding with smooth-quant channel scales")
-            return ops.act_quant(t.reshape(1, -1, t.shape[-1]), n_bits=layer.act_quantizer.n_bits, gelu=gelu)
+            a_ = ops.act_quant(t.reshape(1, -1, t.shape[-1]), n_bits=layer.act_quantizer.n_bits, gelu=gelu)
+            a_.pw = layer.prepared_weight()
+            return a_
         x = x.contiguous()   # fresh tensor from embed(): the residual stream is updated in place below
         ones = torch.ones(1, C, dtype=x.dtype, device=x.device)
         tpe = m.pos_embed_temporal.to(x.dtype)
@@ -452,8 +485,7 @@ class FusedBlocks:
             else:
                 a = self._spatial_library(qkv.view(B * T, S, 3, H, D), pj, blk.attn.scale, B, N, T, S, C, D, independent)
             xr = x.view(M, C)   # residual stream, updated in place: out aliases res -> TMA reduce-add epilogue
-            ops.gemm_w8a8(a, blk.attn.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
-                          rows_per_gate=N, out=xr)
+            ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
             if frames is not None:
                 # frame-sharded: quantise locally, all-to-all the CODES into the (all frames, S / P positions) layout,
@@ -470,8 +502,8 @@ class FusedBlocks:
                 o = ops.attn_temporal(qkv, B, T * P, S // P, H, D, blk.attn_temp.scale)
                 a = ops.act_quant(o.view(1, -1, C), n_bits=blk.attn_temp.proj.act_quantizer.n_bits)
                 a = shard.exchange_act_codes(a, B, T, S, P, False, grp)
-                ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
-                              rows_per_gate=N, out=xr)
+                ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr,
+                              gate=gate_msa, rows_per_gate=N, out=xr)
             elif i == 0 and C == 1152:   # x + tpe rides in the quantise pass (vq_add_act_quant): frame t = (row // S) % T
                 qkv = self._qkv_project(blk.attn_temp, (i, "t"), x, independent=independent, add=(tpe.view(T, C), S))
             else:
@@ -487,18 +519,19 @@ class FusedBlocks:
                     o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
                 # per-token statistics: row order irrelevant
                 a = blk.attn_temp.proj.quantize_input(o.view(B * S, T, C), independent=independent)
-                ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
-                              rows_per_gate=N, out=xr)
+                ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
             # ---- cross attention
             ca = blk.cross_attn
-            q = ops.gemm_w8a8(qi(ca.q_linear, x), ca.q_linear.prepared_weight())
-            kv = ops.gemm_w8a8(ca.kv_linear.quantize_input(y), ca.kv_linear.prepared_weight())
+            a = qi(ca.q_linear, x)
+            q = ops.gemm_w8a8(a, a.pw)
+            a = ca.kv_linear.quantize_input(y)
+            kv = ops.gemm_w8a8(a, a.pw)
             if D == 72 and max(y_lens) <= 128:
                 o = ops.attn_cross(q, kv, segments[0], segments[1], B, N, H, D, max(y_lens), D ** -0.5).view(B, N, C)
             else:
                 o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
-            ops.gemm_w8a8(qi(ca.proj, o), ca.proj.prepared_weight(),
-                          epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=ones, rows_per_gate=M, out=xr)
+            a = qi(ca.proj, o)
+            ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=ones, rows_per_gate=M, out=xr)
             # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
             fc1w = blk.mlp.fc1.prepared_weight()
             a, _ = ops.ln_modulate_act_quant(x.view(1, M, C) if independent else x, shift_mlp, scale_mlp,
@@ -507,6 +540,5 @@ class FusedBlocks:
             # GELU rides in fc2's quantise pass (HBM-bound, idle MUFU) instead of fc1's epilogue (epilogue-bound)
             h = ops.gemm_w8a8(a, fc1w).view(B, N, -1)
             a = qi(blk.mlp.fc2, h, gelu=True)
-            ops.gemm_w8a8(a, blk.mlp.fc2.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp,
-                          rows_per_gate=N, out=xr)
+            ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp, rows_per_gate=N, out=xr)
         return x
