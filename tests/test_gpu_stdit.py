@@ -134,7 +134,7 @@ def test_w8a8_end_to_end_is_inside_the_simulation_noise_band(qnn_gpu, small):  #
     n0 = ops.launch_count()
     with torch.no_grad():
         out = qnn(x, t, y, mask=mask).cpu().numpy()
-    assert ops.launch_count() - n0 >= 2 * 13 * 2      # act-quant + GEMM per quantised linear: our kernels ran
+    assert ops.launch_count() - n0 >= 13 * 2          # >= one own launch per quantised linear: our kernels ran
     assert ops.check_status() == 0
     with torch.no_grad():
         qnn.set_timestep_id_for_quantlayer(float(small["t"][0]))

@@ -148,3 +148,60 @@ def test_frame_sharding_host_helpers():
         G = 2
     with pytest.raises(ValueError):
         shard.exchange_act_codes(A(), 1, 2, 16, 2, True)
+
+
+def test_forward_fused_refuses_states_it_does_not_implement(small):
+    """the fused schedule hard-wires dynamic per-token W+A quantisation of all 13 block linears.  A
+    static-scale checkpoint (w8a8_naive.yaml), a layer switched to FP, or q/k/v with different activation widths must raise
+    on EVERY call (before any kernel runs: this test needs no GPU) instead of silently mixing quantiser types."""
+    from viditq_b200.qdiff import QuantModel
+    from viditq_b200.stdit import STDiT
+    x, t = torch.from_numpy(small["x"]), torch.from_numpy(small["t"])
+    y, mask = torch.from_numpy(small["y"]).float(), torch.from_numpy(small["mask"])
+
+    def fresh(dynamic=True, per_group="token"):
+        model = STDiT(input_size=(4, 16, 16), depth=2)
+        model.eval()
+        wq, aq = quant_cfgs(int(small["T"]), int(small["S"]))
+        aq = Cfg(aq, dynamic=dynamic, per_group=per_group)
+        qnn = QuantModel(model, wq, aq)
+        qnn.set_quant_state(True, True)
+        qnn.set_layer_quant(model=qnn, module_name_list=FP_LAYERS, quant_level="per_layer", weight_quant=False,
+                            act_quant=False, prefix="")
+        return qnn, model
+    qnn, model = fresh(dynamic=False, per_group=False)               # static per-tensor activation scales
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="static"):
+        model.forward_fused(x, t, y, mask=mask)
+    qnn, model = fresh(dynamic=False, per_group="token")             # static per-token: MASK_SELECT=False layouts
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="static per-token"):
+        model.forward_fused(x, t, y, mask=mask)
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="static per-token"):
+        model.forward_fused(x, t, y, mask=mask, plan=model.mask_select_plan(mask))     # the guard does not depend on `plan`
+    qnn, model = fresh()
+    qnn.set_layer_quant(model=qnn, module_name_list=["blocks.1.cross_attn.proj"], quant_level="per_layer",
+                        weight_quant=False, act_quant=False, prefix="")
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="blocks.1.cross_attn.proj"):
+        model.forward_fused(x, t, y, mask=mask)
+    qnn, model = fresh()
+    qnn.load_bitwidth_config(qnn.model, {"blocks.0.attn_temp.k": 6}, "act")
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="activation widths differ"):
+        model.forward_fused(x, t, y, mask=mask)
+
+
+def test_mask_select_false_branch_matches_reference_layout(small):
+    """Quirk Q14 (stdit.py:272-300): with a static per-token activation quantiser the prompt rows are zero-masked, not
+    dropped — every sample keeps max_len rows so that calibrated per-token (delta, zp) keep their positions."""
+    from viditq_b200.qdiff import QuantModel
+    from viditq_b200.stdit import STDiT
+    model = STDiT(input_size=(4, 16, 16), depth=1)
+    model.eval()
+    wq, aq = quant_cfgs(int(small["T"]), int(small["S"]))
+    QuantModel(model, wq, Cfg(aq, dynamic=False, per_group="token"))
+    x, t = torch.from_numpy(small["x"]), torch.from_numpy(small["t"])
+    y, mask = torch.from_numpy(small["y"]).float(), torch.from_numpy(small["mask"])
+    with torch.no_grad():
+        _, _, _, yy, y_lens = model.embed(x, t, y, mask)
+        full = model.y_embedder(y).squeeze(1)
+    n_keep = int(mask.sum())
+    assert y_lens == [120] and yy.shape == (1, 120, 1152)
+    assert torch.equal(yy[0, :n_keep], full[0, :n_keep]) and float(yy[0, n_keep:].abs().max()) == 0.0

@@ -190,6 +190,7 @@ static int run_case(int M, int N, int K, int epi, int period, bool timeit, bool 
 
 int main(int argc, char** argv) {
   bool timeit = argc > 1 && !strcmp(argv[1], "--time");
+  bool time32 = argc > 1 && !strcmp(argv[1], "--time32");   // the shapes a stacked cfg_split step launches (M = 32768)
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s sm_%d%d SMs=%d lib version %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
@@ -198,6 +199,14 @@ int main(int argc, char** argv) {
   if (argc > 5 && !strcmp(argv[1], "--case")) {  // single case, no timing loop: for ncu captures
     int M = atoi(argv[2]), N = atoi(argv[3]), K = atoi(argv[4]), epi = atoi(argv[5]);
     return run_case(M, N, K, epi, M, false);
+  }
+  if (time32) {
+    fails += run_case(32768, 1152, 1152, VQ_EPI_GATE_RESIDUAL, 32768, true, true);
+    fails += run_case(32768, 3456, 1152, VQ_EPI_BIAS, 32768, true);
+    fails += run_case(32768, 4608, 1152, VQ_EPI_BIAS, 32768, true);
+    fails += run_case(32768, 1152, 4608, VQ_EPI_GATE_RESIDUAL, 32768, true, true);
+    printf(fails ? "SELFTEST FAILED (%d cases)\n" : "SELFTEST PASSED\n", fails);
+    return fails ? 1 : 0;
   }
   fails += run_case(128, 192, 128, VQ_EPI_BIAS, 128, false);    // one tile, one K block
   fails += run_case(128, 192, 1152, VQ_EPI_BIAS, 128, false);   // full K pipeline (9 blocks > 5 stages)

@@ -2,6 +2,8 @@
 
 Every function launches hand-written sm_100a kernels from libviditq_b200.so; none has a PyTorch/CPU fallback.
 """
+import functools
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -21,6 +23,22 @@ def launch_count():
 def _count(n=1):
     global _launches
     _launches += n
+
+
+def _nvtx(fn):
+    """NVTX range around every kernel wrapper when VQ_NVTX=1 (nsys / ncu --nvtx timelines name the fused op, not only the
+    kernel); a no-op otherwise."""
+    if os.environ.get("VQ_NVTX", "0") != "1":
+        return fn
+
+    @functools.wraps(fn)
+    def inner(*a, **k):
+        torch.cuda.nvtx.range_push("viditq_b200." + fn.__name__)
+        try:
+            return fn(*a, **k)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return inner
 
 
 def _stream():
@@ -44,6 +62,7 @@ def status_word(device=None):
     return _status[dev]
 
 
+@_nvtx
 def cfg_ddim_step(out_cond, out_uncond, x, coef, cfg_scale, ptqd_k=0.0, out=None):
     """Fused CFG combine + DDIM (eta = 0) update. out_cond / out_uncond: fp32 CUDA [n, 2c, ...]; x: fp32 [n, c, ...];
     coef: fp32 CUDA [4] (SpacedDDIM.coefficients). Returns the next latent (fp32, x's shape)."""
@@ -63,6 +82,7 @@ def cfg_ddim_step(out_cond, out_uncond, x, coef, cfg_scale, ptqd_k=0.0, out=None
     return out
 
 
+@_nvtx
 def patch_embed(latent, weight, bias, pos, patch_hw, T=None):
     """Fused patchify + position embedding. latent: fp32 CUDA [B, Cin, T, H, W] (or [B, Cin, H, W]); weight: fp16 conv
     weight [C, Cin, (1,) ph, pw]; bias fp16 [C] or None; pos fp16 [S, C] or None -> fp16 [B, T*S, C]."""
@@ -127,6 +147,7 @@ class ActCodes:
     pw: Optional[PreparedWeight] = None   # set by QuantLayer.quantize_input: the weight these codes were scaled for
 
 
+@_nvtx
 def prep_weight(w, delta, zp, n_bits=8, smooth=None, bias=None) -> PreparedWeight:
     _need_cuda_f16(w, "weight")
     N, K = w.shape
@@ -154,6 +175,7 @@ def _alloc_act(G, rows, K, device):
                     torch.empty(G * rows, dtype=torch.int32, device=device), G, rows, K)
 
 
+@_nvtx
 def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None, gelu=False) -> ActCodes:
     """x: fp16 [G, rows, K] (reference layout [BS, n_token, C]); statistics per token pooled over G.
     gelu=True quantises gelu_tanh(x) instead (the Mlp activation fused in front of fc2's quantiser)."""
@@ -170,6 +192,7 @@ def act_quant(x, n_bits=8, smooth=None, out: Optional[ActCodes] = None, gelu=Fal
     return a
 
 
+@_nvtx
 def add_act_quant(x, addv, rows_per_add, n_bits=8, smooth=None) -> ActCodes:
     """Quantise h(x + addv[(r // rows_per_add) % len(addv)]) per token: x fp16 [G, rows, K], addv fp16 [period, K]."""
     _need_cuda_f16(x, "x")
@@ -188,6 +211,7 @@ def add_act_quant(x, addv, rows_per_add, n_bits=8, smooth=None) -> ActCodes:
     return a
 
 
+@_nvtx
 def col_absmax(x, gelu=False):
     """input.abs().max(dim=-2)[0] of the smooth-quant statistics (quant_layer.py:116,119): x fp16 [G, n, K] -> fp16 [G, K]
     (exact).  gelu=True: maxima of h(gelu_tanh(x))."""
@@ -200,6 +224,7 @@ def col_absmax(x, gelu=False):
     return bits.to(torch.int16).view(torch.float16)
 
 
+@_nvtx
 def act_quant_static(x, delta, zp, n_bits=8, smooth=None) -> ActCodes:
     """Static (calibrated) activation scales: x fp16 [..., K]; delta / zp: fp16 CUDA [period] (1 = per-tensor, the
     w8a8_naive.yaml case; rows = static per-token). Row m uses index m % period."""
@@ -222,6 +247,7 @@ def act_quant_static(x, delta, zp, n_bits=8, smooth=None) -> ActCodes:
     return ActCodes(codes, delta.reshape(-1), zp.reshape(-1), rowsum, M // period, period, K)
 
 
+@_nvtx
 def act_quant_heads(x, G, rows, S, n_bits=8, out: Optional[ActCodes] = None) -> ActCodes:
     """x: fp16 head-major attention output [G * rows / S, H, S, 72] (contiguous). Quantises the token-major view
     [G, rows, H*72] without materialising it."""
@@ -237,6 +263,7 @@ def act_quant_heads(x, G, rows, S, n_bits=8, out: Optional[ActCodes] = None) -> 
     return a
 
 
+@_nvtx
 def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional[ActCodes] = None, smooth=None,
                           rows_per_mod=None):
     """x: fp16 [G, rows, K]; shift/scale: fp16 [G * rows / rows_per_mod, K] (default one per batch entry); smooth: fp16
@@ -262,6 +289,7 @@ def ln_modulate_act_quant(x, shift, scale, n_bits=8, want_y=False, out: Optional
     return a, y
 
 
+@_nvtx
 def gemm_w8a8(a: ActCodes, w: PreparedWeight, epi=VQ_EPI_BIAS, res=None, gate=None, rows_per_gate=0, out=None, ldo=None):
     """out[M,N] fp16 = epilogue(dequant(a.codes @ w.codes^T)); M = G*rows. `out` may be a column slice of a wider
     row-major tensor (pass its row pitch as ldo)."""
@@ -297,6 +325,7 @@ def linear_launch_count(G, rows, K):
     return _lib.lib().vq_linear_launch_count(G, rows, K)
 
 
+@_nvtx
 def linear_w8a8(x, w: PreparedWeight, n_bits=8, smooth=None, ln=None, rows_per_mod=None, epi=VQ_EPI_BIAS, res=None,
                 gate=None, rows_per_gate=0, out=None, ldo=None):
     """One QuantLayer-family forward in ONE call (vq_linear_w8a8): x fp16 [G, rows, K] (per-token statistics pooled over G)
@@ -340,6 +369,7 @@ def linear_w8a8(x, w: PreparedWeight, n_bits=8, smooth=None, ln=None, rows_per_m
     return out
 
 
+@_nvtx
 def attn_temporal(qkv, B, T, S, H, head_dim, scale, out=None):
     """qkv: fp16 [B*T*S, 3*H*head_dim] (fused q|k|v GEMM output, (T S) token order) -> fp16 [B*T*S, H*head_dim]."""
     _need_cuda_f16(qkv, "qkv")
@@ -354,6 +384,7 @@ def attn_temporal(qkv, B, T, S, H, head_dim, scale, out=None):
     return out
 
 
+@_nvtx
 def attn_spatial(qkv, n_seq, S, H, head_dim, scale, out=None):
     """qkv: fp16 [n_seq*S, 3*H*head_dim] (fused q|k|v GEMM output; n_seq = B*T frames of S tokens) -> fp16
     [n_seq*S, H*head_dim], token-major. tcgen05 flash attention; head_dim 72, S a multiple of 256."""
@@ -373,6 +404,7 @@ def attn_spatial_supported(S, head_dim):
     return head_dim == 72 and S >= 256 and S % 256 == 0
 
 
+@_nvtx
 def attn_cross(q, kv, kv_start, kv_len, B, N, H, head_dim, max_len, scale, out=None):
     """q: fp16 [B*N, C]; kv: fp16 [sum(len), 2C]; kv_start/kv_len: int32 device tensors [B] -> fp16 [B*N, C]."""
     _need_cuda_f16(q, "q")
