@@ -318,9 +318,12 @@ def load_traffic():
         return {}
 
 
-def rooflines(work, prof, peaks, int8_peak, steps_profiled=1):
+def rooflines(work, prof, peaks, int8_peak, busy_ms, ms_per_step_timed):
     """One roofline entry per kernel class: achieved = algorithmic ops (tensor-bound) or bytes (HBM-bound) of the class over
-    one step / the class's summed kernel time inside the (replayed) step."""
+    one step / the class's kernel time inside the TIMED step.  That time = the class's SHARE of the CUPTI-profiled replay x
+    the step time of the timed region: a single profiled replay runs on a cool GPU at higher clocks than K back-to-back
+    steps under the 1000 W cap, so its absolute durations would overstate what the timed region achieved."""
+    steps_profiled = 1
     hbm = peaks.get("hbm_gbs", 6500.0)
     bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
     traffic = load_traffic()
@@ -328,14 +331,15 @@ def rooflines(work, prof, peaks, int8_peak, steps_profiled=1):
     for cls, _, bound in KERNEL_CLASSES:
         if cls not in prof or cls not in work:
             continue
-        launches, ms = prof[cls]
-        ms /= steps_profiled
+        launches, ms_raw = prof[cls]
+        ms = ms_raw / busy_ms * ms_per_step_timed if busy_ms > 0 else ms_raw
         n, ops_, bytes_ = work[cls]
         if ms <= 0:
             continue
         tr = traffic.get(cls)
         entry = {"kernel_class": cls, "bound": bound, "launches_per_step": launches // steps_profiled,
-                 "ms_per_step": ms, "algorithmic_bytes_per_launch": bytes_ / max(1, n),
+                 "ms_per_step": ms, "ms_per_step_single_profiled_replay": ms_raw, "share_of_step": ms_raw / busy_ms,
+                 "algorithmic_bytes_per_launch": bytes_ / max(1, n),
                  "traffic": None if tr is None else tr.get("dram_bytes_per_launch"),
                  "traffic_source": None if tr is None else tr.get("source")}
         if bound == "tensor":
@@ -721,7 +725,7 @@ def main():
         n_samples = world // 2 if pairs else (1 if fsh else world)
         value = n_samples * args.steps / (ms * 1e-3)
         e2e_value = n_samples * args.steps / (ms_e2e * 1e-3)
-        roofs = rooflines(work, prof, peaks, int8_peak)
+        roofs = rooflines(work, prof, peaks, int8_peak, busy_ms, ms / args.steps)
         main_roof = next((r for r in roofs if r["kernel_class"] == "gemm"), None)
         roofline = None
         if main_roof is not None:
@@ -731,8 +735,9 @@ def main():
                         "algorithmic_bytes_per_launch": main_roof["algorithmic_bytes_per_launch"],
                         "kernel": "vq_gemm_w8a8_kernel / vq_linear_fused_kernel (all QuantLinear GEMMs of a step)",
                         "peak_source": main_roof["peak_source"],
-                        "timing": "CUPTI kernel durations of one replay of the timed CUDA graph" if graph is not None
-                                  else "CUPTI kernel durations of one eager step",
+                        "timing": ("share of the kernel class in a CUPTI-profiled replay of the timed CUDA graph x ms_per_step of "
+                                   "the timed region" if graph is not None else
+                                   "share of the kernel class in a CUPTI-profiled eager step x ms_per_step of the timed region"),
                         "gemm_ms_per_step": main_roof["ms_per_step"], "gemm_launches_per_step": main_roof["launches_per_step"],
                         "whole_step_frac": total_linear_top / (ms / args.steps * 1e-3) / main_roof["peak"],
                         "int8_peak_measured": int8_peak}
