@@ -143,6 +143,18 @@ int vq_linear_w8a8(const void* x, int G, int rows, int K, const void* smooth, co
                    const void* res, int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* out_delta,
                    void* out_zp, void* workspace, int64_t workspace_bytes, uint32_t* status, void* stream);
 
+/* (J2: north-star "INT4 x INT8 tensor-core GEMM") W4A8 with PACKED weight codes — the
+ * w4a8_timestep_aware_cb.yaml layers (reference base_quantizer.py:129-144 at n_bits = 4).  vq_pack_u4 packs prepared u8 codes
+ * (< 16) two per byte (low nibble = even k) into w_packed [N, K/2]; vq_linear_w4a8 is vq_linear_w8a8's fused kernel with the
+ * weight operand streamed at half the bytes: the TMA stages packed tiles and two converter warps expand them into the swizzled
+ * u8 operand of tcgen05.mma.kind::i8 (there is no INT4 integer MMA kind on sm_100a).  Same arguments otherwise; only the shapes
+ * vq_linear_launch_count() reports as 1 are supported (VQ_ERR_UNSUPPORTED otherwise: call vq_linear_w8a8 with the u8 codes). */
+int vq_pack_u4(const uint8_t* codes, int N, int K, uint8_t* packed, void* stream);
+int vq_linear_w4a8(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift, const void* ln_scale,
+                   int rows_per_mod, int n_bits, const uint8_t* w_packed, const VqColParam* col, int N, int epi,
+                   const void* res, int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* out_delta,
+                   void* out_zp, uint32_t* status, void* stream);
+
 /* (a9) temporal self-attention of STDiT (stdit.py:112-118, blocks.py:151-195 on "(B S) T C"), reading q|k|v in place
  * from the fused GEMM output qkv fp16 [B*T*S, 3*H*head_dim] in the (T S) token layout; out fp16 [B*T*S, H*head_dim].
  * head_dim must be 72, T <= 16. scale = head_dim^-0.5.                                                             */

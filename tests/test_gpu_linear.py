@@ -145,3 +145,51 @@ def test_col_absmax_is_exact(G, n, K, gelu):
         assert (got.float() - ref.float()).abs().max() <= 2e-3 * ref.float().abs().max()
     else:
         assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("G,rows,N,epi,ln", [(1, 2048, 3456, 0, True), (2, 1024, 1152, 2, False), (1, 109, 2304, 0, False),
+                                              (1, 300, 1152, 1, False), (1, 4096, 4608, 0, True)])
+def test_packed_int4_weights_equal_byte_codes(G, rows, N, epi, ln):
+    """J2: W4A8 with the weight operand streamed as packed INT4 (vq_linear_w4a8: TMA of half-width tiles + converter warps)
+    must be bit-identical to the same 4-bit codes stored one per byte (vq_linear_w8a8), and to quantise pass + GEMM."""
+    _need_gpu()
+    import os
+    from viditq_b200 import ops
+    K, M = 1152, G * rows
+    g = torch.Generator().manual_seed(N + rows)
+    x = torch.randn(G, rows, K, generator=g).half()
+    x[..., 3] *= 9
+    x = x.cuda()
+    w = (torch.randn(N, K, generator=g) * 0.03).half().cuda()
+    b = (torch.randn(N, generator=g) * 0.02).half().cuda()
+    mn, mx = w.float().min(1)[0].clamp(max=0), w.float().max(1)[0].clamp(min=0)
+    d = ((mx - mn) / 15).half()
+    z = torch.round(-mn / d.float()).half()
+    pw = ops.prep_weight(w, d, z, n_bits=4, bias=b)
+    assert int(pw.codes.max()) <= 15
+    shift = scale = None
+    if ln:
+        shift = (torch.randn(G, K, generator=g) * 0.1).half().cuda()
+        scale = (torch.randn(G, K, generator=g) * 0.1).half().cuda()
+    res = gate = None
+    if epi == 2:
+        res = torch.randn(M, N, generator=g).half().cuda()
+        gate = torch.randn(1, N, generator=g).half().cuda()
+    kw = dict(ln=(shift, scale) if ln else None, epi=epi, gate=gate, rows_per_gate=M if epi == 2 else 0)
+    ref = ops.linear_w8a8(x, pw, res=res, **kw)                          # byte codes through the fused kernel
+    if ln:
+        a, _ = ops.ln_modulate_act_quant(x, shift, scale)
+    else:
+        a = ops.act_quant(x)
+    two = ops.gemm_w8a8(a, pw, epi=epi, res=res, gate=gate, rows_per_gate=M if epi == 2 else 0)
+    ops.pack_u4(pw)
+    # the packed form really is two codes per byte
+    pk = pw.packed.cpu().numpy()
+    cd = pw.codes.cpu().numpy()
+    assert pk.shape == (N, K // 2) and np.array_equal(pk & 15, cd[:, 0::2]) and np.array_equal(pk >> 4, cd[:, 1::2])
+    assert os.environ.get("VQ_W4_PACKED", "1") != "0"
+    n0 = ops.launch_count()
+    got = ops.linear_w8a8(x, pw, res=res, **kw)                          # dispatches to vq_linear_w4a8
+    assert ops.launch_count() - n0 == 1
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref) and torch.equal(got, two)

@@ -359,6 +359,22 @@ int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
 }
 
+// general u8 matrix map: box = box_rows x box_cols bytes, 128-byte swizzle or none (dense rows: the packed INT4 weight tiles
+// the converter warps of vq_linear_fused_kernel expand themselves)
+int make_u8_tmap_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_cols,
+                    uint32_t box_rows, bool swizzle128) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return VQ_ERR_DRIVER;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VQ_OK : VQ_ERR_TMAP;
+}
+
 // rows x cols fp16 matrix (row pitch ld elements); box = 32 rows x EPI_CHUNK cols, matching swizzle: the epilogue staging tile.
 int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
   PFN_encodeTiled enc = get_encode_fn();

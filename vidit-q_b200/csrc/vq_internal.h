@@ -79,6 +79,8 @@ int attn_cross_tc(const void* q, const void* kv, void* out, const int* kv_start,
                   int head_dim, long long kv_rows, float scale, void* stream);
 int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch,
                         uint32_t box_rows);
+int make_u8_tmap_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_cols,
+                    uint32_t box_rows, bool swizzle128);
 // rows x cols fp16 matrix (row pitch ld elements), box 32 rows x 32 columns, SWIZZLE_64B: the epilogue staging sub-tile
 int make_f16_out_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
 }  // namespace vq

@@ -38,10 +38,17 @@ constexpr int FL_STAGES_PAIR = 4;                          // x 12 KB (half a 19
 constexpr int FL_STAGES_SINGLE = 2;                        // x 24 KB
 constexpr int FL_B_BYTES = FL_STAGES_PAIR * B_PAIR_STAGE_BYTES;
 static_assert(FL_B_BYTES == FL_STAGES_SINGLE * B_STAGE_BYTES, "weight ring size");
+// W4 (packed INT4 weights, two codes per byte: low nibble = even k): the TMA stages PACKED half-width tiles, converter warps 2-3
+// expand them into the u8 SWIZZLE_128B stage tcgen05.mma reads (kind::i8 is the only integer MMA kind; there is no INT4 kind)
+constexpr int FL_W4_U8_STAGES_PAIR = 3, FL_W4_PK_STAGES_PAIR = 3;        // 3 x 12 KB u8 + 3 x 6 KB packed
+constexpr int FL_W4_U8_STAGES_SINGLE = 1, FL_W4_PK_STAGES_SINGLE = 2;    // 1 x 24 KB u8 + 2 x 12 KB packed
+constexpr int FL_B_BYTES_W4 = FL_W4_U8_STAGES_PAIR * B_PAIR_STAGE_BYTES + FL_W4_PK_STAGES_PAIR * (B_PAIR_STAGE_BYTES / 2);
+static_assert(FL_W4_U8_STAGES_SINGLE * B_STAGE_BYTES + FL_W4_PK_STAGES_SINGLE * (B_STAGE_BYTES / 2) <= FL_B_BYTES_W4, "W4 ring");
 constexpr int FL_EPI_BYTES = NUM_EPI_WARPS * EPI_BUF_BYTES;   // one 32 x 32 fp16 staging sub-tile per epilogue warp
 constexpr int FL_ROWP_BYTES = BM * 16;                        // per panel row {delta, zero point, code sum, -}
 constexpr int FL_SMEM_BYTES = FL_PANEL_BYTES + FL_B_BYTES + FL_EPI_BYTES + COLBUF_BYTES + FL_ROWP_BYTES + 512 + 1024;
-static_assert(FL_SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+constexpr int FL_SMEM_BYTES_W4 = FL_SMEM_BYTES - FL_B_BYTES + FL_B_BYTES_W4;
+static_assert(FL_SMEM_BYTES_W4 <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 constexpr int FL_PROD_WARPS = NUM_EPI_WARPS;               // 8
 constexpr int FL_ROWS_IN_FLIGHT = 4;
 
@@ -109,17 +116,20 @@ __device__ __forceinline__ void fl_zero_row(uint32_t panel, int i, int lane) {
   for (int u = 0; u < FL_KB; ++u) sts_u32(panel_addr(panel, i, u, lane), 0u);
 }
 
-template <int EPI, bool PAIR, bool LN>
+template <int EPI, bool PAIR, bool LN, bool W4>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 vq_linear_fused_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
                        const FusedArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int NS = PAIR ? FL_STAGES_PAIR : FL_STAGES_SINGLE;
+  constexpr int NS = W4 ? (PAIR ? FL_W4_U8_STAGES_PAIR : FL_W4_U8_STAGES_SINGLE) : (PAIR ? FL_STAGES_PAIR : FL_STAGES_SINGLE);
+  constexpr int NSP = PAIR ? FL_W4_PK_STAGES_PAIR : FL_W4_PK_STAGES_SINGLE;   // packed ring (W4 only)
   constexpr int BSB = PAIR ? B_PAIR_STAGE_BYTES : B_STAGE_BYTES;
+  constexpr int PKB = BSB / 2;                                                // bytes of one packed stage
   uint8_t* smem_panel = smem;
   uint8_t* smem_b = smem + FL_PANEL_BYTES;
-  uint8_t* smem_epi = smem_b + FL_B_BYTES;
+  uint8_t* smem_pk = smem_b + NS * BSB;
+  uint8_t* smem_epi = smem_b + (W4 ? FL_B_BYTES_W4 : FL_B_BYTES);
   int4* colbuf = reinterpret_cast<int4*>(smem_epi + FL_EPI_BYTES);
   RowParam* rowp = reinterpret_cast<RowParam*>(smem_epi + FL_EPI_BYTES + COLBUF_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + FL_EPI_BYTES + COLBUF_BYTES + FL_ROWP_BYTES);
@@ -130,7 +140,9 @@ vq_linear_fused_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_
   uint64_t* colfull_bar = bars + 12;               // [2]
   uint64_t* colempty_bar = bars + 14;              // [2]
   uint64_t* a_ready_bar = bars + 16;               // the activation panel(s) of this CTA (pair) are quantised
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* pfull_bar = bars + 18;                 // [4] W4: a packed tile has landed (TMA)
+  uint64_t* pempty_bar = bars + 22;                // [4] W4: both converter warps are done with a packed tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,8 +162,11 @@ vq_linear_fused_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(&full_bar[s], 1);
+      // W4: the u8 stage is filled by the two converter warps of each CTA of the pair, not by the TMA
+      mbar_init(&full_bar[s], W4 ? (PAIR ? 4 : 2) : 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&pfull_bar[s], 1);
+      mbar_init(&pempty_bar[s], 2);
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -187,6 +202,13 @@ vq_linear_fused_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_
       for (int tile = nt0; tile < nt1; ++tile) {
         const int n_idx = tile * BN + (PAIR ? static_cast<int>(cta_rank) * (BN / 2) : 0);
         for (int kb = 0; kb < FL_KB; ++kb) {
+          if (W4) {   // packed tile (64 bytes per row) into this CTA's packed ring, on its own barrier
+            mbar_wait(&pempty_bar[s], phase ^ 1);
+            mbar_arrive_expect_tx(&pfull_bar[s], PKB);
+            tma_load_2d_hint(smem_pk + s * PKB, &tmap_b, &pfull_bar[s], kb * (BK / 2), n_idx, kEvictLast);
+            if (++s == NSP) { s = 0; phase ^= 1; }
+            continue;
+          }
           mbar_wait(&empty_bar[s], phase ^ 1);
           if (PAIR) {
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
@@ -234,26 +256,63 @@ vq_linear_fused_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_
       }
     }
     __syncwarp();
-  } else if (warp == 3) {
-    // ===================== column-record producer =====================
+  } else if (warp == 3 || (W4 && warp == 2)) {
+    // ===================== column-record producer (warp 3) [+ W4: INT4 -> u8 converters (warps 2 and 3)] =====================
     const int4* colg = reinterpret_cast<const int4*>(p.col);
     const int nmax = p.N - 1;
     int local = 0;
+    int us = 0, ps = 0;
+    uint32_t uphase = 0, pphase = 0;
     for (int tile = nt0; tile < nt1; ++tile, ++local) {
-      const int b = local & 1;
-      mbar_wait(&colempty_bar[b], ((local >> 1) & 1) ^ 1);
-      const int n0 = tile * BN;
+      if (warp == 3) {
+        const int b = local & 1;
+        mbar_wait(&colempty_bar[b], ((local >> 1) & 1) ^ 1);
+        const int n0 = tile * BN;
 #pragma unroll
-      for (int i = 0; i < BN / 64; ++i) {
-        const int pr = lane + 32 * i;
-        const int n = n0 + 2 * pr;
-        const int4 r0 = __ldg(colg + (n < nmax ? n : nmax));
-        const int4 r1 = __ldg(colg + (n + 1 < nmax ? n + 1 : nmax));
-        colbuf[b * BN + 2 * pr] = make_int4(r0.x, r1.x, r0.y, r1.y);
-        colbuf[b * BN + 2 * pr + 1] = make_int4(r0.z, r1.z, r0.w, r1.w);
+        for (int i = 0; i < BN / 64; ++i) {
+          const int pr = lane + 32 * i;
+          const int n = n0 + 2 * pr;
+          const int4 r0 = __ldg(colg + (n < nmax ? n : nmax));
+          const int4 r1 = __ldg(colg + (n + 1 < nmax ? n + 1 : nmax));
+          colbuf[b * BN + 2 * pr] = make_int4(r0.x, r1.x, r0.y, r1.y);
+          colbuf[b * BN + 2 * pr + 1] = make_int4(r0.z, r1.z, r0.w, r1.w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&colfull_bar[b]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&colfull_bar[b]);
+      if (W4) {
+        // each K block: packed [rows][64 B] -> u8 [rows][128 B] in the SWIZZLE_128B pattern (16-byte chunk ^ (row & 7)).
+        // One item = 8 packed bytes -> one 16-byte chunk of 16 codes; the two warps split the rows of the stage.
+        constexpr int ROWS = BSB / BK;                  // 96 (pair) | 192
+        constexpr int ITEMS_PER_WARP = ROWS * 8 / 2;
+        const int cw = warp - 2;
+        for (int kb = 0; kb < FL_KB; ++kb) {
+          mbar_wait(&pfull_bar[ps], pphase);
+          mbar_wait(&empty_bar[us], uphase ^ 1);        // the MMAs that read this u8 stage have retired
+          const uint32_t src = smem_u32(smem_pk + ps * PKB);
+          const uint32_t dst = smem_u32(smem_b + us * BSB);
+#pragma unroll 4
+          for (int t = 0; t < ITEMS_PER_WARP / 32; ++t) {
+            const int idx = cw * ITEMS_PER_WARP + t * 32 + lane;
+            const int row = idx >> 3, j = idx & 7;
+            uint32_t px, py;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(px), "=r"(py) : "r"(src + row * (BK / 2) + j * 8));
+            const uint32_t lo0 = px & 0x0F0F0F0Fu, hi0 = (px >> 4) & 0x0F0F0F0Fu;
+            const uint32_t lo1 = py & 0x0F0F0F0Fu, hi1 = (py >> 4) & 0x0F0F0F0Fu;
+            sts_v4_addr(dst + row * BK + ((j ^ (row & 7)) << 4), __byte_perm(lo0, hi0, 0x5140), __byte_perm(lo0, hi0, 0x7362),
+                        __byte_perm(lo1, hi1, 0x5140), __byte_perm(lo1, hi1, 0x7362));
+          }
+          fence_proxy_async_smem();                     // generic-proxy writes -> the tensor core's operand reads
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_leader(&full_bar[us]);
+            else mbar_arrive(&full_bar[us]);
+            mbar_arrive(&pempty_bar[ps]);
+          }
+          if (++us == NS) { us = 0; uphase ^= 1; }
+          if (++ps == NSP) { ps = 0; pphase ^= 1; }
+        }
+      }
     }
   } else if (warp >= 4) {
     // ===================== (A) producers: quantise the activation panel into shared memory =====================
@@ -447,20 +506,21 @@ vq_linear_fused_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_
   }
 }
 
-template <int EPI, bool PAIR, bool LN>
+template <int EPI, bool PAIR, bool LN, bool W4>
 static int launch_fused_impl(const CUtensorMap& tb, const CUtensorMap& to, const FusedArgs& args, int grid, cudaStream_t stream) {
   static bool attr_set[kMaxDevices] = {};
   const int dev = current_device();
+  constexpr int SMEM = W4 ? FL_SMEM_BYTES_W4 : FL_SMEM_BYTES;
   if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(vq_linear_fused_kernel<EPI, PAIR, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             FL_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(vq_linear_fused_kernel<EPI, PAIR, LN, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM) != cudaSuccess)
       return VQ_ERR_LAUNCH;
     attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = FL_SMEM_BYTES;
+  cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -471,15 +531,41 @@ static int launch_fused_impl(const CUtensorMap& tb, const CUtensorMap& to, const
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_linear_fused_kernel<EPI, PAIR, LN>, tb, to, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_linear_fused_kernel<EPI, PAIR, LN, W4>, tb, to, args);
   return e == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
+template <int EPI, bool W4>
+static int launch_fused_w(const CUtensorMap& tb, const CUtensorMap& to, const FusedArgs& a, int grid, bool pair, bool ln,
+                          cudaStream_t st) {
+  if (pair) return ln ? launch_fused_impl<EPI, true, true, W4>(tb, to, a, grid, st) : launch_fused_impl<EPI, true, false, W4>(tb, to, a, grid, st);
+  return ln ? launch_fused_impl<EPI, false, true, W4>(tb, to, a, grid, st) : launch_fused_impl<EPI, false, false, W4>(tb, to, a, grid, st);
+}
+
 template <int EPI>
-static int launch_fused(const CUtensorMap& tb, const CUtensorMap& to, const FusedArgs& a, int grid, bool pair, bool ln,
+static int launch_fused(const CUtensorMap& tb, const CUtensorMap& to, const FusedArgs& a, int grid, bool pair, bool ln, bool w4,
                         cudaStream_t st) {
-  if (pair) return ln ? launch_fused_impl<EPI, true, true>(tb, to, a, grid, st) : launch_fused_impl<EPI, true, false>(tb, to, a, grid, st);
-  return ln ? launch_fused_impl<EPI, false, true>(tb, to, a, grid, st) : launch_fused_impl<EPI, false, false>(tb, to, a, grid, st);
+  return w4 ? launch_fused_w<EPI, true>(tb, to, a, grid, pair, ln, st) : launch_fused_w<EPI, false>(tb, to, a, grid, pair, ln, st);
+}
+
+// two INT4 codes per byte, low nibble = even k (what the converter warps of vq_linear_fused_kernel<.., W4> expand)
+__global__ void __launch_bounds__(256) vq_pack_u4_kernel(const uint8_t* __restrict__ codes, uint8_t* __restrict__ packed,
+                                                         long long n_groups) {
+  grid_dep_sync();
+  const long long gidx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // 16 codes -> 8 bytes
+  if (gidx >= n_groups) return;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(codes) + gidx);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    // word = codes k0..k3 -> byte (k0 | k1 << 4), (k2 | k3 << 4)
+    const uint32_t a = w[2 * h], b = w[2 * h + 1];
+    const uint32_t pa = (a & 0x000F000Fu) | ((a >> 4) & 0x00F000F0u);    // bytes 0 and 2 hold the packed pairs
+    const uint32_t pb = (b & 0x000F000Fu) | ((b >> 4) & 0x00F000F0u);
+    o[h] = __byte_perm(pa, pb, 0x6420);
+  }
+  reinterpret_cast<uint2*>(packed)[gidx] = make_uint2(o[0], o[1]);
 }
 
 static inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
@@ -515,11 +601,11 @@ extern "C" int vq_linear_launch_count(int G, int rows, int K) {
   return fused ? 1 : 2;
 }
 
-extern "C" int vq_linear_w8a8(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift,
-                              const void* ln_scale, int rows_per_mod, int n_bits, const uint8_t* w_codes,
-                              const VqColParam* col, int N, int epi, const void* res, int ldr, const void* gate,
-                              int rows_per_gate, void* out, int ldo, void* out_delta, void* out_zp, void* workspace,
-                              int64_t workspace_bytes, uint32_t* status, void* stream) {
+static int linear_impl(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift,
+                       const void* ln_scale, int rows_per_mod, int n_bits, const uint8_t* w_codes, bool w4,
+                       const VqColParam* col, int N, int epi, const void* res, int ldr, const void* gate,
+                       int rows_per_gate, void* out, int ldo, void* out_delta, void* out_zp, void* workspace,
+                       int64_t workspace_bytes, uint32_t* status, void* stream) {
   using namespace vq;
   if (!x || !w_codes || !col || !out || G <= 0 || rows <= 0 || K <= 0 || N <= 0) return VQ_ERR_ARG;
   if ((K % 16) != 0 || (N % 8) != 0 || (ldo % 8) != 0 || n_bits < 2 || n_bits > 8) return VQ_ERR_ARG;
@@ -532,6 +618,7 @@ extern "C" int vq_linear_w8a8(const void* x, int G, int rows, int K, const void*
   if (M > 0x7fffffffLL) return VQ_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool fused = vq_linear_launch_count(G, rows, K) == 1;
+  if (!fused && w4) return VQ_ERR_UNSUPPORTED;   // packed INT4 weights exist for the fused kernel only: pass the u8 codes
   if (!fused) {
     // two launches through the caller's workspace: (LayerNorm + modulate +) quantise pass, then the persistent GEMM
     if (!workspace || workspace_bytes < vq_linear_workspace_bytes(G, rows, K)) return VQ_ERR_ARG;
@@ -562,8 +649,10 @@ extern "C" int vq_linear_w8a8(const void* x, int G, int rows, int K, const void*
   const int panels = (rows + tpp - 1) / tpp;
   const bool pair = panels > 1;
   CUtensorMap tb, to;
-  int rc = make_u8_kmajor_tmap(&tb, w_codes, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(K),
-                               pair ? BN / 2 : BN);
+  int rc = w4 ? make_u8_tmap_ex(&tb, w_codes, static_cast<uint64_t>(N), static_cast<uint64_t>(K / 2),
+                                static_cast<uint64_t>(K / 2), BK / 2, pair ? BN / 2 : BN, /*swizzle128=*/false)
+              : make_u8_kmajor_tmap(&tb, w_codes, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(K),
+                                    pair ? BN / 2 : BN);
   if (rc != VQ_OK) return rc;
   rc = make_f16_out_tmap(&to, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo));
   if (rc != VQ_OK) return rc;
@@ -593,8 +682,35 @@ extern "C" int vq_linear_w8a8(const void* x, int G, int rows, int K, const void*
   a.n_split = n_split;
   const int grid = clusters * n_split * (pair ? 2 : 1);
   switch (epi) {
-    case VQ_EPI_BIAS: return launch_fused<VQ_EPI_BIAS>(tb, to, a, grid, pair, ln, st);
-    case VQ_EPI_GELU_TANH: return launch_fused<VQ_EPI_GELU_TANH>(tb, to, a, grid, pair, ln, st);
-    default: return launch_fused<VQ_EPI_GATE_RESIDUAL>(tb, to, a, grid, pair, ln, st);
+    case VQ_EPI_BIAS: return launch_fused<VQ_EPI_BIAS>(tb, to, a, grid, pair, ln, w4, st);
+    case VQ_EPI_GELU_TANH: return launch_fused<VQ_EPI_GELU_TANH>(tb, to, a, grid, pair, ln, w4, st);
+    default: return launch_fused<VQ_EPI_GATE_RESIDUAL>(tb, to, a, grid, pair, ln, w4, st);
   }
+}
+
+extern "C" int vq_linear_w8a8(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift,
+                              const void* ln_scale, int rows_per_mod, int n_bits, const uint8_t* w_codes,
+                              const VqColParam* col, int N, int epi, const void* res, int ldr, const void* gate,
+                              int rows_per_gate, void* out, int ldo, void* out_delta, void* out_zp, void* workspace,
+                              int64_t workspace_bytes, uint32_t* status, void* stream) {
+  return linear_impl(x, G, rows, K, smooth, ln_shift, ln_scale, rows_per_mod, n_bits, w_codes, false, col, N, epi, res, ldr,
+                     gate, rows_per_gate, out, ldo, out_delta, out_zp, workspace, workspace_bytes, status, stream);
+}
+
+extern "C" int vq_linear_w4a8(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift,
+                              const void* ln_scale, int rows_per_mod, int n_bits, const uint8_t* w_packed,
+                              const VqColParam* col, int N, int epi, const void* res, int ldr, const void* gate,
+                              int rows_per_gate, void* out, int ldo, void* out_delta, void* out_zp, uint32_t* status,
+                              void* stream) {
+  return linear_impl(x, G, rows, K, smooth, ln_shift, ln_scale, rows_per_mod, n_bits, w_packed, true, col, N, epi, res, ldr,
+                     gate, rows_per_gate, out, ldo, out_delta, out_zp, nullptr, 0, status, stream);
+}
+
+extern "C" int vq_pack_u4(const uint8_t* codes, int N, int K, uint8_t* packed, void* stream) {
+  using namespace vq;
+  if (!codes || !packed || N <= 0 || K <= 0 || (K % 16) != 0) return VQ_ERR_ARG;
+  const long long groups = static_cast<long long>(N) * K / 16;
+  launch_pdl(vq_pack_u4_kernel, dim3(static_cast<unsigned>((groups + 255) / 256)), dim3(256), 0,
+             static_cast<cudaStream_t>(stream), codes, packed, groups);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }

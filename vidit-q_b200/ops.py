@@ -132,6 +132,7 @@ class PreparedWeight:
     K: int
     n_bits: int
     smooth: Optional[torch.Tensor] = None   # fp16 [K] smooth-quant channel scale folded into the codes (or None)
+    packed: Optional[torch.Tensor] = None   # u8 [N, K/2]: the same codes two per byte (n_bits <= 4; vq_linear_w4a8)
 
 
 @dataclass
@@ -166,6 +167,20 @@ def prep_weight(w, delta, zp, n_bits=8, smooth=None, bias=None) -> PreparedWeigh
     _lib.check(rc, "vq_prep_weight")
     _count()
     return PreparedWeight(codes, col, N, K, n_bits)
+
+
+@_nvtx
+def pack_u4(w: PreparedWeight) -> PreparedWeight:
+    """Attach the packed-INT4 form of a prepared weight whose codes are < 16 (n_bits <= 4): two codes per byte."""
+    if w.n_bits > 4:
+        raise _lib.VqError(f"pack_u4: {w.n_bits}-bit codes do not fit a nibble")
+    if w.packed is None:
+        packed = torch.empty((w.N, w.K // 2), dtype=torch.uint8, device=w.codes.device)
+        rc = _lib.lib().vq_pack_u4(_ptr(w.codes), w.N, w.K, _ptr(packed), _stream())
+        _lib.check(rc, "vq_pack_u4")
+        _count()
+        w.packed = packed
+    return w
 
 
 def _alloc_act(G, rows, K, device):
@@ -356,6 +371,14 @@ def linear_w8a8(x, w: PreparedWeight, n_bits=8, smooth=None, ln=None, rows_per_m
         _need_cuda_f16(gate, "gate")
     L = _lib.lib()
     n_launch = L.vq_linear_launch_count(G, rows, K)
+    if n_launch == 1 and w.packed is not None and os.environ.get("VQ_W4_PACKED", "1") != "0":
+        # W4A8: stream the weight operand as packed INT4 (half the bytes), expanded by the kernel's converter warps
+        rc = L.vq_linear_w4a8(_ptr(x), G, rows, K, _ptr(smooth), _ptr(shift), _ptr(scale), rpm, n_bits, _ptr(w.packed),
+                              _ptr(w.col), w.N, epi, _ptr(res), w.N, _ptr(gate), rows_per_gate, _ptr(out),
+                              w.N if ldo is None else ldo, None, None, _ptr(status_word(x.device)), _stream())
+        _lib.check(rc, "vq_linear_w4a8")
+        _count()
+        return out
     ws, ws_bytes = None, 0
     if n_launch != 1:
         ws_bytes = L.vq_linear_workspace_bytes(G, rows, K)

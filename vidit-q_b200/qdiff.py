@@ -279,6 +279,8 @@ class QuantLayer(nn.Module):
         pw = ops.prep_weight(self.weight.data, wq.delta, wq.zero_point, n_bits=wq.n_bits, smooth=smooth,
                              bias=None if self.bias is None else self.bias.data)
         pw.smooth = smooth
+        if wq.n_bits <= 4 and pw.K == 1152:
+            ops.pack_u4(pw)      # W4: the fused one-launch linear streams the weight as packed INT4 (vq_linear_w4a8)
         if live_smooth is None:
             if hit is not None:      # the source tensors changed under a cached entry (reload / .to()): stale everywhere
                 self._gen += 1
