@@ -130,14 +130,18 @@ int vq_col_absmax(const void* x, int G, int n, int K, int gelu, uint32_t* out_bi
  * x fp16 [G*rows, K] contiguous (statistics of token r pooled over the G batch entries, quirk Q1); smooth fp16 [K] or NULL;
  * ln_shift / ln_scale: fp16 [G*rows / rows_per_mod, K] or both NULL — when given, LayerNorm(eps 1e-6, no affine) +
  * t2i_modulate (blocks.py:51) run in front of the quantiser (the producers of the q|k|v and fc1 inputs, stdit.py:104,125).
- * K == 1152 with G in {1, 2, 4} (rows a multiple of 128 / G when G > 1) and G * rows <= 8192 (VQ_LINEAR_FUSED_MAX_M) runs as
- * ONE kernel launch (vq_linear_fused_kernel: producer warps quantise the 128-row activation panel straight into the
- * swizzled shared-memory operand of tcgen05.mma; no codes ever reach HBM); other shapes run the two-launch sequence
- * vq_act_quant | vq_ln_modulate_act_quant -> vq_gemm_w8a8 through `workspace` — vq_linear_launch_count says which.
+ * Two schedules behind the one call, chosen by vq_linear_set_fused_policy (vq_linear_launch_count says which):
+ *  - ONE kernel launch (vq_linear_fused_kernel; K == 1152, G in {1, 2, 4}, rows a multiple of 128 / G when G > 1): producer
+ *    warps quantise the 128-row activation panel straight into the swizzled shared-memory operand of tcgen05.mma; no
+ *    activation codes ever reach HBM;
+ *  - quantise pass + persistent GEMM (vq_act_quant | vq_ln_modulate_act_quant -> vq_gemm_w8a8) through `workspace` — the
+ *    DEFAULT: measured faster on B200 at every size inside a CUDA graph (profiles/r02_s3_linear_bench.md).
  * workspace: device scratch of at least vq_linear_workspace_bytes(G, rows, K) bytes (the library never allocates).
  * out_delta / out_zp (optional, may be NULL): fp16 [rows] per-token parameters, the DynamicActQuantizer side state.     */
 int64_t vq_linear_workspace_bytes(int G, int rows, int K);
 int vq_linear_launch_count(int G, int rows, int K);   /* 1 = fused kernel, 2 = quantise pass + GEMM */
+/* mode 0: never fuse (default); 1: fuse every supported shape; -1: fuse supported shapes with G * rows <= max_m */
+int vq_linear_set_fused_policy(int mode, int64_t max_m);
 int vq_linear_w8a8(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift, const void* ln_scale,
                    int rows_per_mod, int n_bits, const uint8_t* w_codes, const VqColParam* col, int N, int epi,
                    const void* res, int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* out_delta,

@@ -327,22 +327,3 @@ def test_own_attention_kernels_inside_the_model():
     print("own attention vs library-attention schedule: %.3e %.3e | vs layerwise reference schedule: %.3e %.3e" % (i1, l1, i2, l2))
     # distances between two correct fp16 implementations of a re-quantising network: inside the band of the W8A8 test
     assert l1 <= 4e-3 and l2 <= 4e-3, (l1, l2)
-
-
-def test_l2_chunked_mlp_is_bit_identical(qnn_gpu, small):  # noqa: F811
-    """VQ_MLP_CHUNK: fc1 -> GELU + quantise -> fc2 run in row chunks through L2-resident scratch buffers.  Token-local
-    kernels with un-pooled statistics: the output must equal the unchunked schedule bit for bit (ragged last chunk too)."""
-    qnn, model = qnn_gpu
-    _set_w8a8(qnn)
-    x, t, y, mask = _inputs(small)
-    with torch.no_grad():
-        qnn.set_timestep_id_for_quantlayer(float(small["t"][0]))
-        args = (torch.cat([x, x]), torch.cat([t, t]), torch.cat([y, y]))
-        ref = model.forward_fused(*args, mask=mask, independent=True)
-        eng = model._engine
-        try:
-            eng.mlp_chunk = 96                      # 256 tokens per sample -> chunks of 96, 96, 64
-            got = model.forward_fused(*args, mask=mask, independent=True)
-        finally:
-            eng.mlp_chunk = 0
-    assert torch.equal(got, ref)

@@ -320,80 +320,56 @@ vq_linear_fused_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_
     const int w = warp - 4;
     const int tok_per_warp = p.tpp / FL_PROD_WARPS;          // 16 (G = 1), 8 (G = 2), 4 (G = 4)
     const int tok0 = panel * p.tpp;
-    if (p.G == 1) {
-      // one warp per token row, FL_ROWS_IN_FLIGHT rows loaded before the first one is touched
-      for (int j0 = 0; j0 < tok_per_warp; j0 += FL_ROWS_IN_FLIGHT) {
-        UnitRegs<FL_KB> regs[FL_ROWS_IN_FLIGHT];
+    // Each warp owns tok_per_warp tokens x G batch entries = 16 rows, handled in batches of FL_ROWS_IN_FLIGHT = 4 rows that are
+    // all loaded before the first one is touched and stay in registers (one pass, also for pooled statistics): row b of a
+    // batch is (token j / G, batch entry j % G), j = j0 + b — G divides 4, so a token's entries never straddle two batches.
+    for (int j0 = 0; j0 < tok_per_warp * p.G; j0 += FL_ROWS_IN_FLIGHT) {
+      UnitRegs<FL_KB> regs[FL_ROWS_IN_FLIGHT];
+      int grow[FL_ROWS_IN_FLIGHT], irow[FL_ROWS_IN_FLIGHT], tokn[FL_ROWS_IN_FLIGHT];
 #pragma unroll
-        for (int b = 0; b < FL_ROWS_IN_FLIGHT; ++b) {
-          const int token = tok0 + w * tok_per_warp + j0 + b;
-          if (token < p.rows) uload_row<FL_KB>(regs[b], p.x + static_cast<size_t>(token) * FL_K, lane);
-        }
+      for (int b = 0; b < FL_ROWS_IN_FLIGHT; ++b) {
+        const int j = j0 + b;
+        const int tl = w * tok_per_warp + j / p.G, g = j % p.G;
+        tokn[b] = tok0 + tl;
+        grow[b] = g * p.rows + tokn[b];
+        irow[b] = g * p.tpp + tl;
+        if (tokn[b] < p.rows) uload_row<FL_KB>(regs[b], p.x + static_cast<size_t>(grow[b]) * FL_K, lane);
+      }
+      float mn[FL_ROWS_IN_FLIGHT], mx[FL_ROWS_IN_FLIGHT];
 #pragma unroll
-        for (int b = 0; b < FL_ROWS_IN_FLIGHT; ++b) {
-          const int i = w * tok_per_warp + j0 + b;
-          const int token = tok0 + i;
-          if (token < p.rows) {
-            fl_transform<LN>(regs[b], p, token, lane);
-            __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;
-            urow_minmax<FL_KB>(regs[b], mn2, mx2);
-            float mn, mx;
-            warp_minmax(mn2, mx2, mn, mx);
-            const RowStats st = make_stats(mn, mx, p.qmax);
-            const QuantConsts qc = make_consts(st.delta, st.zp, p.qmax);
-            const int rs = fl_quant_row(regs[b], panel_s, i, lane, qc);
-            if (lane == 0) {
-              rowp[i] = RowParam{st.delta, __float2int_rn(st.zp), rs, 0};
-              if (st.degenerate && p.status) atomicOr(p.status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
-              if (split == 0 && p.out_delta) {
-                p.out_delta[token] = __float2half_rn(st.delta);
-                p.out_zp[token] = __float2half_rn(st.zp);
-              }
-            }
-          } else {
-            fl_zero_row(panel_s, i, lane);
-            if (lane == 0) rowp[i] = RowParam{0.f, 0, 0, 0};
-          }
+      for (int b = 0; b < FL_ROWS_IN_FLIGHT; ++b) {
+        mn[b] = mx[b] = 0.f;
+        if (tokn[b] < p.rows) {
+          fl_transform<LN>(regs[b], p, grow[b], lane);
+          __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;   // the range always contains zero
+          urow_minmax<FL_KB>(regs[b], mn2, mx2);
+          warp_minmax(mn2, mx2, mn[b], mx[b]);
         }
       }
-    } else {
-      // pooled batches (quirk Q1): statistics of a token over its G batch entries, then one panel row per entry
-      for (int j = 0; j < tok_per_warp; ++j) {
-        const int tl = w * tok_per_warp + j;
-        const int token = tok0 + tl;
-        if (token < p.rows) {
-          UnitRegs<FL_KB> regs;
-          __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;
-          for (int g = 0; g < p.G; ++g) {
-            const int grow = g * p.rows + token;
-            uload_row<FL_KB>(regs, p.x + static_cast<size_t>(grow) * FL_K, lane);
-            fl_transform<LN>(regs, p, grow, lane);
-            urow_minmax<FL_KB>(regs, mn2, mx2);
-          }
-          float mn, mx;
-          warp_minmax(mn2, mx2, mn, mx);
-          const RowStats st = make_stats(mn, mx, p.qmax);
+      if (p.G == 2) {         // statistics pooled over the batch entries of a token (quirk Q1)
+        mn[0] = mn[1] = fminf(mn[0], mn[1]);  mx[0] = mx[1] = fmaxf(mx[0], mx[1]);
+        mn[2] = mn[3] = fminf(mn[2], mn[3]);  mx[2] = mx[3] = fmaxf(mx[2], mx[3]);
+      } else if (p.G == 4) {
+        mn[0] = mn[1] = mn[2] = mn[3] = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
+        mx[0] = mx[1] = mx[2] = mx[3] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      }
+#pragma unroll
+      for (int b = 0; b < FL_ROWS_IN_FLIGHT; ++b) {
+        if (tokn[b] < p.rows) {
+          const RowStats st = make_stats(mn[b], mx[b], p.qmax);
           const QuantConsts qc = make_consts(st.delta, st.zp, p.qmax);
-          for (int g = 0; g < p.G; ++g) {
-            const int grow = g * p.rows + token;
-            uload_row<FL_KB>(regs, p.x + static_cast<size_t>(grow) * FL_K, lane);
-            fl_transform<LN>(regs, p, grow, lane);
-            const int i = g * p.tpp + tl;
-            const int rs = fl_quant_row(regs, panel_s, i, lane, qc);
-            if (lane == 0) rowp[i] = RowParam{st.delta, __float2int_rn(st.zp), rs, 0};
-          }
+          const int rs = fl_quant_row(regs[b], panel_s, irow[b], lane, qc);
           if (lane == 0) {
+            rowp[irow[b]] = RowParam{st.delta, __float2int_rn(st.zp), rs, 0};
             if (st.degenerate && p.status) atomicOr(p.status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
-            if (split == 0 && p.out_delta) {
-              p.out_delta[token] = __float2half_rn(st.delta);
-              p.out_zp[token] = __float2half_rn(st.zp);
+            if (split == 0 && p.out_delta && grow[b] == tokn[b]) {      // once per token (batch entry 0)
+              p.out_delta[tokn[b]] = __float2half_rn(st.delta);
+              p.out_zp[tokn[b]] = __float2half_rn(st.zp);
             }
           }
         } else {
-          for (int g = 0; g < p.G; ++g) {
-            fl_zero_row(panel_s, g * p.tpp + tl, lane);
-            if (lane == 0) rowp[g * p.tpp + tl] = RowParam{0.f, 0, 0, 0};
-          }
+          fl_zero_row(panel_s, irow[b], lane);
+          if (lane == 0) rowp[irow[b]] = RowParam{0.f, 0, 0, 0};
         }
       }
     }
@@ -585,19 +561,33 @@ static bool fused_shape_supported(int G, int rows, int K) {
   return false;
 }
 
+// Which shapes vq_linear_w8a8 runs as the single fused kernel.  Measured on B200 (profiles/r02_s3_linear_bench.md): inside
+// a replayed CUDA graph the two-launch sequence wins at every size (9.0 vs 21.9 us at M = 109, 14.9 vs 35.7 us at M = 2048,
+// 68 vs 74 us at M = 16384) — the stand-alone quantise pass spreads its rows over 148 SMs x 32 warps with no redundancy,
+// the fused kernel's 8 producer warps per SM re-quantise the panel in every CTA that shares it and cannot overlap the
+// MMAs (one 147 KB panel per SM) — so the default is OFF; eager callers with single-panel problems may opt in.
+// mode: 0 never (default), 1 whenever the shape is supported, -1 up to max_m rows.  Env VQ_LINEAR_FUSED / VQ_LINEAR_FUSED_MAX_M
+// give the initial values.
+static int g_fused_mode = [] {
+  const char* e = getenv("VQ_LINEAR_FUSED");
+  return e ? atoi(e) : 0;
+}();
+static long long g_fused_max_m = [] {
+  const char* e = getenv("VQ_LINEAR_FUSED_MAX_M");
+  return e ? atoll(e) : 0LL;
+}();
+
+extern "C" int vq_linear_set_fused_policy(int mode, int64_t max_m) {
+  if (mode < -1 || mode > 1 || max_m < 0) return VQ_ERR_ARG;
+  g_fused_mode = mode;
+  g_fused_max_m = max_m;
+  return VQ_OK;
+}
+
 extern "C" int vq_linear_launch_count(int G, int rows, int K) {
   if (G <= 0 || rows <= 0 || K <= 0) return VQ_ERR_ARG;
-  // VQ_LINEAR_FUSED: "0" never, "1" whenever the shape is supported, unset: up to VQ_LINEAR_FUSED_MAX_M rows
-  static const int mode = [] {
-    const char* e = getenv("VQ_LINEAR_FUSED");
-    return e ? atoi(e) : -1;
-  }();
-  static const long long max_m = [] {
-    const char* e = getenv("VQ_LINEAR_FUSED_MAX_M");
-    return e ? atoll(e) : 8192LL;
-  }();
   const long long M = static_cast<long long>(G) * rows;
-  const bool fused = fused_shape_supported(G, rows, K) && mode != 0 && (mode == 1 || M <= max_m);
+  const bool fused = fused_shape_supported(G, rows, K) && g_fused_mode != 0 && (g_fused_mode == 1 || M <= g_fused_max_m);
   return fused ? 1 : 2;
 }
 

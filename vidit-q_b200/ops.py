@@ -335,6 +335,13 @@ def _workspace(nbytes, device):
     return buf
 
 
+def set_linear_fused_policy(mode=0, max_m=0):
+    """Which shapes linear_w8a8 runs as the single fused kernel: mode 0 never (default: quantise pass + GEMM measured faster
+    on B200 inside CUDA graphs), 1 every supported shape, -1 supported shapes up to max_m rows.  Returns the previous call's
+    arguments are not tracked: callers restore explicitly."""
+    _lib.check(_lib.lib().vq_linear_set_fused_policy(int(mode), int(max_m)), "vq_linear_set_fused_policy")
+
+
 def linear_launch_count(G, rows, K):
     """1 when vq_linear_w8a8 runs this shape as the single fused kernel, 2 for quantise pass + GEMM."""
     return _lib.lib().vq_linear_launch_count(G, rows, K)

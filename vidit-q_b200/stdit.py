@@ -351,9 +351,6 @@ class FusedBlocks:
         # VQ_SPATIAL_ATTN=sdpa runs the long spatial attention on the library flash kernel (torch SDPA -> cuDNN) instead of
         # vq_attn_spatial: the yardstick bench.py / tools/prof_kernels.py time the own kernel against, not a fallback
         self.own_spatial = os.environ.get("VQ_SPATIAL_ATTN", "own") != "sdpa"
-        # rows per L2-resident MLP chunk (0 = whole tensor at once); see _mlp_chunked
-        self.mlp_chunk = int(os.environ.get("VQ_MLP_CHUNK", "0"))
-        self._mlp_scratch = {}
 
     @staticmethod
     def _spatial_library(qkv, pj, scale, B, N, T, S, C, D, independent):
@@ -541,36 +538,7 @@ class FusedBlocks:
                                              n_bits=blk.mlp.fc1.act_quantizer.n_bits,
                                              smooth=getattr(fc1w, "smooth", None), rows_per_mod=N if independent else None)
             # GELU rides in fc2's quantise pass (HBM-bound, idle MUFU) instead of fc1's epilogue (epilogue-bound)
-            if self.mlp_chunk and independent and frames is None and blk.mlp.fc2.smooth_mode() in (None, "cached"):
-                self._mlp_chunked(blk, a, fc1w, xr, gate_mlp, B, N)
-                continue
             h = ops.gemm_w8a8(a, fc1w).view(B, N, -1)
             a = qi(blk.mlp.fc2, h, gelu=True)
             ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp, rows_per_gate=N, out=xr)
         return x
-
-    def _mlp_chunked(self, blk, a, fc1w, xr, gate_mlp, B, N):
-        """fc1 -> GELU + quantise -> fc2 in row chunks whose hidden tensor (4C fp16 per token) and fc2 codes stay in the
-        126 MB L2: every chunk reuses the SAME scratch buffers, so the 4C-wide hidden tensor — 302 MB written and read again
-        per block and step at 32768 tokens, a quarter of the block's HBM traffic — is produced and consumed in L2 and its
-        dirty lines are overwritten there by the next chunk instead of being written back.  Token-local kernels: the result
-        is bit-identical to the unchunked sequence (un-pooled statistics only: every row has its own scale)."""
-        fc2 = blk.mlp.fc2
-        pw2 = fc2.prepared_weight()
-        C4, rows = fc1w.N, self.mlp_chunk
-        key = (rows, C4, xr.device)
-        buf = self._mlp_scratch.get(key)
-        if buf is None:
-            buf = self._mlp_scratch[key] = (torch.empty(rows, C4, dtype=torch.float16, device=xr.device),
-                                            ops._alloc_act(1, rows, C4, xr.device))
-        h_buf, a2 = buf
-        nb2 = fc2.act_quantizer.n_bits
-        for b in range(B):
-            for r0 in range(b * N, (b + 1) * N, rows):
-                n = min(rows, (b + 1) * N - r0)
-                ac = ops.ActCodes(a.codes[r0:r0 + n], a.delta[r0:r0 + n], a.zp[r0:r0 + n], a.rowsum[r0:r0 + n], 1, n, a.K)
-                h = ops.gemm_w8a8(ac, fc1w, out=h_buf[:n])
-                a2c = ops.ActCodes(a2.codes[:n], a2.delta[:n], a2.zp[:n], a2.rowsum[:n], 1, n, C4)
-                ops.act_quant(h.view(1, n, C4), n_bits=nb2, smooth=getattr(pw2, "smooth", None), out=a2c, gelu=True)
-                ops.gemm_w8a8(a2c, pw2, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr[r0:r0 + n], gate=gate_mlp[b:b + 1],
-                              rows_per_gate=n, out=xr[r0:r0 + n])
