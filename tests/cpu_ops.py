@@ -100,5 +100,6 @@ def linear_w8a8(x, w, n_bits=8, smooth=None, ln=None, rows_per_mod=None, epi=ops
 
 def patch_ops(monkeypatch):
     for name, fn in (("prep_weight", prep_weight), ("act_quant", act_quant), ("act_quant_static", act_quant_static),
-                     ("col_absmax", col_absmax), ("gemm_w8a8", gemm_w8a8), ("linear_w8a8", linear_w8a8)):
+                     ("col_absmax", col_absmax), ("gemm_w8a8", gemm_w8a8), ("linear_w8a8", linear_w8a8),
+                     ("pack_u4", lambda w: w)):
         monkeypatch.setattr(ops, name, fn)
