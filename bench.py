@@ -420,6 +420,82 @@ def build_pixart(device, depth):
     return qnn, model
 
 
+def multi_gpu_selfcheck(dev, world, rank):
+    """Driver-visible multi-GPU parity record (the 2-GPU pytest cases skip on a 1-GPU box): on every pair of ranks (2i, 2i+1)
+    a small STDiT step (2 blocks, 16 frames of 32x32) run (a) as a cfg-branch pair, (b) frame-sharded over the pair — eagerly
+    and as CUDA-graph segments — must be BIT-IDENTICAL to the same step on one GPU.  Returns the all-ranks AND."""
+    import torch
+    import torch.distributed as dist
+    from viditq_b200 import ops, shard
+    from viditq_b200.qdiff import QuantModel
+    from viditq_b200.sampler import SpacedDDIM
+    from viditq_b200.stdit import STDiT
+    torch.manual_seed(11)
+    model = STDiT(input_size=(16, 32, 32), depth=2, hidden_size=HIDDEN, num_heads=HEADS).eval()
+    wq, aq = quant_cfgs(n_spatial=256)
+    qnn = QuantModel(model, wq, aq)
+    qnn.to(dev).half()
+    model.dtype = torch.float16
+    qnn.set_module_name_for_quantizer(module=qnn.model)
+    qnn.fp_layer_list = FP_LAYERS
+    qnn.init_weight_quant_params()
+    qnn.set_quant_init_done("weight")
+    qnn.set_quant_init_done("activation")
+    qnn.set_quant_state(True, True)
+    qnn.set_timestep_id_for_quantlayer(999.0)
+    g = torch.Generator().manual_seed(7)
+    z = torch.randn(1, 4, 16, 32, 32, generator=g).to(dev)
+    yc = torch.randn(1, 1, PROMPT_LEN, 4096, generator=g).to(dev)
+    yu = torch.randn(1, 1, PROMPT_LEN, 4096, generator=g).to(dev)
+    mask = torch.zeros(1, PROMPT_LEN, dtype=torch.int64)
+    mask[0, :77] = 1
+    mask = mask.to(dev)
+    ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
+    t1 = torch.full((1,), 999.0, device=dev)
+    coef = ddim.coefficients(ddim.num_timesteps - 1, "cpu").to(dev)
+    plan1 = model.mask_select_plan(mask)
+    seg1 = model.kv_segments(plan1[1], dev)
+    plan2 = model.mask_select_plan(mask.repeat(2, 1))
+    seg2 = model.kv_segments(plan2[1], dev)
+    pair = shard.cfg_pair_groups()
+    prank = rank % 2
+    y2 = torch.cat([yc, yu])
+    # single-GPU references
+    oc = model.forward_fused(z, t1, yc, plan=plan1, segments=seg1)
+    ou = model.forward_fused(z, t1, yu, plan=plan1, segments=seg1)
+    ref_step = ops.cfg_ddim_step(oc, ou, z, coef, ddim.cfg_scale)
+    ref_fwd = model.forward_fused(torch.cat([z, z]), t1.expand(2), y2, plan=plan2, segments=seg2, independent=True)
+
+    def branch_step():
+        mine = model.forward_fused(z, t1, yu if prank else yc, plan=plan1, segments=seg1)
+        a, b = shard.exchange_cfg_branches(mine, pair)
+        return ops.cfg_ddim_step(a, b, z, coef, ddim.cfg_scale)
+    f0, f1 = shard.frame_slice(16, 2, prank)
+    z_loc = z[:, :, f0:f1].contiguous()
+
+    def frames_fwd():
+        return model.forward_fused(torch.cat([z_loc, z_loc]), t1.expand(2), y2, plan=plan2, segments=seg2, independent=True,
+                                   frames=(pair, 2, prank))
+    res = {}
+    res["cfg_branch_bit_identical"] = bool(torch.equal(branch_step(), ref_step))
+    res["frames_bit_identical"] = bool(torch.equal(frames_fwd(), ref_fwd[:, :, f0:f1]))
+    sg = shard.SegmentedGraph()
+    out = sg.capture(frames_fwd)
+    sg.replay()
+    torch.cuda.synchronize()
+    res["frames_segmented_graph_bit_identical"] = bool(torch.equal(out, ref_fwd[:, :, f0:f1]))
+    sg2 = shard.SegmentedGraph()
+    out2 = sg2.capture(branch_step)
+    sg2.replay()
+    torch.cuda.synchronize()
+    res["cfg_branch_segmented_graph_bit_identical"] = bool(torch.equal(out2, ref_step))
+    flags = torch.tensor([int(v) for v in res.values()], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    out = {k: bool(v) for k, v in zip(res.keys(), flags.tolist())}
+    out["frames_graph_segments"], out["frames_nccl_calls"] = sg.counts()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------------
@@ -439,6 +515,7 @@ def main():
     ap.add_argument("--depth", type=int, default=DEPTH, help="debug only: fewer blocks (result is then NOT the metric)")
     ap.add_argument("--no-graph", action="store_true", help="debug: eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the multi-GPU bit-identity self-check (N >= 2)")
     ap.add_argument("--no-peak", action="store_true", help="skip the INT8 peak measurement (roofline then uses the proxy)")
     ap.add_argument("--cfg-mode", default="stacked", choices=["stacked", "split"],
                     help="cfg_split's cond / uncond forwards as one stacked launch sequence (default) or two calls")
@@ -639,10 +716,14 @@ def main():
     torch.cuda.synchronize()
     work = {k: tuple(v) for k, v in meter.work.items()}
 
-    graph = None
-    # steps with NCCL calls inside (cfg-branch / frames) are launched eagerly: capturing the torch.distributed calls in
-    # the step graph deadlocked on the 2-GPU box (both ranks hung in capture; measured once, not pursued)
-    if use_graph and not (pairs or fsh):
+    graph = seg_graph = None
+    # steps with NCCL calls inside (cfg-branch / frames): CUDA-graph SEGMENTS around eagerly issued collectives
+    # (shard.SegmentedGraph) — capturing the torch.distributed calls inside one whole-step graph deadlocked on the 2-GPU box
+    if use_graph and (pairs or fsh):
+        seg_graph = shard.SegmentedGraph()
+        d_out = seg_graph.capture(step_device)
+        torch.cuda.synchronize()
+    elif use_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -656,6 +737,9 @@ def main():
     def run_step():
         if graph is not None:
             graph.replay()
+            return d_out
+        if seg_graph is not None:
+            seg_graph.replay()
             return d_out
         return step_device()
 
@@ -717,10 +801,13 @@ def main():
     prof, busy_ms, span_ms = profile_kernels(run_step)
     int8_peak = None if (args.no_peak or rank != 0) else measure_int8_peak(dev)
 
+    parity = None
     if world > 1:
         tt = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = tt.tolist()
+        if world % 2 == 0 and wl == "stdit" and not args.no_selfcheck:
+            parity = multi_gpu_selfcheck(dev, world, rank)
     if rank == 0:
         n_samples = world // 2 if pairs else (1 if fsh else world)
         value = n_samples * args.steps / (ms * 1e-3)
@@ -753,7 +840,10 @@ def main():
                                        f"frame-sharded x{world}: {T_FRAMES // world} frames per rank, all-to-all of the "
                                        f"temporal branch's u8 codes per block" if fsh else
                                        f"sample-sharded x{world} (no data-path collective)"),
-                       "schedule": args.schedule, "cuda_graph": graph is not None, "depth": args.depth,
+                       "schedule": args.schedule,
+                       "cuda_graph": (graph is not None) or (seg_graph is not None and
+                                                             "%d graph segments around %d NCCL calls" % seg_graph.counts()),
+                       "depth": args.depth,
                        "cfg_mode": args.cfg_mode,
                        "l2": ("256 MB buffer written between timed iterations (working set fits the 126 MB L2)" if flush is not None
                               else "working set per step (0.74 GB weight codes + >1 GB activations) exceeds the 126 MB L2"),
@@ -765,6 +855,8 @@ def main():
             "roofline_kernels": roofs,
             "step_busy_ms_cupti": busy_ms, "step_span_ms_cupti": span_ms,
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
         if world == 1 and not args.no_cpu_baseline and wl in ("stdit", "w4a8mp"):
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)

@@ -77,8 +77,14 @@ def _worker(rank, world, port, ret):
     new = _one_step(model, ops, ddim, z, yu if shard.cfg_branch() else yc, mask, dev,
                     exchange=lambda o: shard.exchange_cfg_branches(o, grp))
     ref = _one_step(model, ops, ddim, z, (yc, yu), mask, dev) if rank == 0 else None
+    # the same pair step as CUDA-graph segments around the eagerly issued all_gather (shard.SegmentedGraph)
+    sg = shard.SegmentedGraph()
+    seg_out = sg.capture(lambda: _one_step(model, ops, ddim, z, yu if shard.cfg_branch() else yc, mask, dev,
+                                           exchange=lambda o: shard.exchange_cfg_branches(o, grp)))
+    sg.replay()
+    sg.replay()
     torch.cuda.synchronize()
-    ret[rank] = (new.cpu().numpy(), None if ref is None else ref.cpu().numpy())
+    ret[rank] = (new.cpu().numpy(), None if ref is None else ref.cpu().numpy(), seg_out.cpu().numpy(), sg.counts())
     dist.destroy_process_group()
 
 
@@ -91,12 +97,14 @@ def test_cfg_branch_pair_equals_single_gpu_step():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
-    new0, ref = ret[0]
-    new1, _ = ret[1]
+    new0, ref, seg0, counts = ret[0]
+    new1, _, seg1, _ = ret[1]
     import numpy as np
     assert np.isfinite(ref).all() and float(np.abs(ref).max()) > 0
     assert np.array_equal(new0, ref)       # the pair reproduces the single-GPU step bit for bit ...
     assert np.array_equal(new0, new1)      # ... on both ranks
+    assert counts == (2, 1)                # graph | all_gather | graph
+    assert np.array_equal(seg0, ref) and np.array_equal(seg1, ref)      # ... and so do the replayed graph segments
 
 
 def _frames_worker(rank, world, port, ret):
@@ -121,8 +129,13 @@ def _frames_worker(rank, world, port, ret):
     ref = None
     if rank == 0:
         ref = model.forward_fused(torch.cat([z, z]), t, y2, plan=plan, segments=seg, independent=True)
+    sg = shard.SegmentedGraph()
+    seg_out = sg.capture(lambda: model.forward_fused(torch.cat([z_loc, z_loc]), t, y2, plan=plan, segments=seg,
+                                                     independent=True, frames=(None, world, rank)))
+    sg.replay()
+    sg.replay()
     torch.cuda.synchronize()
-    ret[rank] = (out.cpu().numpy(), (t0, t1), None if ref is None else ref.cpu().numpy())
+    ret[rank] = (out.cpu().numpy(), (t0, t1), None if ref is None else ref.cpu().numpy(), seg_out.cpu().numpy(), sg.counts())
     dist.destroy_process_group()
 
 
@@ -142,6 +155,8 @@ def test_frame_sharded_forward_equals_single_gpu_forward():
     ref = ret[0][2]
     assert np.isfinite(ref).all() and float(np.abs(ref).max()) > 0
     for rank in range(2):
-        out, (t0, t1), _ = ret[rank]
+        out, (t0, t1), _, seg_out, counts = ret[rank]
         assert out.shape == ref[:, :, t0:t1].shape
         assert np.array_equal(out, ref[:, :, t0:t1]), rank
+        assert counts == (2 * 2 + 1, 2 * 2)       # two exchanges per block: 5 graph segments around 4 all-to-alls
+        assert np.array_equal(seg_out, ref[:, :, t0:t1]), rank   # replayed graph segments: same bits
