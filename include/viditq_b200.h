@@ -159,6 +159,16 @@ int vq_linear_w4a8(const void* x, int G, int rows, int K, const void* smooth, co
                    const void* res, int ldr, const void* gate, int rows_per_gate, void* out, int ldo, void* out_delta,
                    void* out_zp, uint32_t* status, void* stream);
 
+/* (section 8e (2), frame sharding) Pack / unpack the rows a frame-sharded forward exchanges around the temporal attention:
+ * per-token QUANTISED activations travel as K code bytes + a 16-byte tail {delta fp16, zp fp16, rowsum i32, pad}.  The rows
+ * form a 4-D array (d0, d1, d2, d3) in source order; the destination position of row (i0, i1, i2, i3) is
+ * i0 s0 + i1 s1 + i2 s2 + i3 s3 (strides in rows) — the "B (T S) <-> rank-major" permutations of the reference's
+ * sequence-parallel all-to-all (t2v/opensora/acceleration/communications.py) applied to codes instead of fp16 tensors.
+ * unpack == 0: src = codes u8 [rows, K], arrays read, dst = rows with tails [rows, K + 16];
+ * unpack != 0: src = rows with tails (source order), dst = codes u8 [rows, K], arrays written, all at the permuted position. */
+int vq_row_pack(const uint8_t* src, uint8_t* dst, void* delta, void* zp, int32_t* rowsum, int rows, int K, int d1, int d2,
+                int d3, int64_t s0, int64_t s1, int64_t s2, int64_t s3, int unpack, void* stream);
+
 /* (a9) temporal self-attention of STDiT (stdit.py:112-118, blocks.py:151-195 on "(B S) T C"), reading q|k|v in place
  * from the fused GEMM output qkv fp16 [B*T*S, 3*H*head_dim] in the (T S) token layout; out fp16 [B*T*S, H*head_dim].
  * head_dim must be 72, T <= 16. scale = head_dim^-0.5.                                                             */

@@ -14,7 +14,7 @@ VQ_STATUS_EPS_DEGENERATE = 1
 _ERR = {-1: "VQ_ERR_ARG", -2: "VQ_ERR_DRIVER", -3: "VQ_ERR_TMAP", -4: "VQ_ERR_LAUNCH", -5: "VQ_ERR_UNSUPPORTED"}
 
 EXPORTS = ["vq_version", "vq_num_sms", "vq_prep_weight", "vq_act_quant", "vq_act_quant_static", "vq_add_act_quant", "vq_gelu_act_quant", "vq_act_quant_heads", "vq_ln_modulate_act_quant", "vq_gemm_w8a8",
-           "vq_col_absmax", "vq_linear_w8a8", "vq_linear_workspace_bytes", "vq_linear_launch_count", "vq_linear_set_fused_policy", "vq_pack_u4", "vq_linear_w4a8",
+           "vq_col_absmax", "vq_row_pack", "vq_linear_w8a8", "vq_linear_workspace_bytes", "vq_linear_launch_count", "vq_linear_set_fused_policy", "vq_pack_u4", "vq_linear_w4a8",
            "vq_attn_temporal", "vq_attn_cross", "vq_attn_spatial", "vq_cfg_ddim_step", "vq_patch_embed", "vq_status_read"]
 
 _lib = None
@@ -45,6 +45,7 @@ def lib():
     L.vq_ln_modulate_act_quant.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.vq_gemm_w8a8.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
     L.vq_col_absmax.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.vq_row_pack.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i32, vp]
     L.vq_linear_workspace_bytes.argtypes = [i32, i32, i32]
     L.vq_linear_launch_count.argtypes = [i32, i32, i32]
     L.vq_linear_set_fused_policy.argtypes = [i32, i64]

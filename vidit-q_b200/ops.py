@@ -240,6 +240,31 @@ def col_absmax(x, gelu=False):
 
 
 @_nvtx
+def pack_rows(a: ActCodes, dims, strides):
+    """ActCodes (G == 1) -> u8 [rows, K + 16] exchange rows (codes + {delta, zp, rowsum} tail), row (i0, i1, i2, i3) of the
+    4-D source order `dims` written at position sum(i * stride)."""
+    rows, K = a.codes.shape[0], a.K
+    out = torch.empty((rows, K + 16), dtype=torch.uint8, device=a.codes.device)
+    rc = _lib.lib().vq_row_pack(_ptr(a.codes), _ptr(out), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum), rows, K, dims[1], dims[2],
+                                dims[3], strides[0], strides[1], strides[2], strides[3], 0, _stream())
+    _lib.check(rc, "vq_row_pack")
+    _count()
+    return out
+
+
+@_nvtx
+def unpack_rows(buf, K, dims, strides) -> ActCodes:
+    """Inverse of pack_rows on a received buffer: u8 [rows, K + 16] in source order `dims` -> ActCodes in the permuted order."""
+    rows = buf.shape[0]
+    a = _alloc_act(1, rows, K, buf.device)
+    rc = _lib.lib().vq_row_pack(_ptr(buf), _ptr(a.codes), _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum), rows, K, dims[1], dims[2],
+                                dims[3], strides[0], strides[1], strides[2], strides[3], 1, _stream())
+    _lib.check(rc, "vq_row_pack")
+    _count()
+    return a
+
+
+@_nvtx
 def act_quant_static(x, delta, zp, n_bits=8, smooth=None) -> ActCodes:
     """Static (calibrated) activation scales: x fp16 [..., K]; delta / zp: fp16 CUDA [period] (1 = per-tensor, the
     w8a8_naive.yaml case; rows = static per-token). Row m uses index m % period."""
