@@ -98,6 +98,47 @@ def linear_w8a8(x, w, n_bits=8, smooth=None, ln=None, rows_per_mod=None, epi=ops
                      out=out, ldo=ldo)
 
 
+def _row_positions(rows, dims, strides):
+    idx = np.arange(rows)
+    i3 = idx % dims[3]
+    q = idx // dims[3]
+    i2 = q % dims[2]
+    q = q // dims[2]
+    i1 = q % dims[1]
+    i0 = q // dims[1]
+    return i0 * strides[0] + i1 * strides[1] + i2 * strides[2] + i3 * strides[3]
+
+
+def pack_rows(a, dims, strides):
+    """numpy restatement of vq_row_pack (pack): codes + {delta, zp, rowsum} tail, rows scattered to the permuted position."""
+    rows, K = a.codes.shape[0], a.K
+    out = np.zeros((rows, K + 16), np.uint8)
+    pos = _row_positions(rows, dims, strides)
+    out[pos, :K] = a.codes.numpy()
+    tail = np.zeros((rows, 4), np.int32)
+    tail[:, 0] = (a.delta.numpy().view(np.uint16).astype(np.uint32) | (a.zp.numpy().view(np.uint16).astype(np.uint32) << 16)).view(np.int32)
+    tail[:, 1] = a.rowsum.numpy()
+    out[pos, K:] = tail.view(np.uint8).reshape(rows, 16)
+    return torch.from_numpy(out)
+
+
+def unpack_rows(buf, K, dims, strides):
+    b = buf.numpy()
+    rows = b.shape[0]
+    pos = _row_positions(rows, dims, strides)
+    codes = np.zeros((rows, K), np.uint8)
+    codes[pos] = b[:, :K]
+    tail = np.ascontiguousarray(b[:, K:]).view(np.int32).reshape(rows, 4)
+    dz = tail[:, 0].view(np.uint32)
+    delta = np.zeros(rows, np.float16)
+    zp = np.zeros(rows, np.float16)
+    rowsum = np.zeros(rows, np.int32)
+    delta[pos] = (dz & 0xffff).astype(np.uint16).view(np.float16)
+    zp[pos] = (dz >> 16).astype(np.uint16).view(np.float16)
+    rowsum[pos] = tail[:, 1]
+    return ops.ActCodes(torch.from_numpy(codes), torch.from_numpy(delta), torch.from_numpy(zp), torch.from_numpy(rowsum), 1, rows, K)
+
+
 def patch_ops(monkeypatch):
     for name, fn in (("prep_weight", prep_weight), ("act_quant", act_quant), ("act_quant_static", act_quant_static),
                      ("col_absmax", col_absmax), ("gemm_w8a8", gemm_w8a8), ("linear_w8a8", linear_w8a8),

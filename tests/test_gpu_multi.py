@@ -47,11 +47,15 @@ def _build(dev):
     return qnn, model
 
 
+_STEP_CONST = {}
+
+
 def _one_step(model, ops, ddim, z, y, mask, dev, exchange=None):
-    t = torch.full((1,), float(ddim.model_timestep(ddim.num_timesteps - 1)), device=dev)
-    coef = ddim.coefficients(ddim.num_timesteps - 1, "cpu").to(dev)
-    plan = model.mask_select_plan(mask)
-    seg = model.kv_segments(plan[1], dev)
+    if dev not in _STEP_CONST:       # host-side planning and H2D copies happen once, outside any graph capture
+        plan = model.mask_select_plan(mask)
+        _STEP_CONST[dev] = (torch.full((1,), float(ddim.model_timestep(ddim.num_timesteps - 1)), device=dev),
+                            ddim.coefficients(ddim.num_timesteps - 1, "cpu").to(dev), plan, model.kv_segments(plan[1], dev))
+    t, coef, plan, seg = _STEP_CONST[dev]
     if exchange is None:
         oc = model.forward_fused(z, t, y[0], plan=plan, segments=seg)
         ou = model.forward_fused(z, t, y[1], plan=plan, segments=seg)

@@ -106,7 +106,23 @@ def _frames_worker(rank, world, port, ret):
                and torch.equal(a_sp.rowsum, ids_sp * 3) and torch.equal(a_sp.codes, want_sp.to(torch.uint8)))
     a_fr = shard.exchange_act_codes(a_sp, B, T_loc, S, P, False)
     rt_ok = (torch.equal(a_fr.codes, a.codes) and torch.equal(a_fr.delta, a.delta) and torch.equal(a_fr.rowsum, a.rowsum))
-    ret[rank] = (torch.equal(sp, want_sp), torch.equal(back, local), meta_ok, rt_ok, a_sp.rows == B * T * Sp)
+    # the GPU path of the same exchange (vq_row_pack: rows packed straight into rank-major order, unpacked into the target
+    # order) with the kernel restated in numpy (tests/cpu_ops.py): identical layouts and scales
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import cpu_ops
+    from viditq_b200 import ops
+    ops.pack_rows, ops.unpack_rows = cpu_ops.pack_rows, cpu_ops.unpack_rows
+    K16 = 16
+    wide = torch.arange(rows * K16, dtype=torch.int64).view(rows, K16).remainder(251).to(torch.uint8) + local[:, :1].to(torch.uint8)
+    aw = ops.ActCodes(wide, a.delta, a.zp, a.rowsum.to(torch.int32), 1, rows, K16)
+    g_sp = shard._exchange_act_codes_cuda(aw, B, T_loc, S, P, True, None)
+    t_sp = shard.exchange_act_codes(A(wide, a.delta, a.zp, a.rowsum.to(torch.int32), 1, rows, K16), B, T_loc, S, P, True)
+    g_fr = shard._exchange_act_codes_cuda(g_sp, B, T_loc, S, P, False, None)
+    gpu_path_ok = (torch.equal(g_sp.codes, t_sp.codes) and torch.equal(g_sp.delta, t_sp.delta) and torch.equal(g_sp.zp, t_sp.zp)
+                   and torch.equal(g_sp.rowsum, t_sp.rowsum) and torch.equal(g_fr.codes, wide) and torch.equal(g_fr.delta, a.delta)
+                   and torch.equal(g_fr.rowsum, a.rowsum.to(torch.int32)))
+    ret[rank] = (torch.equal(sp, want_sp), torch.equal(back, local), meta_ok, rt_ok, a_sp.rows == B * T * Sp, gpu_path_ok)
     dist.destroy_process_group()
 
 

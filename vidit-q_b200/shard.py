@@ -223,7 +223,8 @@ def _exchange_act_codes_cuda(a, B, T_loc, S, P, to_spatial, group):
     received rows into the target order — one pass each at HBM speed (the torch path below costs five strided byte copies
     per exchange: 8 of the 30 ms of a frame-sharded step at P = 2)."""
     from . import ops
-    Sp, n = S // P, B * T_loc * Sp            # rows per (source, destination) rank pair
+    Sp = S // P
+    n = B * T_loc * Sp                        # rows per (source, destination) rank pair
     if to_spatial:
         # local (b, t_loc, p, s') -> send [p, b, t_loc, s'];  recv [r, b, t_loc, s'] -> (b, frame = r T_loc + t_loc, s')
         send = ops.pack_rows(a, (B, T_loc, P, Sp), (T_loc * Sp, Sp, n, 1))
