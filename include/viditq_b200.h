@@ -174,6 +174,15 @@ int vq_row_pack(const uint8_t* src, uint8_t* dst, void* delta, void* zp, int32_t
  * head_dim must be 72, T <= 16. scale = head_dim^-0.5.                                                             */
 int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S, int H, int head_dim, float scale, void* stream);
 
+/* (a9 + a1) vq_attn_temporal with the DynamicActQuantizer of attn_temp.proj fused behind it (stdit.py:112-118 ->
+ * stdit_quant_layer.py:155-165 on the "(B S) T C" view): one block owns all H = 16 heads of a (batch, position), so the token
+ * rows it produces are complete and are quantised in place — u8 codes [B*T*S, 1152] + delta / zp fp16 [B*T*S] + rowsum i32,
+ * every token on its own statistics (un-pooled: B == 1, or stacked independent calls).  Bit-identical to vq_attn_temporal
+ * followed by vq_act_quant; the fp16 attention output is never written.  head_dim 72, H = 16, T <= 16.                     */
+int vq_attn_temporal_quant(const void* qkv, int B, int T, int S, int H, int head_dim, float scale, const void* smooth,
+                           int n_bits, uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* status,
+                           void* stream);
+
 /* (a9) spatial self-attention of STDiT (stdit.py:104-109, blocks.py:151-195 on "(B T) S C"; the reference calls
  * flash-attn / xformers there) and PixArt (PixArt_blocks.py AttentionKVCompress, sr_ratio 1): n_seq independent sequences
  * of S tokens, q|k|v read in place from the fused GEMM output qkv fp16 [n_seq*S, 3*H*head_dim]; out fp16

@@ -447,3 +447,24 @@ def test_add_act_quant_equals_add_then_quant(ops, G, T, S, smooth):
     b = ops.act_quant(xt, smooth=sm)
     for u, v in ((a.codes, b.codes), (a.delta, b.delta), (a.zp, b.zp), (a.rowsum, b.rowsum)):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("B,T,S", [(1, 16, 256), (2, 16, 64), (1, 4, 64), (2, 7, 33)])
+def test_temporal_attention_with_fused_quantiser_is_bit_identical(B, T, S):
+    """vq_attn_temporal_quant (one block = all 16 heads of a position; the projection's per-token quantiser fused behind
+    the attention) against vq_attn_temporal -> vq_act_quant: same codes, delta, zero points and row sums."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from viditq_b200 import ops
+    H, D = 16, 72
+    g = torch.Generator().manual_seed(B * 100 + T + S)
+    qkv = (torch.randn(B * T * S, 3 * H * D, generator=g) * 1.3).half().cuda()
+    qkv[:, 5] *= 6
+    o = ops.attn_temporal(qkv, B, T, S, H, D, D ** -0.5)
+    for n_bits, smooth in ((8, None), (6, (torch.rand(H * D, generator=g) + 0.5).half().cuda())):
+        ref = ops.act_quant(o.view(1, -1, H * D), n_bits=n_bits, smooth=smooth)
+        got = ops.attn_temporal_quant(qkv, B, T, S, H, D, D ** -0.5, n_bits=n_bits, smooth=smooth)
+        torch.cuda.synchronize()
+        assert torch.equal(got.codes, ref.codes) and torch.equal(got.delta, ref.delta)
+        assert torch.equal(got.zp, ref.zp) and torch.equal(got.rowsum, ref.rowsum)
+    assert ops.check_status() == 0

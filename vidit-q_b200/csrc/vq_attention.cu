@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "vq_internal.h"
+#include "vq_quant_common.cuh"
 
 namespace vq {
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ void load_tile(__half* dst, const __half* src, long l
 // One warp: 16 query rows in sQ (rows >= nq are zero), keys/values in sK/sV (rows >= lk zero), processed in chunks of
 // CK*16 keys with online softmax (running max / sum, accumulator rescale). Result rows [0, nq) are written to global
 // through sQ as staging.
-template <int CK>
+template <int CK, bool STORE = true>
 __device__ __forceinline__ void warp_attend(__half* sQ, const __half* sK, const __half* sV, int lk, float scale_log2e,
                                             __half* out, long long ostride, int nq, int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -169,6 +170,7 @@ __device__ __forceinline__ void warp_attend(__half* sQ, const __half* sK, const 
     *reinterpret_cast<uint32_t*>(sQ + (g + 8) * PITCH + n * 8 + 2 * t) = pack_h2(o[n][2] * i1, o[n][3] * i1);
   }
   __syncwarp();
+  if (!STORE) return;      // the caller consumes the normalised fp16 rows from sQ (fused quantiser)
   for (int c = lane; c < 16 * 9; c += 32) {
     const int r = c / 9, cc = c % 9;
     if (r < nq) *(reinterpret_cast<uint4*>(out + r * ostride) + cc) = *reinterpret_cast<const uint4*>(sQ + r * PITCH + cc * 8);
@@ -219,6 +221,86 @@ __global__ void __launch_bounds__(TEMPORAL_WARPS * 32) vq_attn_temporal_kernel(c
   cp_async_wait_all();
   __syncwarp();
   warp_attend<1>(sQ, sK, sV, a.T, a.scale_log2e, a.out + tok0 * C + h * HD, static_cast<long long>(a.S) * C, a.T, lane);
+}
+
+// ------------------------------------------------------------------------------------------------- temporal + quantiser
+// Temporal attention with the projection's DynamicActQuantizer (a1) fused behind it: one 16-warp block owns ONE (batch,
+// spatial position) — all H = 16 heads x all T <= 16 frames — so the T token rows it produces are complete (1152 channels)
+// inside the block: after the attention every warp takes one token row out of the 16 heads' shared-memory tiles, computes
+// its min / max, and writes u8 codes + (delta, zp, code sum).  The fp16 attention output (75 MB per launch at 32768 tokens)
+// and the separate quantise pass that re-read it never exist; codes are bit-identical to vq_attn_temporal -> vq_act_quant.
+struct TemporalQArgs {
+  const __half* qkv;
+  int B, T, S;
+  float scale_log2e;
+  const __half* smooth;    // [1152] or null
+  float qmax;
+  uint8_t* codes;          // [B*T*S, 1152], (T S) token order
+  __half* delta;           // [B*T*S]
+  __half* zp;
+  int32_t* rowsum;
+  uint32_t* status;
+};
+
+constexpr int TQ_HEADS = 16;
+
+__global__ void __launch_bounds__(TQ_HEADS * 32, 1) vq_attn_temporal_quant_kernel(const TemporalQArgs a) {
+  grid_dep_sync();
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* tiles = reinterpret_cast<__half*>(smem_attn);
+  __half* sQ = tiles + warp * 3 * 16 * PITCH;
+  __half* sK = sQ + 16 * PITCH;
+  __half* sV = sK + 16 * PITCH;
+  const int sidx = static_cast<int>(blockIdx.x % a.S);
+  const int b = static_cast<int>(blockIdx.x / a.S);
+  const int h = warp;
+  constexpr int C = TQ_HEADS * HD;
+  const long long tok0 = static_cast<long long>(b) * a.T * a.S + sidx;   // token (b, t = 0, s)
+  const long long rstride = static_cast<long long>(a.S) * 3 * C;
+  const __half* q = a.qkv + tok0 * 3 * C + h * HD;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int c = lane + 32 * i;
+    const int r = c / 10, cc = c - r * 10;
+    const bool real = cc < 9 && r < a.T;
+    const long long goff = real ? r * rstride + cc * 8 : 0;
+    const int soff = r * PITCH + cc * 8;
+    const int nbytes = real ? 16 : 0;
+    cp_async16(sQ + soff, q + goff, nbytes);
+    cp_async16(sK + soff, q + C + goff, nbytes);
+    cp_async16(sV + soff, q + 2 * C + goff, nbytes);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  warp_attend<1, false>(sQ, sK, sV, a.T, a.scale_log2e, nullptr, 0, a.T, lane);
+  __syncthreads();      // every head's normalised rows are in its sQ tile
+  // ---- warp t quantises token row (b, t, s): unit u = lane + 32 i (4 halves) belongs to head u / 18
+  const int t = warp;
+  if (t >= a.T) return;
+  UnitRegs<9> regs;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int u = lane + 32 * i;
+    const int head = u / 18, w = u - head * 18;
+    regs.u[i] = *reinterpret_cast<const uint2*>(tiles + head * 3 * 16 * PITCH + t * PITCH + w * 4);
+  }
+  if (a.smooth) uapply_smooth<9>(regs, a.smooth, lane);
+  __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;   // the range always contains zero
+  urow_minmax<9>(regs, mn2, mx2);
+  float mn, mx;
+  warp_minmax(mn2, mx2, mn, mx);
+  const RowStats st = make_stats(mn, mx, a.qmax);
+  const QuantConsts qc = make_consts(st.delta, st.zp, a.qmax);
+  const long long m = tok0 + static_cast<long long>(t) * a.S;
+  int sum = uquant_store_row<9>(regs, a.codes + m * C, lane, qc);
+  sum = warp_sum_i(sum);
+  if (lane == 0) {
+    a.delta[m] = __float2half_rn(st.delta);
+    a.zp[m] = __float2half_rn(st.zp);
+    a.rowsum[m] = sum;
+    if (st.degenerate && a.status) atomicOr(a.status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------- cross
@@ -296,6 +378,30 @@ extern "C" int vq_attn_temporal(const void* qkv, void* out, int B, int T, int S,
   }
   const unsigned grid = static_cast<unsigned>((units + TEMPORAL_WARPS - 1) / TEMPORAL_WARPS);
   launch_pdl(vq_attn_temporal_kernel, dim3(grid), dim3(TEMPORAL_WARPS * 32), smem, static_cast<cudaStream_t>(stream), a);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+extern "C" int vq_attn_temporal_quant(const void* qkv, int B, int T, int S, int H, int head_dim, float scale,
+                                      const void* smooth, int n_bits, uint8_t* codes, void* delta, void* zp,
+                                      int32_t* rowsum, uint32_t* status, void* stream) {
+  using namespace vq;
+  if (!qkv || !codes || !delta || !zp || !rowsum || B <= 0 || S <= 0) return VQ_ERR_ARG;
+  if (head_dim != HD || H != TQ_HEADS || T <= 0 || T > 16 || n_bits < 2 || n_bits > 8) return VQ_ERR_UNSUPPORTED;
+  TemporalQArgs a{static_cast<const __half*>(qkv), B, T, S, scale * 1.4426950408889634f, static_cast<const __half*>(smooth),
+                  static_cast<float>((1 << n_bits) - 1), codes, static_cast<__half*>(delta), static_cast<__half*>(zp),
+                  rowsum, status};
+  const int smem = TQ_HEADS * 3 * 16 * PITCH * 2;
+  static bool attr_dev[kMaxDevices] = {};
+  bool& attr = attr_dev[current_device()];
+  if (!attr) {
+    if (cudaFuncSetAttribute(vq_attn_temporal_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return VQ_ERR_LAUNCH;
+    attr = true;
+  }
+  const long long blocks = static_cast<long long>(B) * S;
+  if (blocks > 0x7fffffffLL) return VQ_ERR_ARG;
+  launch_pdl(vq_attn_temporal_quant_kernel, dim3(static_cast<unsigned>(blocks)), dim3(TQ_HEADS * 32), smem,
+             static_cast<cudaStream_t>(stream), a);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 

@@ -35,6 +35,7 @@ struct ActQuantArgs {
   int head_S;            // > 0: x is head-major [G*rows / head_S, H, head_S, 72] (attention output), H = K / 72
   const __half* addv;    // optional [add_period, K]: row r is quantised as h(x + addv[(r / rows_per_add) % add_period])
   int rows_per_add, add_period;
+  int reverse;           // consume rows last-first (L2 reuse of the producer's tail); results do not depend on it
   float qmax;
   uint8_t* codes;
   __half* delta;
@@ -172,14 +173,18 @@ __global__ void __launch_bounds__(256, PF ? 3 : 4) vq_act_quant_unit_kernel(cons
   grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int wstride = gridDim.x * (blockDim.x >> 5);
-  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= a.rows) return;
+  int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= a.rows) return;
+  // a.reverse: rows are consumed LAST FIRST — the producer kernel wrote the tensor front to back, so its tail is what
+  // still sits in the 126 MB L2 when this pass starts; reading forwards would evict that tail before reaching it
+  const int rlast = a.rows - 1;
   UnitRegs<U> regs, nxt;
-  if (PF && a.G == 1) uload_any<U, HEADS>(regs, a, 0, r, lane);
-  for (; r < a.rows; r += wstride) {
-    const bool has_next = PF && a.G == 1 && r + wstride < a.rows;
+  if (PF && a.G == 1) uload_any<U, HEADS>(regs, a, 0, a.reverse ? rlast - q : q, lane);
+  for (; q < a.rows; q += wstride) {
+    const int r = a.reverse ? rlast - q : q;
+    const bool has_next = PF && a.G == 1 && q + wstride < a.rows;
     if (!PF && a.G == 1) uload_any<U, HEADS>(regs, a, 0, r, lane);
-    if (has_next) uload_any<U, HEADS>(nxt, a, 0, r + wstride, lane);   // prefetch
+    if (has_next) uload_any<U, HEADS>(nxt, a, 0, a.reverse ? rlast - (q + wstride) : q + wstride, lane);   // prefetch
     __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
     if (a.G == 1) {
       utransform<U, LN>(regs, a, 0, r, lane);
@@ -247,8 +252,9 @@ __global__ void __launch_bounds__(256, OCC) vq_act_quant_seg_kernel(const ActQua
   __shared__ int s_sum[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rl = warp / WPR, seg = warp - rl * WPR;
-  const int r = blockIdx.x * RPB + rl;
-  const bool ok = r < a.rows;
+  const int r0 = blockIdx.x * RPB + rl;
+  const bool ok = r0 < a.rows;
+  const int r = (ok && a.reverse) ? a.rows - 1 - r0 : r0;   // last rows first: the producer's tail is what is still in L2
   UnitRegs<9> regs;
   __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;  // the range always contains zero
   if (ok) {
@@ -291,7 +297,14 @@ __global__ void __launch_bounds__(256, OCC) vq_act_quant_seg_kernel(const ActQua
 }
 
 template <bool LN, bool GELU = false>
-static int launch_act_quant(const ActQuantArgs& a, cudaStream_t st) {
+static int launch_act_quant(const ActQuantArgs& a_in, cudaStream_t st) {
+  // VQ_AQ_REVERSE=0: consume rows front to back (A/B knob; default: last rows first)
+  static const int reverse = [] {
+    const char* e = getenv("VQ_AQ_REVERSE");
+    return e ? atoi(e) : 1;
+  }();
+  ActQuantArgs a = a_in;
+  a.reverse = reverse;
   const int nchunk = a.K >> 3;
   const int maxc = (nchunk + 31) / 32;
   const int warps = 8;

@@ -439,6 +439,28 @@ def attn_temporal(qkv, B, T, S, H, head_dim, scale, out=None):
     return out
 
 
+def attn_temporal_quant_supported(T, H, head_dim):
+    return head_dim == 72 and H == 16 and 0 < T <= 16
+
+
+@_nvtx
+def attn_temporal_quant(qkv, B, T, S, H, head_dim, scale, n_bits=8, smooth=None) -> ActCodes:
+    """attn_temporal + the per-token dynamic quantiser of the projection in one kernel: qkv fp16 [B*T*S, 3*H*head_dim] ->
+    ActCodes of the attention output in (T S) token order (G = 1: every token on its own statistics)."""
+    _need_cuda_f16(qkv, "qkv")
+    C = H * head_dim
+    if qkv.shape != (B * T * S, 3 * C):
+        raise _lib.VqError(f"attn_temporal_quant: qkv shape {tuple(qkv.shape)} != {(B * T * S, 3 * C)}")
+    if smooth is not None:
+        _need_cuda_f16(smooth, "smooth")
+    a = _alloc_act(1, B * T * S, C, qkv.device)
+    rc = _lib.lib().vq_attn_temporal_quant(_ptr(qkv), B, T, S, H, head_dim, float(scale), _ptr(smooth), n_bits, _ptr(a.codes),
+                                           _ptr(a.delta), _ptr(a.zp), _ptr(a.rowsum), _ptr(status_word(qkv.device)), _stream())
+    _lib.check(rc, "vq_attn_temporal_quant")
+    _count()
+    return a
+
+
 @_nvtx
 def attn_spatial(qkv, n_seq, S, H, head_dim, scale, out=None):
     """qkv: fp16 [n_seq*S, 3*H*head_dim] (fused q|k|v GEMM output; n_seq = B*T frames of S tokens) -> fp16

@@ -351,6 +351,8 @@ class FusedBlocks:
         # VQ_SPATIAL_ATTN=sdpa runs the long spatial attention on the library flash kernel (torch SDPA -> cuDNN) instead of
         # vq_attn_spatial: the yardstick bench.py / tools/prof_kernels.py time the own kernel against, not a fallback
         self.own_spatial = os.environ.get("VQ_SPATIAL_ATTN", "own") != "sdpa"
+        # VQ_TEMPORAL_FUSED_QUANT=0: temporal attention and the projection's quantiser as two kernels (A/B knob)
+        self.temporal_fused_quant = os.environ.get("VQ_TEMPORAL_FUSED_QUANT", "1") != "0"
 
     @staticmethod
     def _spatial_library(qkv, pj, scale, B, N, T, S, C, D, independent):
@@ -499,8 +501,12 @@ class FusedBlocks:
                      else ops.act_quant(x1, n_bits=nb))
                 a = shard.exchange_act_codes(a, B, T, S, P, True, grp)
                 qkv = ops.gemm_w8a8(a, pw_t)
-                o = ops.attn_temporal(qkv, B, T * P, S // P, H, D, blk.attn_temp.scale)
-                a = ops.act_quant(o.view(1, -1, C), n_bits=blk.attn_temp.proj.act_quantizer.n_bits)
+                nbp = blk.attn_temp.proj.act_quantizer.n_bits
+                if self.temporal_fused_quant and ops.attn_temporal_quant_supported(T * P, H, D):
+                    a = ops.attn_temporal_quant(qkv, B, T * P, S // P, H, D, blk.attn_temp.scale, n_bits=nbp)
+                else:
+                    o = ops.attn_temporal(qkv, B, T * P, S // P, H, D, blk.attn_temp.scale)
+                    a = ops.act_quant(o.view(1, -1, C), n_bits=nbp)
                 a = shard.exchange_act_codes(a, B, T, S, P, False, grp)
                 ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr,
                               gate=gate_msa, rows_per_gate=N, out=xr)
@@ -509,7 +515,16 @@ class FusedBlocks:
             else:
                 xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
                 qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt, independent=independent)
-            if frames is None:
+            pjt = blk.attn_temp.proj
+            if (frames is None and self.temporal_fused_quant and (independent or B == 1)
+                    and ops.attn_temporal_quant_supported(T, H, D) and pjt.smooth_mode() in (None, "cached")):
+                # temporal attention + the projection's quantiser in ONE kernel (all 16 heads of a position in one block):
+                # no fp16 attention output, no separate quantise pass
+                pwt = pjt.prepared_weight()
+                a = ops.attn_temporal_quant(qkv, B, T, S, H, D, blk.attn_temp.scale, n_bits=pjt.act_quantizer.n_bits,
+                                            smooth=getattr(pwt, "smooth", None))
+                ops.gemm_w8a8(a, pwt, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
+            elif frames is None:
                 if T <= 16 and D == 72:      # own kernel: reads the (T S) layout in place, no permute copies
                     o = ops.attn_temporal(qkv, B, T, S, H, D, blk.attn_temp.scale).view(B, N, C)
                 else:                        # library path for shapes the kernel does not cover
