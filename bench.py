@@ -212,7 +212,7 @@ KERNEL_CLASSES = [
     ("gemm", r"vq_gemm_w8a8_kernel|vq_linear_fused_kernel", "tensor"),
     ("quant", r"vq_act_quant|vq_col_absmax", "hbm"),
     ("attn_tc", r"vq_attn_spatial_kernel", "tensor"),
-    ("attn_small", r"vq_attn_temporal_kernel|vq_attn_cross_kernel", "hbm"),
+    ("attn_small", r"vq_attn_temporal|vq_attn_cross_kernel", "hbm"),
     ("embed_sampler", r"vq_patch_embed_kernel|vq_cfg_ddim_kernel", "hbm"),
 ]
 
@@ -295,6 +295,8 @@ class WorkMeter:
         wrap("attn_cross", lambda q, kv, ks, kl, B, N, H, D, max_len, scale, **k: me.add(
             "attn_tc" if N % 256 == 0 else "attn_small", 1, 4.0 * N * kv.shape[0] * H * D, 4 * B * N * H * D + 2 * kv.numel()))
         wrap("attn_temporal", lambda qkv, B, T, S, H, D, scale, **k: me.add("attn_small", 1, 4.0 * B * S * H * T * T * D, 8 * B * T * S * H * D))
+        wrap("attn_temporal_quant", lambda qkv, B, T, S, H, D, scale, **k: me.add("attn_small", 1, 4.0 * B * S * H * T * T * D,
+                                                                                    7 * B * T * S * H * D + 8 * B * T * S))
         wrap("patch_embed", lambda latent, weight, *a, **k: me.add("embed_sampler", 1, 0, 4 * latent.numel() + 2 * (latent.numel() // (latent.shape[1] * 4)) * weight.shape[0]))
         wrap("cfg_ddim_step", lambda oc, ou, x, *a, **k: me.add("embed_sampler", 1, 0, 8 * oc.numel() + 8 * x.numel()))
         return self
