@@ -14,10 +14,10 @@ run() { echo "=== $*"; timeout 900 "$@" 2>&1 | grep -E "ERROR SUMMARY|passed|fai
 race() {
   tag=$1; shift
   echo "=== racecheck $*"
-  timeout 900 $CS --tool racecheck --racecheck-report hazard --print-limit 100000 "$@" > gpurun_out/racecheck_$tag.log 2>&1
-  echo "rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed|mismatches" gpurun_out/racecheck_$tag.log | tail -3
+  timeout 900 $CS --tool racecheck --racecheck-report hazard --print-limit 100000 "$@" > /tmp/racecheck_$tag.log 2>&1
+  echo "rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed|mismatches" /tmp/racecheck_$tag.log | tail -3
   # distinct hazard kinds: "<type> | writer file:line | reader file:line"
-  awk '/hazard detected/ {t=$4} /Write Thread/ {w=$NF} /Read Thread/ {print t " | write " w " | read " $NF}' gpurun_out/racecheck_$tag.log \
+  awk '/hazard detected/ {t=$4} /Write Thread/ {w=$NF} /Read Thread/ {print t " | write " w " | read " $NF}' /tmp/racecheck_$tag.log \
     | sort | uniq -c | sort -rn | head -30
 }
 run $CS --tool memcheck --error-exitcode 9 tools/gemm_selftest

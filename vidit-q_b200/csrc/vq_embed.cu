@@ -17,7 +17,7 @@
 namespace vq {
 
 constexpr int PE_MAXK = 16;          // in_channels * patch_h * patch_w
-constexpr int PE_TOKENS = 16;        // tokens per chunk; persistent CTAs walk chunks blockIdx.x, + gridDim.x, ...
+constexpr int PE_TOKENS = 64;        // tokens per CTA
 constexpr int PE_CPT = 4;            // channels per thread
 
 struct PatchEmbedArgs {
@@ -29,90 +29,89 @@ struct PatchEmbedArgs {
   int B, Cin, T, Hh, Ww, ph, pw, C;
 };
 
-// Round 2: persistent CTAs (two per SM) that load their 4 x 16 weights once and walk 16-token chunks (2048 chunks over 296
-// CTAs: 99 % balanced; round 1 launched 512 CTAs of 64 tokens = 3.46 waves), and the 64 multiply-adds per token and thread
-// issued as 32 packed FFMA2 (two channels per instruction; same sequential fp32 sums, bit-identical): the kernel was
-// instruction-bound at 64 us for a 75 MB write.
-__global__ void __launch_bounds__(320, 2) vq_patch_embed_kernel(const PatchEmbedArgs a) {
+__global__ void __launch_bounds__(320) vq_patch_embed_kernel(const PatchEmbedArgs a) {
   grid_dep_sync();
-  __shared__ __align__(16) float patch[2][PE_TOKENS][PE_MAXK];
+  __shared__ __align__(16) float patch[PE_TOKENS][PE_MAXK];
   const int gw = a.Ww / a.pw, gh = a.Hh / a.ph;
   const int S = gh * gw;
   const int K = a.Cin * a.ph * a.pw;
   const long long M = static_cast<long long>(a.B) * a.T * S;
-  const long long n_chunks = (M + PE_TOKENS - 1) / PE_TOKENS;
+  const long long tok0 = static_cast<long long>(blockIdx.x) * PE_TOKENS;
+  // gather the patches of this CTA's tokens (fp32 latent -> fp16 rounding, as x.to(dtype) does)
+  for (int i = threadIdx.x; i < PE_TOKENS * K; i += blockDim.x) {
+    const int tl = i / K, k = i - tl * K;
+    const long long tok = tok0 + tl;
+    float v = 0.f;
+    if (tok < M) {
+      const int s = static_cast<int>(tok % S);
+      const long long bt = tok / S;
+      const int t = static_cast<int>(bt % a.T);
+      const int b = static_cast<int>(bt / a.T);
+      const int ci = k / (a.ph * a.pw), r = k - ci * (a.ph * a.pw);
+      const int dy = r / a.pw, dx = r - dy * a.pw;
+      const int hy = s / gw, wx = s - hy * gw;
+      const long long off = (((static_cast<long long>(b) * a.Cin + ci) * a.T + t) * a.Hh + hy * a.ph + dy) * a.Ww + wx * a.pw + dx;
+      v = __half2float(__float2half_rn(__ldg(a.latent + off)));
+    }
+    patch[tl][k] = v;
+  }
   const int c0 = threadIdx.x * PE_CPT;
   const bool active = c0 < a.C;
-  // weights of this thread's 4 channels as channel PAIRS: w2[p][k] = {w[2p][k], w[2p+1][k]}
-  float2 w2[PE_CPT / 2][PE_MAXK];
-  float2 bias2[PE_CPT / 2];
+  float w[PE_CPT][PE_MAXK];
+  float bias[PE_CPT];
   if (active) {
 #pragma unroll
     for (int j = 0; j < PE_CPT; ++j) {
-      const float bj = a.bias ? __half2float(a.bias[c0 + j]) : 0.f;
-      if (j & 1) bias2[j >> 1].y = bj;
-      else bias2[j >> 1].x = bj;
+      bias[j] = a.bias ? __half2float(a.bias[c0 + j]) : 0.f;
+      if (K == PE_MAXK) {   // the thread's 4 x 16 weights are 128 contiguous bytes: 16-byte loads
+        const uint4* wp = reinterpret_cast<const uint4*>(a.weight + static_cast<size_t>(c0 + j) * PE_MAXK);
 #pragma unroll
-      for (int k = 0; k < PE_MAXK; ++k) {
-        const float wv = k < K ? __half2float(__ldg(a.weight + static_cast<size_t>(c0 + j) * K + k)) : 0.f;
-        if (j & 1) w2[j >> 1][k].y = wv;
-        else w2[j >> 1][k].x = wv;
+        for (int v = 0; v < 2; ++v) {
+          const uint4 wv = __ldg(wp + v);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            w[j][v * 8 + 2 * e] = f.x;
+            w[j][v * 8 + 2 * e + 1] = f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PE_MAXK; ++k) w[j][k] = k < K ? __half2float(a.weight[static_cast<size_t>(c0 + j) * K + k]) : 0.f;
       }
     }
   }
-  int buf = 0;
-  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, buf ^= 1) {
-    const long long tok0 = chunk * PE_TOKENS;
-    // gather the patches of this chunk's tokens (fp32 latent -> fp16 rounding, as x.to(dtype) does); double-buffered so one
-    // barrier per chunk suffices
-    for (int i = threadIdx.x; i < PE_TOKENS * K; i += blockDim.x) {
-      const int tl = i / K, k = i - tl * K;
-      const long long tok = tok0 + tl;
-      float v = 0.f;
-      if (tok < M) {
-        const int s = static_cast<int>(tok % S);
-        const long long bt = tok / S;
-        const int t = static_cast<int>(bt % a.T);
-        const int b = static_cast<int>(bt / a.T);
-        const int ci = k / (a.ph * a.pw), r = k - ci * (a.ph * a.pw);
-        const int dy = r / a.pw, dx = r - dy * a.pw;
-        const int hy = s / gw, wx = s - hy * gw;
-        const long long off = (((static_cast<long long>(b) * a.Cin + ci) * a.T + t) * a.Hh + hy * a.ph + dy) * a.Ww + wx * a.pw + dx;
-        v = __half2float(__float2half_rn(__ldg(a.latent + off)));
-      }
-      patch[buf][tl][k] = v;
-    }
-    __syncthreads();
-    if (!active) continue;
-    const int ntok = static_cast<int>(M - tok0 < PE_TOKENS ? M - tok0 : PE_TOKENS);
-    int s_idx = static_cast<int>(tok0 % S);   // spatial position of the token, kept incrementally (no division in the loop)
-    __half* orow = a.out + static_cast<size_t>(tok0) * a.C + c0;
-    for (int tl = 0; tl < ntok; ++tl, orow += a.C) {
-      float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+  __syncthreads();
+  if (!active) return;
+  const int ntok = static_cast<int>(M - tok0 < PE_TOKENS ? M - tok0 : PE_TOKENS);
+  int s_idx = static_cast<int>(tok0 % S);   // spatial position of the token, kept incrementally (no division in the loop)
+  __half* orow = a.out + static_cast<size_t>(tok0) * a.C + c0;
+  for (int tl = 0; tl < ntok; ++tl, orow += a.C) {
+    float acc[PE_CPT];
 #pragma unroll
-      for (int k4 = 0; k4 < PE_MAXK; k4 += 4) {
-        const float4 p4 = *reinterpret_cast<const float4*>(&patch[buf][tl][k4]);   // broadcast 16-byte shared load
-        const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+    for (int j = 0; j < PE_CPT; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 pp = make_float2(p[e], p[e]);
-          acc01 = __ffma2_rn(pp, w2[0][k4 + e], acc01);
-          acc23 = __ffma2_rn(pp, w2[1][k4 + e], acc23);
-        }
-      }
-      __half2 h01 = __floats2half2_rn(acc01.x + bias2[0].x, acc01.y + bias2[0].y);
-      __half2 h23 = __floats2half2_rn(acc23.x + bias2[1].x, acc23.y + bias2[1].y);
-      if (a.pos) {   // separate fp16 add, as the reference's `x + pos_embed` on half tensors
-        const uint2 pv = __ldg(reinterpret_cast<const uint2*>(a.pos + static_cast<size_t>(s_idx) * a.C + c0));
-        h01 = __hadd2_rn(h01, *reinterpret_cast<const __half2*>(&pv.x));
-        h23 = __hadd2_rn(h23, *reinterpret_cast<const __half2*>(&pv.y));
-      }
-      uint2 o;
-      o.x = *reinterpret_cast<const uint32_t*>(&h01);
-      o.y = *reinterpret_cast<const uint32_t*>(&h23);
-      *reinterpret_cast<uint2*>(orow) = o;
-      if (++s_idx == S) s_idx = 0;
+    for (int k4 = 0; k4 < PE_MAXK; k4 += 4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&patch[tl][k4]);   // broadcast 16-byte shared load
+      const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < PE_CPT; ++j) acc[j] = fmaf(p[e], w[j][k4 + e], acc[j]);
     }
+    __half2 h01 = __floats2half2_rn(acc[0] + bias[0], acc[1] + bias[1]);
+    __half2 h23 = __floats2half2_rn(acc[2] + bias[2], acc[3] + bias[3]);
+    if (a.pos) {   // separate fp16 add, as the reference's `x + pos_embed` on half tensors
+      const uint2 pv = __ldg(reinterpret_cast<const uint2*>(a.pos + static_cast<size_t>(s_idx) * a.C + c0));
+      h01 = __hadd2_rn(h01, *reinterpret_cast<const __half2*>(&pv.x));
+      h23 = __hadd2_rn(h23, *reinterpret_cast<const __half2*>(&pv.y));
+    }
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&h01);
+    o.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(orow) = o;
+    if (++s_idx == S) s_idx = 0;
   }
 }
 
@@ -128,9 +127,7 @@ extern "C" int vq_patch_embed(const float* latent, const void* weight, const voi
   PatchEmbedArgs a{latent, static_cast<const __half*>(weight), static_cast<const __half*>(bias),
                    static_cast<const __half*>(pos), static_cast<__half*>(out), B, Cin, T, Hh, Ww, ph, pw, C};
   const long long M = static_cast<long long>(B) * T * (Hh / ph) * (Ww / pw);
-  const long long chunks = (M + PE_TOKENS - 1) / PE_TOKENS;
-  const long long persistent = 2LL * num_sms();
-  const unsigned grid = static_cast<unsigned>(chunks < persistent ? chunks : persistent);
+  const unsigned grid = static_cast<unsigned>((M + PE_TOKENS - 1) / PE_TOKENS);
   launch_pdl(vq_patch_embed_kernel, dim3(grid), dim3(320), 0, static_cast<cudaStream_t>(stream), a);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
