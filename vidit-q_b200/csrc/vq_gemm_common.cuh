@@ -38,12 +38,6 @@ constexpr int OPERAND_BYTES_PAIR = PAIR_STAGES * (A_STAGE_BYTES + B_PAIR_STAGE_B
 constexpr int OPERAND_BYTES = OPERAND_BYTES_PAIR > OPERAND_BYTES_SINGLE ? OPERAND_BYTES_PAIR : OPERAND_BYTES_SINGLE;
 constexpr int SMEM_BYTES = OPERAND_BYTES + EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-// Residual-prefetch variant of the gated-residual epilogue (CTA pairs, short K): TWO staging strips per epilogue warp — the
-// residual strip of tile i + 1 is TMA-loaded while tile i is dequantised and stored — paid for with two operand stages.
-constexpr int RESPF_STAGES = 4;
-constexpr int RESPF_OPERAND_BYTES = RESPF_STAGES * (A_STAGE_BYTES + B_PAIR_STAGE_BYTES);
-constexpr int RESPF_SMEM_BYTES = RESPF_OPERAND_BYTES + 2 * EPI_STAGING_BYTES + COLBUF_BYTES + 512 + 1024;
-static_assert(RESPF_SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 struct GemmArgs {
   int M, N, K;

@@ -34,9 +34,7 @@ namespace vq {
 // PAIR = true: launched as 2-CTA clusters; one output tile is 256 rows (128 per CTA) x 192 columns, the leader CTA
 // (cluster rank 0) issues tcgen05.mma.cta_group::2 for both, every CTA TMA-loads its own 128 A rows and HALF of the
 // B tile (96 rows) — 30 % less operand traffic per SM than two independent CTAs — and drains its own TMEM half.
-// RESPF = true (gated residual, CTA pairs, K <= 2304): the residual strip is prefetched one whole tile ahead into a second
-// staging set, at the price of a 4-deep instead of 6-deep operand ring.
-template <int EPI, bool PAIR, bool RESPF = false>
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -44,21 +42,19 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  static_assert(!RESPF || (PAIR && EPI == VQ_EPI_GATE_RESIDUAL), "residual prefetch: CTA-pair gated-residual kernel only");
-  constexpr int NS = RESPF ? RESPF_STAGES : (PAIR ? PAIR_STAGES : STAGES);
+  constexpr int NS = PAIR ? PAIR_STAGES : STAGES;
   constexpr int BSB = PAIR ? B_PAIR_STAGE_BYTES : B_STAGE_BYTES;   // per-CTA bytes of one B stage
-  constexpr int EPI_SETS = RESPF ? 2 : 1;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NS * A_STAGE_BYTES;
-  uint8_t* smem_epi = smem + (RESPF ? RESPF_OPERAND_BYTES : OPERAND_BYTES);
-  int4* colbuf = reinterpret_cast<int4*>(smem_epi + EPI_SETS * EPI_STAGING_BYTES);   // [2][BN] records
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_SETS * EPI_STAGING_BYTES + COLBUF_BYTES);
+  uint8_t* smem_epi = smem + OPERAND_BYTES;
+  int4* colbuf = reinterpret_cast<int4*>(smem_epi + EPI_STAGING_BYTES);   // [2][BN] records
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGING_BYTES + COLBUF_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
   uint64_t* tempty_bar = bars + 2 * MAX_STAGES + ACC_STAGES;
-  uint64_t* res_bar = bars + 2 * MAX_STAGES + 2 * ACC_STAGES;   // [2][NUM_EPI_WARPS] residual strip (of staging set s) landed
-  uint64_t* colfull_bar = res_bar + 2 * NUM_EPI_WARPS;       // [2] column records of a tile are in colbuf[b]
+  uint64_t* res_bar = bars + 2 * MAX_STAGES + 2 * ACC_STAGES;   // [NUM_EPI_WARPS] residual strip landed
+  uint64_t* colfull_bar = res_bar + NUM_EPI_WARPS;           // [2] column records of a tile are in colbuf[b]
   uint64_t* colempty_bar = colfull_bar + 2;                  // [2] all epilogue warps are done with colbuf[b]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(colempty_bar + 2);
 
@@ -91,7 +87,7 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);   // leader collects both CTAs' epilogues
     }
-    for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&colfull_bar[b], 1);
       mbar_init(&colempty_bar[b], NUM_EPI_WARPS);
@@ -208,35 +204,10 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // software-pipelined), then staged and handed to the TMA with ONE proxy fence and three bulk stores per tile.
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int h = (warp - 4) >> 2;   // column half
-    uint8_t* stage_base = smem_epi + (warp - 4) * EPI_NCHUNK * EPI_BUF_BYTES;   // set s at + s * EPI_STAGING_BYTES
-    uint64_t* my_res_bar = res_bar + (warp - 4);                               // set s at + s * NUM_EPI_WARPS
-    uint32_t res_uses = 0, res_uses1 = 0;   // completed phases of the residual barrier (RESPF: of staging set 0 / set 1)
+    uint8_t* stage0 = smem_epi + (warp - 4) * EPI_NCHUNK * EPI_BUF_BYTES;
+    uint64_t* my_res_bar = res_bar + (warp - 4);
+    uint32_t res_uses = 0;
     int local = 0;
-    // sub-tiles of this warp that lie inside the matrix for a given tile, and the residual load of a tile into a staging set
-    auto tile_geom = [&](int tile_, int& row0_, int& cbase_) {
-      int tm_, tn_;
-      tile_to_mn(tile_, num_m_tiles, num_n_tiles, p.group_m, tm_, tn_);
-      row0_ = tm_ * TILE_M + m_cta + q * 32;
-      cbase_ = tn_ * BN + h * EPI_COLS;
-      int n_ = 0;
-      if (row0_ < p.M) {
-#pragma unroll
-        for (int c = 0; c < EPI_NCHUNK; ++c) n_ += (cbase_ + c * EPI_CHUNK < p.N) ? 1 : 0;
-      }
-      return n_;
-    };
-    auto load_residual = [&](int tile_, int set_) {   // lane 0 only
-      int r0_, cb_;
-      const int n_ = tile_geom(tile_, r0_, cb_);
-      if (n_ > 0) {
-        uint8_t* dst = stage_base + set_ * EPI_STAGING_BYTES;
-        mbar_arrive_expect_tx(my_res_bar + set_ * NUM_EPI_WARPS, n_ * EPI_BUF_BYTES);
-        for (int c = 0; c < n_; ++c)
-          tma_load_2d_hint(dst + c * EPI_BUF_BYTES, &tmap_res, my_res_bar + set_ * NUM_EPI_WARPS, cb_ + c * EPI_CHUNK, r0_,
-                           kEvictFirst);
-      }
-    };
-    if (RESPF && lane == 0 && worker < num_tiles) load_residual(worker, 0);   // first tile's residual: set 0
     // per-row dequant parameters {delta, zero point, row sum}, fetched one tile ahead
     struct RowP { float dx; int32_t zx, rs; };
     auto load_rowp = [&](int tile_) {
@@ -272,23 +243,13 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int c = 0; c < EPI_NCHUNK; ++c) nact += (cbase + c * EPI_CHUNK < p.N) ? 1 : 0;
       }
 
-      const int set = RESPF ? (local & 1) : 0;
-      uint8_t* stage0 = stage_base + set * EPI_STAGING_BYTES;
-      if (RESPF) {
-        // the other staging set was last used by tile i - 1, whose stores were issued a whole tile ago: once they have read
-        // it, the residual strip of tile i + 1 goes there — in flight during this tile's TMEM loads, dequant and stores
-        if (lane == 0) {
-          tma_store_wait_read<0>();
-          if (tile + num_workers < num_tiles) load_residual(tile + num_workers, set ^ 1);
-        }
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + h * EPI_COLS;
       uint32_t v[2][32];
       tmem_ld_32x32b_x32(t_base, v[0]);
       // the previous tile's TMA stores have finished reading the staging strip (they were issued a whole tile ago)
-      if (!RESPF && lane == 0 && nact > 0) {
+      if (lane == 0 && nact > 0) {
         tma_store_wait_read<0>();
         if (EPI == VQ_EPI_GATE_RESIDUAL) {   // residual strip -> staging (same swizzle), landed on my_res_bar
           mbar_arrive_expect_tx(my_res_bar, nact * EPI_BUF_BYTES);
@@ -335,14 +296,8 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (nact > 0) {
         if (EPI == VQ_EPI_GATE_RESIDUAL) {
-          // RESPF: one barrier per staging set; a set's barrier completes a phase per tile in which this warp was active
-          if (RESPF && set == 1) {
-            mbar_wait(my_res_bar + NUM_EPI_WARPS, res_uses1 & 1);
-            ++res_uses1;
-          } else {
-            mbar_wait(my_res_bar, res_uses & 1);
-            ++res_uses;
-          }
+          mbar_wait(my_res_bar, res_uses & 1);
+          ++res_uses;
         } else {
           __syncwarp();   // lane 0's wait_read above precedes every lane's staging writes
         }
@@ -448,22 +403,21 @@ int num_sms() {   // per device ordinal: one process may drive several GPUs
   return n[dev];
 }
 
-template <int EPI, bool PAIR, bool RESPF = false>
+template <int EPI, bool PAIR>
 static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                             const GemmArgs& args, int grid, cudaStream_t stream) {
   static bool attr_set[kMaxDevices] = {};   // the > 48 KB dynamic shared memory opt-in is a per-device function attribute
   const int dev = current_device();
-  constexpr int SMEM = RESPF ? RESPF_SMEM_BYTES : SMEM_BYTES;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI, PAIR, RESPF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SMEM);
+    cudaError_t e = cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BYTES);
     if (e != cudaSuccess) return VQ_ERR_LAUNCH;
     attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = SMEM;
+  cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -474,7 +428,7 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const 
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, PAIR, RESPF>, ta, tb, to, tr, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, PAIR>, ta, tb, to, tr, args);
   return e == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 
@@ -555,16 +509,7 @@ extern "C" int vq_gemm_w8a8(const uint8_t* a_codes, const void* a_delta, const v
   switch (epi) {
     case VQ_EPI_BIAS: return launch_gemm<VQ_EPI_BIAS>(ta, tb, to, tr, args, grid, pair, st);
     case VQ_EPI_GELU_TANH: return launch_gemm<VQ_EPI_GELU_TANH>(ta, tb, to, tr, args, grid, pair, st);
-    case VQ_EPI_GATE_RESIDUAL: {
-      // residual prefetch (second staging set, 4 operand stages) where the epilogue is the critical path: short K on CTA
-      // pairs.  VQ_GEMM_RESPF=0 disables it (A/B knob).
-      static const bool respf = [] {
-        const char* e = getenv("VQ_GEMM_RESPF");
-        return !(e && e[0] == '0');
-      }();
-      if (respf && pair && K <= 2304) return launch_gemm_impl<VQ_EPI_GATE_RESIDUAL, true, true>(ta, tb, to, tr, args, grid, st);
-      return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, tr, args, grid, pair, st);
-    }
+    case VQ_EPI_GATE_RESIDUAL: return launch_gemm<VQ_EPI_GATE_RESIDUAL>(ta, tb, to, tr, args, grid, pair, st);
 #ifdef VQ_DEBUG_EPI
     case VQ_EPI_DEBUG_LOADS: return launch_gemm<VQ_EPI_DEBUG_LOADS>(ta, tb, to, tr, args, grid, pair, st);
     case VQ_EPI_DEBUG_MATH: return launch_gemm<VQ_EPI_DEBUG_MATH>(ta, tb, to, tr, args, grid, pair, st);
