@@ -55,7 +55,24 @@ struct GemmArgs {
   int rows_per_gate;
   uint64_t store_policy;    // L2 cache policy of the output stores (kEvictFirst unless VQ_STORE_POLICY=normal)
   int group_m;              // rasterisation: m-panels per group (tile_to_mn)
+  // ---- quantise-producer variant (QPRO): the activation codes this GEMM consumes are produced INSIDE the kernel by two
+  // quantiser warpgroups running ahead of the MMAs (vq_gemm_w8a8.cu); a_codes / a_delta / a_zp / a_rowsum are then scratch
+  const __half* qx;         // [M, K] fp16 source rows (K = 1152)
+  const __half* q_shift;    // LayerNorm + modulate variant: [M / q_rows_per_mod, K]
+  const __half* q_scale;
+  const __half* q_smooth;   // [K] or null
+  int q_rows_per_mod;
+  float q_qmax;
+  uint8_t* q_codes;         // scratch [M, K]: what tmap_a describes
+  uint32_t* q_sync;         // [0] next row of the work queue; [1 + m] rows of m-panel m (TILE_M rows) quantised so far
+  uint32_t* q_status;
 };
+
+constexpr int QP_THREADS = 640;           // 4 control warps + 8 epilogue warps + 8 quantiser warps
+constexpr int QP_ROWS = 2;                // rows a quantiser warp takes from the work queue at a time
+constexpr int QP_REGS_CONTROL = 40;       // setmaxnreg budgets per warpgroup: 128 x 40 + 256 x 144 + 256 x 72 = 60416 <= 640 x 96
+constexpr int QP_REGS_EPILOGUE = 144;
+constexpr int QP_REGS_QUANT = 72;
 
 // Tile index -> (m-panel, n-tile): groups of `gm` m-panels; inside a group the m-panel runs fastest, then the n-tile; the
 // last group may be narrower.  gm = num_m gives plain m-fastest order.

@@ -28,14 +28,22 @@
 #include <stdlib.h>
 
 #include "vq_gemm_common.cuh"
+#include "vq_quant_common.cuh"
 
 namespace vq {
 
 // PAIR = true: launched as 2-CTA clusters; one output tile is 256 rows (128 per CTA) x 192 columns, the leader CTA
 // (cluster rank 0) issues tcgen05.mma.cta_group::2 for both, every CTA TMA-loads its own 128 A rows and HALF of the
 // B tile (96 rows) — 30 % less operand traffic per SM than two independent CTAs — and drains its own TMEM half.
-template <int EPI, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// QPRO = 1 | 2 (CTA pairs, K = 1152): the activation codes are produced INSIDE the kernel.  Two extra warpgroups (warps
+// 12-19) take fp16 rows from a global work queue in ascending order — the order the rasterisation consumes m-panels —,
+// run the exact quantiser ([LayerNorm + modulate for QPRO = 2], [/ smooth], min / max, codes, row sum) and write codes and
+// per-row parameters to an L2-resident scratch; every finished row is counted on its m-panel's flag.  The TMA producer
+// acquires a panel's flag before loading its A tiles, the epilogue before reading its row parameters.  The quantise
+// arithmetic thus overlaps the tensor pipe instead of running as a pass in front of the GEMM.  Register budgets per
+// warpgroup via setmaxnreg (control 40, epilogue 144, quantisers 72).
+template <int EPI, bool PAIR, int QPRO = 0>
+__global__ void __launch_bounds__(QPRO ? QP_THREADS : GEMM_THREADS, 1)
 vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmArgs p) {
@@ -109,7 +117,12 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_dep_sync();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
+  static_assert(QPRO == 0 || PAIR, "quantise-producer variant: CTA pairs only");
 
+  // Role dispatch by warpGROUP first: with QPRO every group sets its register budget at the top of its own branch
+  // (setmaxnreg dominates the code it governs; one instruction executed by all four warps of the group).
+  if (warp < 4) {
+  if (QPRO) setmaxnreg_dec<QP_REGS_CONTROL>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -121,6 +134,13 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tile_to_mn(tile, num_m_tiles, num_n_tiles, p.group_m, tm, tn);
         const int m_idx = tm * TILE_M + m_cta;
         const int n_idx = tn * BN + (PAIR ? static_cast<int>(cta_rank) * (BN / 2) : 0);
+        if (QPRO) {
+          // the quantiser warpgroups (of any CTA) have finished every row of this m-panel: acquire, then order the
+          // generic-proxy writes of the codes before this thread's async-proxy (TMA) reads
+          const int need = min(TILE_M, p.M - tm * TILE_M);
+          wait_counter(p.q_sync + 1 + tm, static_cast<uint32_t>(need));
+          fence_proxy_async_all();
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           // operand tiles are re-read by other CTAs (A by every n-tile, B by every m-tile): keep them in L2
@@ -198,8 +218,56 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&colfull_bar[b]);
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
+  }
+  } else if (QPRO && warp >= 12) {
+    // ===================== quantiser warpgroups (QPRO) =====================
+    setmaxnreg_dec<QP_REGS_QUANT>();
+    // work queue of row batches in ascending order; one warp per row, QP_ROWS rows in flight
+    const int KQ = 9 * 128;
+    for (;;) {
+      int r0 = 0;
+      if (lane == 0) r0 = static_cast<int>(atomicAdd(p.q_sync, static_cast<uint32_t>(QP_ROWS)));
+      r0 = __shfl_sync(0xffffffffu, r0, 0);
+      if (r0 >= p.M) break;
+      UnitRegs<9> regs[QP_ROWS];
+#pragma unroll
+      for (int b = 0; b < QP_ROWS; ++b)
+        if (r0 + b < p.M) uload_row<9>(regs[b], p.qx + static_cast<size_t>(r0 + b) * KQ, lane);
+      int nvalid = 0;
+#pragma unroll
+      for (int b = 0; b < QP_ROWS; ++b) {
+        const int row = r0 + b;
+        if (row < p.M) {
+          if (QPRO == 2) {
+            const size_t mo = static_cast<size_t>(row / p.q_rows_per_mod) * KQ;
+            uapply_ln_modulate<9>(regs[b], p.q_shift + mo, p.q_scale + mo, KQ, lane);
+          }
+          if (p.q_smooth) uapply_smooth<9>(regs[b], p.q_smooth, lane);
+          __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;   // the range always contains zero
+          urow_minmax<9>(regs[b], mn2, mx2);
+          float mn, mx;
+          warp_minmax(mn2, mx2, mn, mx);
+          const RowStats st = make_stats(mn, mx, p.q_qmax);
+          const QuantConsts qc = make_consts(st.delta, st.zp, p.q_qmax);
+          int sum = uquant_store_row<9>(regs[b], p.q_codes + static_cast<size_t>(row) * KQ, lane, qc);
+          sum = warp_sum_i(sum);
+          if (lane == 0) {
+            const_cast<__half*>(p.a_delta)[row] = __float2half_rn(st.delta);
+            const_cast<__half*>(p.a_zp)[row] = __float2half_rn(st.zp);
+            const_cast<int32_t*>(p.a_rowsum)[row] = sum;
+            if (st.degenerate && p.q_status) atomicOr(p.q_status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
+          }
+          ++nvalid;
+        }
+      }
+      // every lane's stores before the panel's flag: fence, converge, one release-add (QP_ROWS divides TILE_M: one panel)
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) red_release_gpu_add(p.q_sync + 1 + r0 / TILE_M, static_cast<uint32_t>(nvalid));
+    }
+  } else {
+    // ===================== epilogue (warps 4-11) =====================
+    if (QPRO) setmaxnreg_inc<QP_REGS_EPILOGUE>();
     // Per tile and warp: 32 rows x 96 columns. The strip is dequantised into registers chunk by chunk (TMEM loads
     // software-pipelined), then staged and handed to the TMA with ONE proxy fence and three bulk stores per tile.
     const int q = warp & 3;          // TMEM lane quarter this warp may access
@@ -222,7 +290,21 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       r.rs = p.a_rowsum[rc];
       return r;
     };
-    RowP rp_next = load_rowp(worker < num_tiles ? worker : 0);
+    // QPRO: the parameters are produced inside this kernel — acquire the m-panel's flag, then read them past the L1
+    auto load_rowp_acquired = [&](int tile_) {
+      RowP r;
+      int tm_, tn_;
+      tile_to_mn(tile_, num_m_tiles, num_n_tiles, p.group_m, tm_, tn_);
+      wait_counter(p.q_sync + 1 + tm_, static_cast<uint32_t>(min(TILE_M, p.M - tm_ * TILE_M)));
+      const int row_ = tm_ * TILE_M + m_cta + q * 32 + lane;
+      const int rc = row_ < p.M ? row_ : p.M - 1;
+      r.dx = __half2float(__ldcg(p.a_delta + rc));
+      r.zx = __float2int_rn(__half2float(__ldcg(p.a_zp + rc)));
+      r.rs = __ldcg(p.a_rowsum + rc);
+      return r;
+    };
+    RowP rp_next = RowP{0.f, 0, 0};
+    if (!QPRO) rp_next = load_rowp(worker < num_tiles ? worker : 0);
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -233,8 +315,9 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int row0 = m_idx + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const RowP rp = rp_next;
-      if (tile + num_workers < num_tiles) rp_next = load_rowp(tile + num_workers);
+      RowP rp = rp_next;
+      if (QPRO) rp = load_rowp_acquired(tile);   // in flight long before the accumulator is complete
+      else if (tile + num_workers < num_tiles) rp_next = load_rowp(tile + num_workers);
       const int cbase = n_idx + h * EPI_COLS;
       // active sub-tiles of this warp: rows in range and first column in range (N is a multiple of 8)
       int nact = 0;
@@ -430,6 +513,98 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const 
   cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, PAIR>, ta, tb, to, tr, args);
   return e == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+template <int EPI, int QPRO>
+static int launch_gemm_qpro(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                            const GemmArgs& args, int grid, cudaStream_t stream) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(vq_gemm_w8a8_kernel<EPI, true, QPRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+        cudaSuccess)
+      return VQ_ERR_LAUNCH;
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(QP_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, vq_gemm_w8a8_kernel<EPI, true, QPRO>, ta, tb, to, tr, args);
+  return e == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+// One QuantLinear with the quantise pass running INSIDE the GEMM kernel (quantiser warpgroups ahead of the MMAs).
+// K = 1152, un-pooled statistics (one scale pair per row), M > 128, bias or gated-residual epilogue.  codes / delta / zp /
+// rowsum / sync are caller scratch; sync (2 + ceil(M / 256) words) is zeroed here (a memset node in a captured graph).
+int gemm_w8a8_qpro(const void* x, const void* shift, const void* scale, int rows_per_mod, const void* smooth, int n_bits,
+                   uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* sync, const uint8_t* w_codes,
+                   const VqColParam* col, int M, int N, int K, int epi, const void* res, int ldr, const void* gate,
+                   int rows_per_gate, void* out, int ldo, uint32_t* status, cudaStream_t st) {
+  if (K != 9 * 128 || M <= BM || (epi != VQ_EPI_BIAS && epi != VQ_EPI_GATE_RESIDUAL)) return VQ_ERR_UNSUPPORTED;
+  const bool ln = shift != nullptr;
+  CUtensorMap ta, tb, to;
+  int rc = make_u8_kmajor_tmap(&ta, codes, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM);
+  if (rc != VQ_OK) return rc;
+  rc = make_u8_kmajor_tmap(&tb, w_codes, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN / 2);
+  if (rc != VQ_OK) return rc;
+  rc = make_f16_out_tmap(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo);
+  if (rc != VQ_OK) return rc;
+  CUtensorMap tr = to;
+  if (epi == VQ_EPI_GATE_RESIDUAL) {
+    rc = make_f16_out_tmap(&tr, res, (uint64_t)M, (uint64_t)N, (uint64_t)ldr);
+    if (rc != VQ_OK) return rc;
+  }
+  const int tile_m = 2 * BM;
+  const int m_tiles = (M + tile_m - 1) / tile_m;
+  if (cudaMemsetAsync(sync, 0, sizeof(uint32_t) * (2 + m_tiles), st) != cudaSuccess) return VQ_ERR_LAUNCH;
+  GemmArgs args{};
+  args.M = M; args.N = N; args.K = K;
+  args.a_delta = static_cast<const __half*>(delta);
+  args.a_zp = static_cast<const __half*>(zp);
+  args.a_rowsum = rowsum;
+  args.a_period = M;
+  args.col = col;
+  args.out = static_cast<__half*>(out);
+  args.ldo = ldo;
+  args.epi = epi;
+  args.res = static_cast<const __half*>(res);
+  args.ldr = ldr;
+  args.gate = static_cast<const __half*>(gate);
+  args.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+  args.store_policy = kEvictFirst;
+  static const int group_m_env = [] {
+    const char* e = getenv("VQ_GEMM_GROUP_M");
+    return e ? atoi(e) : 8;
+  }();
+  args.group_m = group_m_env <= 0 ? m_tiles : (group_m_env < m_tiles ? group_m_env : m_tiles);
+  args.qx = static_cast<const __half*>(x);
+  args.q_shift = static_cast<const __half*>(shift);
+  args.q_scale = static_cast<const __half*>(scale);
+  args.q_smooth = static_cast<const __half*>(smooth);
+  args.q_rows_per_mod = rows_per_mod > 0 ? rows_per_mod : 1;
+  args.q_qmax = static_cast<float>((1 << n_bits) - 1);
+  args.q_codes = codes;
+  args.q_sync = sync;
+  args.q_status = status;
+  const int tiles = m_tiles * ((N + BN - 1) / BN);
+  const int workers = num_sms() / 2;
+  const int grid = (tiles < workers ? tiles : workers) * 2;
+  if (epi == VQ_EPI_BIAS)
+    return ln ? launch_gemm_qpro<VQ_EPI_BIAS, 2>(ta, tb, to, tr, args, grid, st)
+              : launch_gemm_qpro<VQ_EPI_BIAS, 1>(ta, tb, to, tr, args, grid, st);
+  return ln ? launch_gemm_qpro<VQ_EPI_GATE_RESIDUAL, 2>(ta, tb, to, tr, args, grid, st)
+            : launch_gemm_qpro<VQ_EPI_GATE_RESIDUAL, 1>(ta, tb, to, tr, args, grid, st);
 }
 
 template <int EPI>

@@ -79,6 +79,11 @@ int attn_cross_tc(const void* q, const void* kv, void* out, const int* kv_start,
                   int head_dim, long long kv_rows, float scale, void* stream);
 int make_u8_kmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch,
                         uint32_t box_rows);
+// QuantLinear with the quantise pass inside the GEMM kernel (vq_gemm_w8a8.cu, QPRO): see vq_linear_w8a8, policy mode 2
+int gemm_w8a8_qpro(const void* x, const void* shift, const void* scale, int rows_per_mod, const void* smooth, int n_bits,
+                   uint8_t* codes, void* delta, void* zp, int32_t* rowsum, uint32_t* sync, const uint8_t* w_codes,
+                   const VqColParam* col, int M, int N, int K, int epi, const void* res, int ldr, const void* gate,
+                   int rows_per_gate, void* out, int ldo, uint32_t* status, cudaStream_t st);
 int make_u8_tmap_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_cols,
                     uint32_t box_rows, bool swizzle128);
 // rows x cols fp16 matrix (row pitch ld elements), box 32 rows x 32 columns, SWIZZLE_64B: the epilogue staging sub-tile

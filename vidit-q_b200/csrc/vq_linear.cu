@@ -551,7 +551,8 @@ static inline int64_t align16(int64_t v) { return (v + 15) & ~int64_t(15); }
 extern "C" int64_t vq_linear_workspace_bytes(int G, int rows, int K) {
   if (G <= 0 || rows <= 0 || K <= 0) return 0;
   const int64_t M = static_cast<int64_t>(G) * rows;
-  return vq::align16(M * K) + 2 * vq::align16(2LL * rows) + vq::align16(4 * M);
+  // codes | delta | zp | rowsum | sync words of the overlapped schedule (work-queue head + one flag per 256-row panel)
+  return vq::align16(M * K) + 2 * vq::align16(2LL * rows) + vq::align16(4 * M) + vq::align16(4 * (2 + (M + 255) / 256));
 }
 
 static bool fused_shape_supported(int G, int rows, int K) {
@@ -566,8 +567,9 @@ static bool fused_shape_supported(int G, int rows, int K) {
 // 68 vs 74 us at M = 16384) — the stand-alone quantise pass spreads its rows over 148 SMs x 32 warps with no redundancy,
 // the fused kernel's 8 producer warps per SM re-quantise the panel in every CTA that shares it and cannot overlap the
 // MMAs (one 147 KB panel per SM) — so the default is OFF; eager callers with single-panel problems may opt in.
-// mode: 0 never (default), 1 whenever the shape is supported, -1 up to max_m rows.  Env VQ_LINEAR_FUSED / VQ_LINEAR_FUSED_MAX_M
-// give the initial values.
+// mode: 0 never (default), 1 whenever the shape is supported, -1 up to max_m rows; 2: the OVERLAPPED schedule — the
+// persistent GEMM with quantiser warpgroups running ahead of its MMAs (vq_gemm_w8a8.cu, QPRO) for K = 1152, G = 1, M > 128,
+// bias / gated-residual epilogue; other shapes as mode 0.  Env VQ_LINEAR_FUSED / VQ_LINEAR_FUSED_MAX_M give the initial values.
 static int g_fused_mode = [] {
   const char* e = getenv("VQ_LINEAR_FUSED");
   return e ? atoi(e) : 0;
@@ -578,7 +580,7 @@ static long long g_fused_max_m = [] {
 }();
 
 extern "C" int vq_linear_set_fused_policy(int mode, int64_t max_m) {
-  if (mode < -1 || mode > 1 || max_m < 0) return VQ_ERR_ARG;
+  if (mode < -1 || mode > 2 || max_m < 0) return VQ_ERR_ARG;
   g_fused_mode = mode;
   g_fused_max_m = max_m;
   return VQ_OK;
@@ -587,6 +589,7 @@ extern "C" int vq_linear_set_fused_policy(int mode, int64_t max_m) {
 extern "C" int vq_linear_launch_count(int G, int rows, int K) {
   if (G <= 0 || rows <= 0 || K <= 0) return VQ_ERR_ARG;
   const long long M = static_cast<long long>(G) * rows;
+  if (g_fused_mode == 2) return (G == 1 && K == vq::FL_K && M >= 1024) ? 1 : 2;   // overlapped schedule (epilogue checked at call)
   const bool fused = fused_shape_supported(G, rows, K) && g_fused_mode != 0 && (g_fused_mode == 1 || M <= g_fused_max_m);
   return fused ? 1 : 2;
 }
@@ -607,8 +610,29 @@ static int linear_impl(const void* x, int G, int rows, int K, const void* smooth
   const long long M = static_cast<long long>(G) * rows;
   if (M > 0x7fffffffLL) return VQ_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool fused = vq_linear_launch_count(G, rows, K) == 1;
+  const bool overlapped = g_fused_mode == 2 && !w4 && G == 1 && K == FL_K && M >= 1024 &&
+                          (epi == VQ_EPI_BIAS || epi == VQ_EPI_GATE_RESIDUAL);
+  const bool fused = g_fused_mode != 2 && vq_linear_launch_count(G, rows, K) == 1;
   if (!fused && w4) return VQ_ERR_UNSUPPORTED;   // packed INT4 weights exist for the fused kernel only: pass the u8 codes
+  if (overlapped) {
+    if (!workspace || workspace_bytes < vq_linear_workspace_bytes(G, rows, K)) return VQ_ERR_ARG;
+    if (ln && (rows_per_mod > rows || (rows % rows_per_mod) != 0)) return VQ_ERR_ARG;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    uint8_t* codes = ws;
+    void* delta = ws + align16(M * K);
+    void* zp = ws + align16(M * K) + align16(2LL * rows);
+    int32_t* rowsum = reinterpret_cast<int32_t*>(ws + align16(M * K) + 2 * align16(2LL * rows));
+    uint32_t* sync = reinterpret_cast<uint32_t*>(ws + align16(M * K) + 2 * align16(2LL * rows) + align16(4 * M));
+    int rc = gemm_w8a8_qpro(x, ln_shift, ln_scale, rows_per_mod, smooth, n_bits, codes, delta, zp, rowsum, sync, w_codes, col,
+                            static_cast<int>(M), N, K, epi, res, ldr, gate, rows_per_gate, out, ldo, status, st);
+    if (rc != VQ_OK) return rc;
+    if (out_delta) {
+      if (cudaMemcpyAsync(out_delta, delta, 2 * static_cast<size_t>(rows), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+          cudaMemcpyAsync(out_zp, zp, 2 * static_cast<size_t>(rows), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return VQ_ERR_LAUNCH;
+    }
+    return VQ_OK;
+  }
   if (!fused) {
     // two launches through the caller's workspace: (LayerNorm + modulate +) quantise pass, then the persistent GEMM
     if (!workspace || workspace_bytes < vq_linear_workspace_bytes(G, rows, K)) return VQ_ERR_ARG;

@@ -361,9 +361,9 @@ def _workspace(nbytes, device):
 
 
 def set_linear_fused_policy(mode=0, max_m=0):
-    """Which shapes linear_w8a8 runs as the single fused kernel: mode 0 never (default: quantise pass + GEMM measured faster
-    on B200 inside CUDA graphs), 1 every supported shape, -1 supported shapes up to max_m rows.  Returns the previous call's
-    arguments are not tracked: callers restore explicitly."""
+    """Schedule behind linear_w8a8: mode 0 quantise pass + GEMM (default), 1 the panel-resident fused kernel on every
+    supported shape, -1 the same up to max_m rows, 2 the OVERLAPPED schedule (persistent GEMM with quantiser warpgroups
+    running ahead of its MMAs; K = 1152, un-pooled statistics, >= 1024 rows).  Callers restore explicitly."""
     _lib.check(_lib.lib().vq_linear_set_fused_policy(int(mode), int(max_m)), "vq_linear_set_fused_policy")
 
 
@@ -411,10 +411,10 @@ def linear_w8a8(x, w: PreparedWeight, n_bits=8, smooth=None, ln=None, rows_per_m
         _lib.check(rc, "vq_linear_w4a8")
         _count()
         return out
-    ws, ws_bytes = None, 0
-    if n_launch != 1:
-        ws_bytes = L.vq_linear_workspace_bytes(G, rows, K)
-        ws = _workspace(ws_bytes, x.device)
+    # scratch of the two-launch and of the overlapped schedule (codes, per-row parameters, panel flags); the panel-resident
+    # fused kernel ignores it
+    ws_bytes = L.vq_linear_workspace_bytes(G, rows, K)
+    ws = _workspace(ws_bytes, x.device)
     rc = L.vq_linear_w8a8(_ptr(x), G, rows, K, _ptr(smooth), _ptr(shift), _ptr(scale), rpm, n_bits, _ptr(w.codes),
                           _ptr(w.col), w.N, epi, _ptr(res), w.N, _ptr(gate), rows_per_gate, _ptr(out),
                           w.N if ldo is None else ldo, None, None, _ptr(ws), ws_bytes, _ptr(status_word(x.device)),

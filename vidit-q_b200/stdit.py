@@ -351,6 +351,9 @@ class FusedBlocks:
         # VQ_SPATIAL_ATTN=sdpa runs the long spatial attention on the library flash kernel (torch SDPA -> cuDNN) instead of
         # vq_attn_spatial: the yardstick bench.py / tools/prof_kernels.py time the own kernel against, not a fallback
         self.own_spatial = os.environ.get("VQ_SPATIAL_ATTN", "own") != "sdpa"
+        # VQ_LINEAR_FUSED=2: every K = 1152 linear of the schedule goes through the ONE-call entry vq_linear_w8a8 in its
+        # overlapped mode — the persistent GEMM with quantiser warpgroups running ahead of its MMAs (no separate quantise pass)
+        self.overlap = os.environ.get("VQ_LINEAR_FUSED", "0") == "2"
         # VQ_TEMPORAL_FUSED_QUANT=1: temporal attention + the projection's quantiser as ONE kernel (vq_attn_temporal_quant).
         # Bit-identical; measured on B200: 101 us against 62 + 18 us for the two kernels in a single replay (the 16-warp,
         # 135 KB block runs one per SM: no second block to cover its load and barrier phases), equal step time under the
@@ -410,6 +413,16 @@ class FusedBlocks:
             hit = self._qkv[tag] = (key, ops.PreparedWeight(codes, col, codes.shape[0], pws[0].K, pws[0].n_bits))
         return hit[1]
 
+    def _qlin(self, layer, t, qi, unpooled, **kw):
+        """Quantiser + GEMM of one block linear on `t` [.., n, C].  Overlapped mode (un-pooled statistics only): one call,
+        the quantise arithmetic runs inside the GEMM kernel."""
+        if self.overlap and unpooled and layer.smooth_mode() in (None, "cached"):
+            pw = layer.prepared_weight()
+            return ops.linear_w8a8(t.reshape(1, -1, t.shape[-1]), pw, n_bits=layer.act_quantizer.n_bits,
+                                   smooth=getattr(pw, "smooth", None), **kw)
+        a = qi(layer, t)
+        return ops.gemm_w8a8(a, a.pw, **kw)
+
     def _qkv_project(self, attn, tag, x, ln=None, independent=False, add=None):
         """q|k|v of one attention as one [M, 3C] tensor. ln = (shift, scale) fuses LayerNorm+modulate in front.
         Without smooth-quant: one quantise pass + one N=3C GEMM. With it (w4a8_timestep_aware_cb.yaml): each layer has
@@ -423,6 +436,8 @@ class FusedBlocks:
             rpm = x.shape[1]
             x = x.view(1, -1, x.shape[2])
         if pw is not None:
+            if self.overlap and add is None and x.shape[0] == 1:
+                return ops.linear_w8a8(x, pw, n_bits=nb, ln=ln, rows_per_mod=rpm if ln is not None else None)
             if ln is not None:
                 a = ops.ln_modulate_act_quant(x, ln[0], ln[1], n_bits=nb, rows_per_mod=rpm)[0]
             elif add is not None:
@@ -483,14 +498,16 @@ class FusedBlocks:
             # ---- spatial attention: LN + modulate + quantise once, one q|k|v GEMM
             qkv = self._qkv_project(blk.attn, (i, "s"), x, ln=(shift_msa, scale_msa), independent=independent)
             pj = blk.attn.proj
+            unpooled = frames is None and (independent or B == 1)
+            xr = x.view(M, C)   # residual stream, updated in place: out aliases res
             if self.own_spatial and ops.attn_spatial_supported(S, D):
                 # tcgen05 flash attention reading q|k|v in place, token-major output: the projection's quantiser input
                 o = ops.attn_spatial(qkv, B * T, S, H, D, blk.attn.scale)
-                a = qi(pj, o.view(B * T, S, C))
+                self._qlin(pj, o.view(B * T, S, C), qi, unpooled, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
+                           rows_per_gate=N, out=xr)
             else:
                 a = self._spatial_library(qkv.view(B * T, S, 3, H, D), pj, blk.attn.scale, B, N, T, S, C, D, independent)
-            xr = x.view(M, C)   # residual stream, updated in place: out aliases res -> TMA reduce-add epilogue
-            ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
+                ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
             if frames is not None:
                 # frame-sharded: quantise locally, all-to-all the CODES into the (all frames, S / P positions) layout,
@@ -536,27 +553,30 @@ class FusedBlocks:
                     o = F.scaled_dot_product_attention(qt, kt, vt, scale=blk.attn_temp.scale)
                     o = o.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B, N, C)
                 # per-token statistics: row order irrelevant
-                a = blk.attn_temp.proj.quantize_input(o.view(B * S, T, C), independent=independent)
-                ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
+                self._qlin(blk.attn_temp.proj, o.view(B * S, T, C),
+                           lambda l, t_: l.quantize_input(t_, independent=independent), unpooled,
+                           epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
             # ---- cross attention
             ca = blk.cross_attn
-            a = qi(ca.q_linear, x)
-            q = ops.gemm_w8a8(a, a.pw)
+            q = self._qlin(ca.q_linear, x, qi, unpooled)
             a = ca.kv_linear.quantize_input(y)
             kv = ops.gemm_w8a8(a, a.pw)
             if D == 72 and max(y_lens) <= 128:
                 o = ops.attn_cross(q, kv, segments[0], segments[1], B, N, H, D, max(y_lens), D ** -0.5).view(B, N, C)
             else:
                 o = MultiHeadCrossAttention.attend(q, kv, B, N, y_lens, H, D).view(B, N, C)
-            a = qi(ca.proj, o)
-            ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=ones, rows_per_gate=M, out=xr)
+            self._qlin(ca.proj, o, qi, unpooled, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=ones, rows_per_gate=M, out=xr)
             # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
             fc1w = blk.mlp.fc1.prepared_weight()
-            a, _ = ops.ln_modulate_act_quant(x.view(1, M, C) if independent else x, shift_mlp, scale_mlp,
-                                             n_bits=blk.mlp.fc1.act_quantizer.n_bits,
-                                             smooth=getattr(fc1w, "smooth", None), rows_per_mod=N if independent else None)
             # GELU rides in fc2's quantise pass (HBM-bound, idle MUFU) instead of fc1's epilogue (epilogue-bound)
-            h = ops.gemm_w8a8(a, fc1w).view(B, N, -1)
+            if self.overlap and unpooled:
+                h = ops.linear_w8a8(x.view(1, M, C), fc1w, n_bits=blk.mlp.fc1.act_quantizer.n_bits,
+                                    smooth=getattr(fc1w, "smooth", None), ln=(shift_mlp, scale_mlp), rows_per_mod=N).view(B, N, -1)
+            else:
+                a, _ = ops.ln_modulate_act_quant(x.view(1, M, C) if independent else x, shift_mlp, scale_mlp,
+                                                 n_bits=blk.mlp.fc1.act_quantizer.n_bits,
+                                                 smooth=getattr(fc1w, "smooth", None), rows_per_mod=N if independent else None)
+                h = ops.gemm_w8a8(a, fc1w).view(B, N, -1)
             a = qi(blk.mlp.fc2, h, gelu=True)
             ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_mlp, rows_per_gate=N, out=xr)
         return x
