@@ -69,7 +69,8 @@ struct GemmArgs {
 };
 
 constexpr int QP_THREADS = 640;           // 4 control warps + 8 epilogue warps + 8 quantiser warps
-constexpr int QP_ROWS = 2;                // rows a quantiser warp takes from the work queue at a time
+constexpr int QP_ROWS = 2;                // rows a quantiser warp keeps in flight
+constexpr int QP_GRAB = 8;                // rows it takes from the work queue per atomic (one flag update per grab)
 constexpr int QP_REGS_CONTROL = 40;       // setmaxnreg budgets per warpgroup: 128 x 40 + 256 x 144 + 256 x 72 = 60416 <= 640 x 96
 constexpr int QP_REGS_EPILOGUE = 144;
 constexpr int QP_REGS_QUANT = 72;

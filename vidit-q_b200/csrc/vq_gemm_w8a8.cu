@@ -225,45 +225,48 @@ vq_gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // work queue of row batches in ascending order; one warp per row, QP_ROWS rows in flight
     const int KQ = 9 * 128;
     for (;;) {
-      int r0 = 0;
-      if (lane == 0) r0 = static_cast<int>(atomicAdd(p.q_sync, static_cast<uint32_t>(QP_ROWS)));
-      r0 = __shfl_sync(0xffffffffu, r0, 0);
-      if (r0 >= p.M) break;
-      UnitRegs<9> regs[QP_ROWS];
-#pragma unroll
-      for (int b = 0; b < QP_ROWS; ++b)
-        if (r0 + b < p.M) uload_row<9>(regs[b], p.qx + static_cast<size_t>(r0 + b) * KQ, lane);
+      int g0 = 0;
+      if (lane == 0) g0 = static_cast<int>(atomicAdd(p.q_sync, static_cast<uint32_t>(QP_GRAB)));
+      g0 = __shfl_sync(0xffffffffu, g0, 0);
+      if (g0 >= p.M) break;
       int nvalid = 0;
+#pragma unroll 1
+      for (int r0 = g0; r0 < g0 + QP_GRAB && r0 < p.M; r0 += QP_ROWS) {
+        UnitRegs<9> regs[QP_ROWS];
 #pragma unroll
-      for (int b = 0; b < QP_ROWS; ++b) {
-        const int row = r0 + b;
-        if (row < p.M) {
-          if (QPRO == 2) {
-            const size_t mo = static_cast<size_t>(row / p.q_rows_per_mod) * KQ;
-            uapply_ln_modulate<9>(regs[b], p.q_shift + mo, p.q_scale + mo, KQ, lane);
+        for (int b = 0; b < QP_ROWS; ++b)
+          if (r0 + b < p.M) uload_row<9>(regs[b], p.qx + static_cast<size_t>(r0 + b) * KQ, lane);
+#pragma unroll
+        for (int b = 0; b < QP_ROWS; ++b) {
+          const int row = r0 + b;
+          if (row < p.M) {
+            if (QPRO == 2) {
+              const size_t mo = static_cast<size_t>(row / p.q_rows_per_mod) * KQ;
+              uapply_ln_modulate<9>(regs[b], p.q_shift + mo, p.q_scale + mo, KQ, lane);
+            }
+            if (p.q_smooth) uapply_smooth<9>(regs[b], p.q_smooth, lane);
+            __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;   // the range always contains zero
+            urow_minmax<9>(regs[b], mn2, mx2);
+            float mn, mx;
+            warp_minmax(mn2, mx2, mn, mx);
+            const RowStats st = make_stats(mn, mx, p.q_qmax);
+            const QuantConsts qc = make_consts(st.delta, st.zp, p.q_qmax);
+            int sum = uquant_store_row<9>(regs[b], p.q_codes + static_cast<size_t>(row) * KQ, lane, qc);
+            sum = warp_sum_i(sum);
+            if (lane == 0) {
+              const_cast<__half*>(p.a_delta)[row] = __float2half_rn(st.delta);
+              const_cast<__half*>(p.a_zp)[row] = __float2half_rn(st.zp);
+              const_cast<int32_t*>(p.a_rowsum)[row] = sum;
+              if (st.degenerate && p.q_status) atomicOr(p.q_status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
+            }
+            ++nvalid;
           }
-          if (p.q_smooth) uapply_smooth<9>(regs[b], p.q_smooth, lane);
-          __half2 mn2 = __float2half2_rn(0.f), mx2 = mn2;   // the range always contains zero
-          urow_minmax<9>(regs[b], mn2, mx2);
-          float mn, mx;
-          warp_minmax(mn2, mx2, mn, mx);
-          const RowStats st = make_stats(mn, mx, p.q_qmax);
-          const QuantConsts qc = make_consts(st.delta, st.zp, p.q_qmax);
-          int sum = uquant_store_row<9>(regs[b], p.q_codes + static_cast<size_t>(row) * KQ, lane, qc);
-          sum = warp_sum_i(sum);
-          if (lane == 0) {
-            const_cast<__half*>(p.a_delta)[row] = __float2half_rn(st.delta);
-            const_cast<__half*>(p.a_zp)[row] = __float2half_rn(st.zp);
-            const_cast<int32_t*>(p.a_rowsum)[row] = sum;
-            if (st.degenerate && p.q_status) atomicOr(p.q_status, static_cast<uint32_t>(VQ_STATUS_EPS_DEGENERATE));
-          }
-          ++nvalid;
         }
       }
-      // every lane's stores before the panel's flag: fence, converge, one release-add (QP_ROWS divides TILE_M: one panel)
-      __threadfence();
+      // all lanes' stores are ordered before lane 0's release by the warp barrier (causality order; the release is
+      // cumulative); QP_GRAB divides TILE_M, so a grab lies in one m-panel
       __syncwarp();
-      if (lane == 0) red_release_gpu_add(p.q_sync + 1 + r0 / TILE_M, static_cast<uint32_t>(nvalid));
+      if (lane == 0) red_release_gpu_add(p.q_sync + 1 + g0 / TILE_M, static_cast<uint32_t>(nvalid));
     }
   } else {
     // ===================== epilogue (warps 4-11) =====================
