@@ -140,7 +140,9 @@ int vq_col_absmax(const void* x, int G, int n, int K, int gelu, uint32_t* out_bi
  * out_delta / out_zp (optional, may be NULL): fp16 [rows] per-token parameters, the DynamicActQuantizer side state.     */
 int64_t vq_linear_workspace_bytes(int G, int rows, int K);
 int vq_linear_launch_count(int G, int rows, int K);   /* 1 = fused kernel, 2 = quantise pass + GEMM */
-/* mode 0: never fuse (default); 1: fuse every supported shape; -1: fuse supported shapes with G * rows <= max_m */
+/* mode 0: quantise pass + GEMM (default); 1: panel-resident fused kernel on every supported shape; -1: the same for
+ * G * rows <= max_m; 2: overlapped — the persistent GEMM with quantiser warpgroups running ahead of its MMAs (K = 1152, G = 1,
+ * >= 1024 rows, bias / gated-residual epilogue; other shapes as mode 0)                                                   */
 int vq_linear_set_fused_policy(int mode, int64_t max_m);
 int vq_linear_w8a8(const void* x, int G, int rows, int K, const void* smooth, const void* ln_shift, const void* ln_scale,
                    int rows_per_mod, int n_bits, const uint8_t* w_codes, const VqColParam* col, int N, int epi,
