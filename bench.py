@@ -519,8 +519,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfcheck", action="store_true", help="skip the multi-GPU bit-identity self-check (N >= 2)")
     ap.add_argument("--no-peak", action="store_true", help="skip the INT8 peak measurement (roofline then uses the proxy)")
-    ap.add_argument("--cfg-mode", default="stacked", choices=["stacked", "split"],
-                    help="cfg_split's cond / uncond forwards as one stacked launch sequence (default) or two calls")
+    ap.add_argument("--cfg-mode", default="stacked", choices=["stacked", "split", "split2"],
+                    help="cfg_split's cond / uncond forwards as one stacked launch sequence (default), as two calls, or as two "
+                         "calls on two CUDA streams (split2: one branch's tail waves and HBM-bound passes may overlap the other's)")
     ap.add_argument("--parallelism", default="samples", choices=["samples", "cfg-branch", "frames"],
                     help="samples: one sample per rank, no data-path collective (the metric, weak scaling). cfg-branch: "
                          "two ranks per sample, one CFG branch each, model outputs exchanged every step (latency / "
@@ -617,6 +618,7 @@ def main():
         hook = args.schedule == "hook"
         if hook:
             use_graph = False
+        side_streams = [torch.cuda.Stream(), torch.cuda.Stream()] if args.cfg_mode == "split2" else []
 
         def step_device():
             """The denoise step on device-resident inputs (iddpm forward_with_cfg + ddim_sample, cfg_split): the cond and
@@ -636,6 +638,16 @@ def main():
                 out = model.forward_fused(torch.cat([d_z, d_z]), d_t.expand(2), d_y, plan=plan, segments=segments,
                                           independent=True)
                 out_c, out_u = out[:1], out[1:]
+            elif args.cfg_mode == "split2":
+                cur = torch.cuda.current_stream()
+                for st_ in side_streams:
+                    st_.wait_stream(cur)
+                with torch.cuda.stream(side_streams[0]):
+                    out_c = model.forward_fused(d_z, d_t, d_yc, plan=plan1, segments=segments1)
+                with torch.cuda.stream(side_streams[1]):
+                    out_u = model.forward_fused(d_z, d_t, d_yu, plan=plan1, segments=segments1)
+                for st_ in side_streams:
+                    cur.wait_stream(st_)
             else:
                 out_c = model.forward_fused(d_z, d_t, d_yc, plan=plan1, segments=segments1)
                 out_u = model.forward_fused(d_z, d_t, d_yu, plan=plan1, segments=segments1)
