@@ -821,7 +821,10 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = tt.tolist()
         if world % 2 == 0 and wl == "stdit" and not args.no_selfcheck:
-            parity = multi_gpu_selfcheck(dev, world, rank)
+            try:
+                parity = multi_gpu_selfcheck(dev, world, rank)
+            except Exception as e:      # the record must not cost the bench line
+                parity = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if rank == 0:
         n_samples = world // 2 if pairs else (1 if fsh else world)
         value = n_samples * args.steps / (ms * 1e-3)
