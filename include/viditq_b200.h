@@ -192,6 +192,22 @@ int vq_attn_temporal_quant(const void* qkv, int B, int T, int S, int H, int head
  * accumulators; head_dim must be 72 and S a multiple of 256. scale = head_dim^-0.5.                                  */
 int vq_attn_spatial(const void* qkv, void* out, int n_seq, int S, int H, int head_dim, float scale, void* stream);
 
+/* (J3, opt-in) spatial self-attention that consumes INT8 Q / K / V: both matrix products on tcgen05.mma.kind::i8.
+ * NO reference counterpart — the reference never quantises Q / K / V or the probabilities (hooks commented out,
+ * qdiff/models/quant_block.py:617-623, :630-632; blocks.py:169-188 runs flash-attn on the fp16 linear outputs) — so the
+ * default path stays vq_attn_spatial and this entry carries its own tolerance (restated by
+ * oracle/attn_i8_oracle.py).  Scheme: Q8 per (token, head), K8 = rint((K - mean_tokens K) / sk) per (64-key block, head),
+ * V8 per (sequence, channel), P8 = rint(127 * 2^(x - m)) as u8; integer accumulation is exact.
+ *   vq_attn_i8_workspace_bytes  size of the operand workspace (codes + scales) for a shape, -1 if unsupported
+ *   vq_attn_i8_quantise         q|k|v fp16 [n_seq*S, 3*H*72] -> workspace (two passes: per-sequence statistics, codes)
+ *   vq_attn_i8_attend           workspace -> out fp16 [n_seq*S, H*72] token-major (one persistent tcgen05 kernel)
+ *   vq_attn_spatial_i8          both.  workspace: 256-byte aligned device memory; head_dim 72, S a multiple of 256.     */
+int64_t vq_attn_i8_workspace_bytes(int n_seq, int S, int H, int head_dim);
+int vq_attn_i8_quantise(const void* qkv, void* workspace, int n_seq, int S, int H, int head_dim, void* stream);
+int vq_attn_i8_attend(const void* workspace, void* out, int n_seq, int S, int H, int head_dim, float scale, void* stream);
+int vq_attn_spatial_i8(const void* qkv, void* out, void* workspace, int n_seq, int S, int H, int head_dim, float scale,
+                       void* stream);
+
 /* (a9) cross attention (blocks.py:292-310, xformers BlockDiagonalMask.from_seqlens([N]*B, y_lens)): q fp16
  * [B*N, H*head_dim]; kv fp16 [kv_rows, 2*H*head_dim] (k | v), kv_rows = sum(len) = the rows actually allocated (the
  * TMA tensor map is bounded by it); kv_start / kv_len: device int32 [B]; max_len <= 128.  N a multiple of 256 runs on

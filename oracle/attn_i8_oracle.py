@@ -1,0 +1,107 @@
+"""CPU restatement of the opt-in INT8 Q/K/V spatial attention (`vq_attn_spatial_i8`) — TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED BY CONSTRUCTION: the reference never quantises Q / K / V or the probabilities — the hooks are commented
+out (qdiff/models/quant_block.py:617-623, :630-632) and STDiT / PixArt attention runs flash-attn on the fp16 linear
+outputs (t2v/opensora/models/layers/blocks.py:169-188).  There is therefore no reference output to pin this against;
+the scheme below is this repo's own (opt-in, own tolerance), and the tests state two tolerances:
+kernel vs this restatement (same integers, fp32 softmax), and this scheme vs the fp16 attention the reference computes.
+
+Scheme (per sequence of S tokens, per head, head_dim 72):
+  Q8 = rint(Q / sq), sq = max|Q[token, head, :]| / 127                        per token, per head
+  K' = K - mean over the sequence's tokens (softmax is invariant to it);
+  K8 = rint(K' / sk), sk = max|K'[64-token block, head, :]| / 127             per 64-key block, per head
+  V8 = rint(V / sv), sv = max|V[:, head, dim]| / 127 over the sequence        per channel
+  S  = (Q8 K8^T) * sq * sk * scale      integer dot products, exact
+  P8 = rint(127 * exp(S - m)) as u8 (m = the running row maximum: P8 <= 254 with the lazy threshold of one octave)
+  O  = (sum_k P8 V8) * sv / sum_k (127 * exp(S - m))                          integer accumulation, exact
+The restatement takes the exact row maximum (no lazy rescale): the kernel's deviations from it are its in-place integer
+rescales (<= 0.5 LSB of a >= 2^10 accumulator each) and P8 rounded against a maximum that lags by < 1 octave.
+"""
+import torch
+
+BLOCK_K = 64
+
+
+def quantise_qkv(qkv, n_seq, S, H, D=72, kmean=None):
+    """qkv [n_seq * S, 3 * H * D] fp16/fp32 -> dict of integer codes and scales (fp32 arithmetic, the kernel's formulas).
+    kmean [n_seq, H, D]: use this mean of K instead of computing it (a sum over 1024 tokens depends on the summation
+    order in its last bits; the code tests feed the kernel's own mean so that the codes compare bit for bit)."""
+    x = qkv.float().reshape(n_seq, S, 3, H, D)
+    q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]
+    kmean = k.mean(dim=1, keepdim=True) if kmean is None else kmean.float().reshape(n_seq, 1, H, D)
+    ks = k - kmean
+    sq = q.abs().amax(dim=-1) / 127.0                                   # [n_seq, S, H]
+    sq = torch.where(sq > 0, sq, torch.ones_like(sq))
+    q8 = torch.clamp(torch.round(q / sq[..., None]), -127, 127)
+    kb = ks.reshape(n_seq, S // BLOCK_K, BLOCK_K, H, D)
+    sk = kb.abs().amax(dim=(2, 4)) / 127.0                              # [n_seq, S / 64, H]
+    sk = torch.where(sk > 0, sk, torch.ones_like(sk))
+    k8 = torch.clamp(torch.round(kb / sk[:, :, None, :, None]), -127, 127).reshape(n_seq, S, H, D)
+    sv = v.abs().amax(dim=1) / 127.0                                    # [n_seq, H, D]
+    sv = torch.where(sv > 0, sv, torch.ones_like(sv))
+    v8 = torch.clamp(torch.round(v / sv[:, None]), -127, 127)
+    return dict(q8=q8, k8=k8, v8=v8, sq=sq, sk=sk, sv=sv, kmean=kmean[:, 0])
+
+
+def attention_i8(qkv, n_seq, S, H, scale, D=72):
+    """The scheme end to end; returns [n_seq * S, H * D] fp32."""
+    z = quantise_qkv(qkv, n_seq, S, H, D)
+    q8, k8, v8 = (z[n].permute(0, 2, 1, 3).double() for n in ("q8", "k8", "v8"))        # [n_seq, H, S, D]
+    s_int = q8 @ k8.transpose(-1, -2)                                                   # exact integers
+    sq = z["sq"].permute(0, 2, 1)[..., None].double()                                   # [n_seq, H, S, 1]
+    sk = z["sk"].permute(0, 2, 1).repeat_interleave(BLOCK_K, dim=-1)[:, :, None, :].double()
+    s = s_int * sq * sk * scale
+    m = s.amax(dim=-1, keepdim=True)
+    e = 127.0 * torch.exp(s - m)
+    p8 = torch.round(e)
+    o_int = p8 @ v8
+    o = o_int * z["sv"][:, :, None, :].double() / e.sum(dim=-1, keepdim=True)
+    return o.permute(0, 2, 1, 3).reshape(n_seq * S, H * D).float()
+
+
+def attention_fp(qkv, n_seq, S, H, scale, D=72):
+    """What the reference computes (blocks.py:169-188), in fp64 on the fp16 inputs."""
+    x = qkv.double().reshape(n_seq, S, 3, H, D).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(x[0] @ x[1].transpose(-1, -2) * scale, dim=-1)
+    return (p @ x[2]).permute(0, 2, 1, 3).reshape(n_seq * S, H * D).float()
+
+
+def attention_i8_tiled(z, scale, tile=128, warp=32):
+    """The kernel's own order of operations on the codes / scales `z` (quantise_qkv's dict): 64-key tiles, a running
+    maximum that is only raised when a row of the 32-row warp exceeds it by more than one octave, the in-place integer
+    rescale of the accumulators, P8 rounded against the lagging maximum.  fp32 where the kernel computes in fp32."""
+    q8, k8, v8 = (z[n].permute(0, 2, 1, 3).contiguous() for n in ("q8", "k8", "v8"))     # [n_seq, H, S, D]
+    n_seq, H, S, D = q8.shape
+    f32 = torch.float32
+    scale_log2e = (torch.tensor(scale, dtype=f32) * torch.tensor(1.4426950408889634, dtype=f32))
+    c_row = z["sq"].permute(0, 2, 1).to(f32) * scale_log2e                                # [n_seq, H, S]
+    sk = z["sk"].permute(0, 2, 1).to(f32)                                                 # [n_seq, H, S / 64]
+    lg127 = torch.tensor(6.988684686772166, dtype=f32)
+    m_used = torch.zeros(n_seq, H, S, dtype=f32)
+    l = torch.zeros(n_seq, H, S, dtype=f32)
+    o = torch.zeros(n_seq, H, S, D, dtype=torch.int64)
+    for j in range(S // BLOCK_K):
+        kt = k8[:, :, j * BLOCK_K:(j + 1) * BLOCK_K].double()
+        s_int = (q8.double() @ kt.transpose(-1, -2))                                      # exact integers
+        c_rt = c_row * sk[:, :, j:j + 1]
+        mx = s_int.amax(dim=-1).to(f32) * c_rt
+        if j == 0:
+            m_used = mx.clone()
+        else:
+            need = (mx - m_used) > 1.0
+            trig = need.reshape(n_seq, H, S // warp, warp).any(dim=-1, keepdim=True).expand(-1, -1, -1, warp)
+            trig = trig.reshape(n_seq, H, S)
+            m_new = torch.maximum(m_used, mx)
+            f = torch.exp2((m_used - m_new).double()).to(f32)
+            f = torch.where(trig, f, torch.ones_like(f))
+            o_resc = torch.round((o.to(f32) * f[..., None]).double()).to(torch.int64)
+            o = torch.where(trig[..., None], o_resc, o)
+            l = torch.where(trig, l * f, l)
+            m_used = torch.where(trig, m_new, m_used)
+        x = (s_int * c_rt[..., None].double() + (lg127 - m_used)[..., None].double()).to(f32)
+        e = torch.exp2(x.double()).to(f32)
+        p8 = torch.round(e.double())                                                       # half to even, as the magic add
+        l = l + e.double().sum(dim=-1).to(f32)
+        o = o + (p8 @ v8[:, :, j * BLOCK_K:(j + 1) * BLOCK_K].double()).to(torch.int64)
+    out = o.double() * z["sv"][:, :, None, :].double() / l[..., None].double()
+    return out.permute(0, 2, 1, 3).reshape(n_seq * S, H * D).float()

@@ -15,7 +15,7 @@ _ERR = {-1: "VQ_ERR_ARG", -2: "VQ_ERR_DRIVER", -3: "VQ_ERR_TMAP", -4: "VQ_ERR_LA
 
 EXPORTS = ["vq_version", "vq_num_sms", "vq_prep_weight", "vq_act_quant", "vq_act_quant_static", "vq_add_act_quant", "vq_gelu_act_quant", "vq_act_quant_heads", "vq_ln_modulate_act_quant", "vq_gemm_w8a8",
            "vq_col_absmax", "vq_row_pack", "vq_linear_w8a8", "vq_linear_workspace_bytes", "vq_linear_launch_count", "vq_linear_set_fused_policy", "vq_pack_u4", "vq_linear_w4a8",
-           "vq_attn_temporal", "vq_attn_temporal_quant", "vq_attn_cross", "vq_attn_spatial", "vq_cfg_ddim_step", "vq_patch_embed", "vq_status_read"]
+           "vq_attn_temporal", "vq_attn_temporal_quant", "vq_attn_cross", "vq_attn_spatial", "vq_attn_i8_workspace_bytes", "vq_attn_i8_quantise", "vq_attn_i8_attend", "vq_attn_spatial_i8", "vq_cfg_ddim_step", "vq_patch_embed", "vq_status_read"]
 
 _lib = None
 
@@ -57,6 +57,10 @@ def lib():
     f32 = ctypes.c_float
     L.vq_attn_temporal.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp]
     L.vq_attn_spatial.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    L.vq_attn_i8_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.vq_attn_i8_quantise.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.vq_attn_i8_attend.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    L.vq_attn_spatial_i8.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, vp]
     L.vq_attn_temporal_quant.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, i32, vp, vp, vp, vp, vp, vp]
     L.vq_attn_cross.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, f32, vp]
     L.vq_cfg_ddim_step.argtypes = [vp, vp, vp, vp, f32, ctypes.c_double, i32, i32, i32, i64, vp, vp]
@@ -65,6 +69,7 @@ def lib():
     for name in EXPORTS:
         getattr(L, name).restype = i32
     L.vq_linear_workspace_bytes.restype = i64
+    L.vq_attn_i8_workspace_bytes.restype = i64
     _lib = L
     return L
 

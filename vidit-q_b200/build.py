@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libviditq_b200.so")
 # tuning / measurement build: the bisection epilogues of the GEMM (mainloop-only etc.) exist only here
 DEBUG_LIB = "libviditq_b200_dbg.so"
 DEBUG_DEFINES = ("VQ_DEBUG_EPI",)
-SOURCES = ["vq_gemm_w8a8.cu", "vq_linear.cu", "vq_quant.cu", "vq_attention.cu", "vq_attn_spatial.cu", "vq_sampler.cu",
+SOURCES = ["vq_gemm_w8a8.cu", "vq_linear.cu", "vq_quant.cu", "vq_attention.cu", "vq_attn_spatial.cu", "vq_attn_i8.cu", "vq_sampler.cu",
            "vq_embed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

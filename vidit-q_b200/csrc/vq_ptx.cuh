@@ -412,6 +412,29 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, ui
   return (1u << 4) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ----------------------------------------------------------------------------- INT8 attention (vq_attn_i8.cu)
+// 3-D tiled load global -> shared with an L2 cache-policy operand
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1,
+                                                 int32_t c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+// kind::i8 with the A operand read from TMEM (K-major: lane = row, four 8-bit elements per 32-bit column)
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // L2 cache-policy words for TMA cache hints (createpolicy results are architectural constants).
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

@@ -477,6 +477,52 @@ def attn_spatial(qkv, n_seq, S, H, head_dim, scale, out=None):
     return out
 
 
+_i8_workspaces = {}    # (device index, stream handle) -> operand workspace of attn_spatial_i8 (separate from the linear scratch)
+
+
+def attn_i8_workspace_layout(n_seq, S, H, head_dim=72):
+    """Byte offsets of the pieces inside vq_attn_spatial_i8's workspace (mirrors ia_layout in vq_attn_i8.cu); tests read
+    the codes and scales through it."""
+    rows, C = n_seq * S, H * head_dim
+    up = lambda v: (v + 255) & ~255
+    off = {"qk8": 0}
+    off["vt8"] = up(rows * 2 * H * 80)
+    off["sq"] = up(off["vt8"] + n_seq * C * S)
+    off["sk"] = up(off["sq"] + rows * H * 4)
+    off["sv"] = up(off["sk"] + rows // 64 * H * 4)
+    off["kmean"] = up(off["sv"] + n_seq * C * 4)
+    off["total"] = up(off["kmean"] + n_seq * C * 4)
+    return off
+
+
+@_nvtx
+def attn_spatial_i8(qkv, n_seq, S, H, head_dim, scale, out=None, workspace=None):
+    """OPT-IN INT8 Q/K/V attention (vq_attn_spatial_i8; no reference counterpart, own tolerance — DESIGN.md 4.2d).
+    Same contract as attn_spatial: qkv fp16 [n_seq*S, 3*H*72] -> fp16 [n_seq*S, H*72]; three launches (per-sequence
+    statistics, operand codes, the tcgen05 kind::i8 attention kernel)."""
+    _need_cuda_f16(qkv, "qkv")
+    C = H * head_dim
+    if qkv.shape != (n_seq * S, 3 * C):
+        raise _lib.VqError(f"attn_spatial_i8: qkv shape {tuple(qkv.shape)} != {(n_seq * S, 3 * C)}")
+    L = _lib.lib()
+    nbytes = L.vq_attn_i8_workspace_bytes(n_seq, S, H, head_dim)
+    if nbytes < 0:
+        raise _lib.VqError(f"attn_spatial_i8: unsupported shape S={S} head_dim={head_dim}")
+    if workspace is None:
+        key = (qkv.device.index, _stream())
+        workspace = _i8_workspaces.get(key)
+        if workspace is None or workspace.numel() < nbytes:
+            workspace = _i8_workspaces[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=qkv.device)
+    elif workspace.numel() < nbytes:
+        raise _lib.VqError(f"attn_spatial_i8: workspace of {workspace.numel()} bytes < {nbytes}")
+    if out is None:
+        out = torch.empty((n_seq * S, C), dtype=torch.float16, device=qkv.device)
+    rc = L.vq_attn_spatial_i8(_ptr(qkv), _ptr(out), _ptr(workspace), n_seq, S, H, head_dim, float(scale), _stream())
+    _lib.check(rc, "vq_attn_spatial_i8")
+    _count(3)
+    return out
+
+
 def attn_spatial_supported(S, head_dim):
     return head_dim == 72 and S >= 256 and S % 256 == 0
 

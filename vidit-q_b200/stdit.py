@@ -359,6 +359,10 @@ class FusedBlocks:
         # 135 KB block runs one per SM: no second block to cover its load and barrier phases), equal step time under the
         # power cap — so the two-kernel sequence stays the default
         self.temporal_fused_quant = os.environ.get("VQ_TEMPORAL_FUSED_QUANT", "0") == "1"
+        # VQ_ATTN_INT8=1 (or .attn_int8 = True): OPT-IN spatial attention that consumes INT8 Q/K/V on tcgen05 kind::i8
+        # (vq_attn_spatial_i8).  The reference keeps attention in fp16 (its Q/K/V quantisers are commented out,
+        # quant_block.py:617-632), so this leaves the reference's numerics: own tolerance, DESIGN.md 4.2d.  Default off.
+        self.attn_int8 = os.environ.get("VQ_ATTN_INT8", "0") == "1"
 
     @staticmethod
     def _spatial_library(qkv, pj, scale, B, N, T, S, C, D, independent):
@@ -502,7 +506,7 @@ class FusedBlocks:
             xr = x.view(M, C)   # residual stream, updated in place: out aliases res
             if self.own_spatial and ops.attn_spatial_supported(S, D):
                 # tcgen05 flash attention reading q|k|v in place, token-major output: the projection's quantiser input
-                o = ops.attn_spatial(qkv, B * T, S, H, D, blk.attn.scale)
+                o = (ops.attn_spatial_i8 if self.attn_int8 else ops.attn_spatial)(qkv, B * T, S, H, D, blk.attn.scale)
                 self._qlin(pj, o.view(B * T, S, C), qi, unpooled, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                            rows_per_gate=N, out=xr)
             else:
