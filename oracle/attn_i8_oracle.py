@@ -7,15 +7,14 @@ the scheme below is this repo's own (opt-in, own tolerance), and t
 kernel vs this restatement (same integers, fp32 softmax), and this scheme vs the fp16 attention the reference computes.
 
 Scheme (per sequence of S tokens, per head, head_dim 72):
-  Q8 = rint(Q / sq), sq = max|Q[token, head, :]| / 127                        per token, per head
+  Q8 = rint(Q * (1 / sq)), sq = max|Q[token, head, :]| / 127                  per token, per head (fp32: one reciprocal
+                                                                              per scale, then products — K8, V8 alike)
   K' = K - mean over the sequence's tokens (softmax is invariant to it);
   K8 = rint(K' / sk), sk = max|K'[64-token block, head, :]| / 127             per 64-key block, per head
   V8 = rint(V / sv), sv = max|V[:, head, dim]| / 127 over the sequence        per channel
   S  = (Q8 K8^T) * sq * sk * scale      integer dot products, exact
-  P8 = rint(127 * exp(S - m)) as u8 (m = the running row maximum: P8 <= 254 with the lazy threshold of one octave)
-  O  = (sum_k P8 V8) * sv / sum_k (127 * exp(S - m))                          integer accumulation, exact
-The restatement takes the exact row maximum (no lazy rescale): the kernel's deviations from it are its in-place integer
-rescales (<= 0.5 LSB of a >= 2^10 accumulator each) and P8 rounded against a maximum that lags by < 1 octave.
+  P8 = rint(255 * exp(S - m)) as u8, m = the exact row maximum (the kernel takes it in a first pass over the key tiles)
+  O  = (sum_k P8 V8) * sv / sum_k (255 * exp(S - m))                          integer accumulation, exact
 """
 import torch
 
@@ -32,14 +31,14 @@ def quantise_qkv(qkv, n_seq, S, H, D=72, kmean=None):
     ks = k - kmean
     sq = q.abs().amax(dim=-1) / 127.0                                   # [n_seq, S, H]
     sq = torch.where(sq > 0, sq, torch.ones_like(sq))
-    q8 = torch.clamp(torch.round(q / sq[..., None]), -127, 127)
+    q8 = torch.clamp(torch.round(q * (1.0 / sq)[..., None]), -127, 127)        # one reciprocal per scale, fp32 products
     kb = ks.reshape(n_seq, S // BLOCK_K, BLOCK_K, H, D)
     sk = kb.abs().amax(dim=(2, 4)) / 127.0                              # [n_seq, S / 64, H]
     sk = torch.where(sk > 0, sk, torch.ones_like(sk))
-    k8 = torch.clamp(torch.round(kb / sk[:, :, None, :, None]), -127, 127).reshape(n_seq, S, H, D)
+    k8 = torch.clamp(torch.round(kb * (1.0 / sk)[:, :, None, :, None]), -127, 127).reshape(n_seq, S, H, D)
     sv = v.abs().amax(dim=1) / 127.0                                    # [n_seq, H, D]
     sv = torch.where(sv > 0, sv, torch.ones_like(sv))
-    v8 = torch.clamp(torch.round(v / sv[:, None]), -127, 127)
+    v8 = torch.clamp(torch.round(v * (1.0 / sv)[:, None]), -127, 127)
     return dict(q8=q8, k8=k8, v8=v8, sq=sq, sk=sk, sv=sv, kmean=kmean[:, 0])
 
 
@@ -52,7 +51,7 @@ def attention_i8(qkv, n_seq, S, H, scale, D=72):
     sk = z["sk"].permute(0, 2, 1).repeat_interleave(BLOCK_K, dim=-1)[:, :, None, :].double()
     s = s_int * sq * sk * scale
     m = s.amax(dim=-1, keepdim=True)
-    e = 127.0 * torch.exp(s - m)
+    e = 255.0 * torch.exp(s - m)
     p8 = torch.round(e)
     o_int = p8 @ v8
     o = o_int * z["sv"][:, :, None, :].double() / e.sum(dim=-1, keepdim=True)
@@ -66,42 +65,25 @@ def attention_fp(qkv, n_seq, S, H, scale, D=72):
     return (p @ x[2]).permute(0, 2, 1, 3).reshape(n_seq * S, H * D).float()
 
 
-def attention_i8_tiled(z, scale, tile=128, warp=32):
-    """The kernel's own order of operations on the codes / scales `z` (quantise_qkv's dict): 64-key tiles, a running
-    maximum that is only raised when a row of the 32-row warp exceeds it by more than one octave, the in-place integer
-    rescale of the accumulators, P8 rounded against the lagging maximum.  fp32 where the kernel computes in fp32."""
-    q8, k8, v8 = (z[n].permute(0, 2, 1, 3).contiguous() for n in ("q8", "k8", "v8"))     # [n_seq, H, S, D]
+def attention_i8_tiled(z, scale):
+    """The kernel's own order of operations on the codes / scales `z` (quantise_qkv's dict), fp32 where the kernel
+    computes in fp32: pass A takes the row maximum tile by tile (integer maximum x the tile's fp32 scale), pass B forms
+    x = fma(S, c, log2(255) - m), P8 = rint(2^x), the fp32 row sum of the un-rounded 2^x and the exact integer P8 V8."""
+    q8, k8, v8 = (z[n].permute(0, 2, 1, 3).contiguous().double() for n in ("q8", "k8", "v8"))     # [n_seq, H, S, D]
     n_seq, H, S, D = q8.shape
     f32 = torch.float32
     scale_log2e = (torch.tensor(scale, dtype=f32) * torch.tensor(1.4426950408889634, dtype=f32))
     c_row = z["sq"].permute(0, 2, 1).to(f32) * scale_log2e                                # [n_seq, H, S]
     sk = z["sk"].permute(0, 2, 1).to(f32)                                                 # [n_seq, H, S / 64]
-    lg127 = torch.tensor(6.988684686772166, dtype=f32)
-    m_used = torch.zeros(n_seq, H, S, dtype=f32)
-    l = torch.zeros(n_seq, H, S, dtype=f32)
-    o = torch.zeros(n_seq, H, S, D, dtype=torch.int64)
-    for j in range(S // BLOCK_K):
-        kt = k8[:, :, j * BLOCK_K:(j + 1) * BLOCK_K].double()
-        s_int = (q8.double() @ kt.transpose(-1, -2))                                      # exact integers
-        c_rt = c_row * sk[:, :, j:j + 1]
-        mx = s_int.amax(dim=-1).to(f32) * c_rt
-        if j == 0:
-            m_used = mx.clone()
-        else:
-            need = (mx - m_used) > 1.0
-            trig = need.reshape(n_seq, H, S // warp, warp).any(dim=-1, keepdim=True).expand(-1, -1, -1, warp)
-            trig = trig.reshape(n_seq, H, S)
-            m_new = torch.maximum(m_used, mx)
-            f = torch.exp2((m_used - m_new).double()).to(f32)
-            f = torch.where(trig, f, torch.ones_like(f))
-            o_resc = torch.round((o.to(f32) * f[..., None]).double()).to(torch.int64)
-            o = torch.where(trig[..., None], o_resc, o)
-            l = torch.where(trig, l * f, l)
-            m_used = torch.where(trig, m_new, m_used)
-        x = (s_int * c_rt[..., None].double() + (lg127 - m_used)[..., None].double()).to(f32)
-        e = torch.exp2(x.double()).to(f32)
-        p8 = torch.round(e.double())                                                       # half to even, as the magic add
-        l = l + e.double().sum(dim=-1).to(f32)
-        o = o + (p8 @ v8[:, :, j * BLOCK_K:(j + 1) * BLOCK_K].double()).to(torch.int64)
-    out = o.double() * z["sv"][:, :, None, :].double() / l[..., None].double()
+    lg255 = torch.tensor(7.994353436858858, dtype=f32)
+    s_int = q8 @ k8.transpose(-1, -2)                                                     # exact integers [.., S, S]
+    c_rt = (c_row[..., None] * sk[:, :, None, :])                                         # fp32 [n_seq, H, S, S / 64]
+    tile_max = s_int.reshape(n_seq, H, S, S // BLOCK_K, BLOCK_K).amax(dim=-1).to(f32)
+    m = (tile_max * c_rt).amax(dim=-1)                                                    # fp32 products, then the maximum
+    neg = (lg255 - m)[..., None]
+    x = (s_int * c_rt.repeat_interleave(BLOCK_K, dim=-1).double() + neg.double()).to(f32)  # one rounding, as the FMA
+    e = torch.exp2(x.double()).to(f32)
+    p8 = torch.round(e.double())                                                          # half to even, as the magic add
+    l = e.double().sum(dim=-1)
+    out = (p8 @ v8) * z["sv"][:, :, None, :].double() / l[..., None]
     return out.permute(0, 2, 1, 3).reshape(n_seq * S, H * D).float()

@@ -60,12 +60,14 @@ constexpr int IA_SMEM_K = IA_QT * IA_QTILE;
 constexpr int IA_SMEM_V = IA_SMEM_K + IA_STAGES * IA_KTILE;
 constexpr int IA_SMEM_O = IA_SMEM_V + IA_STAGES * IA_VTILE;
 constexpr int IA_SMEM_BAR = IA_SMEM_O + IA_QT * IA_OSTAGE;
-constexpr int IA_SMEM_BYTES = IA_SMEM_BAR + 512 + 1024;
+constexpr int IA_SMEM_SCALES = IA_SMEM_BAR + 512;                   // 2 tiles x 2 parities x 136 floats
+constexpr int IA_SCALES = 136;                                      // 64 key-block scales (S <= 4096) + 72 V scales
+constexpr int IA_SMEM_BYTES = IA_SMEM_SCALES + IA_QT * 2 * IA_SCALES * 4 + 1024;
 constexpr int IA_THREADS = 384;
 constexpr uint32_t IA_TMEM_COLS = 512;
 constexpr uint32_t IA_O_COL = 256;         // O accumulators; S / P8 buffer b of tile t at t * 128 + b * 64
 constexpr float IA_MAGIC = 12582912.0f;    // 1.5 * 2^23
-constexpr float IA_LOG2_127 = 6.988684686772166f;
+constexpr float IA_LOG2_255 = 7.994353436858858f;
 
 struct AttnI8Args {
   int n_seq, S, H;
@@ -102,63 +104,88 @@ __device__ __forceinline__ float2 ia_exp2_poly(float2 x) {
 }
 
 // ----------------------------------------------------------------------------- operand preparation
-// per (sequence, channel): mean of K over the sequence's tokens, max |V| / 127.  block (128 half2 pairs, 8 token slices)
-__global__ void __launch_bounds__(1024) ia_stats_kernel(const __half* __restrict__ qkv, float* __restrict__ kmean,
-                                                        float* __restrict__ sv, int S, int C) {
+// per (sequence, channel): mean of K over the sequence's tokens, max |V| / 127.  Block = 32 chunks of 8 channels (16-byte
+// loads) x 16 token slices; a chunk lies entirely in the k part (sum) or the v part (maximum) of the row.
+__global__ void __launch_bounds__(512) ia_stats_kernel(const __half* __restrict__ qkv, float* __restrict__ kmean,
+                                                       float* __restrict__ sv, float* __restrict__ svi, int S, int C) {
   grid_dep_sync();
-  __shared__ float2 s_sum[8][128];
-  __shared__ float2 s_max[8][128];
+  __shared__ float s_acc[16][32][8];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int pair = blockIdx.x * 128 + tx;          // half2 index inside the k|v part of a row (C pairs)
+  const int col0 = (blockIdx.x * 32 + tx) * 8;     // first of this thread's 8 channels inside the k|v part (2C channels)
   const int seq = blockIdx.y;
-  float2 sum = make_float2(0.f, 0.f), mx = make_float2(0.f, 0.f);
-  if (pair < C) {
-    const __half2* src = reinterpret_cast<const __half2*>(qkv + static_cast<size_t>(seq) * S * 3 * C + C) + pair;
-    const size_t pitch = static_cast<size_t>(3 * C) / 2;
-    for (int tok = ty; tok < S; tok += 8) {
-      const float2 v = __half22float2(src[tok * pitch]);
-      sum.x += v.x;
-      sum.y += v.y;
-      mx.x = fmaxf(mx.x, fabsf(v.x));
-      mx.y = fmaxf(mx.y, fabsf(v.y));
+  const bool is_k = col0 < C;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col0 < 2 * C) {
+    const __half* src = qkv + static_cast<size_t>(seq) * S * 3 * C + C + col0;
+    for (int tok = ty; tok < S; tok += 16) {
+      const int4 raw = *reinterpret_cast<const int4*>(src + static_cast<size_t>(tok) * 3 * C);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = __half22float2(h2[i]);
+        if (is_k) {
+          acc[2 * i] += v.x;
+          acc[2 * i + 1] += v.y;
+        } else {
+          acc[2 * i] = fmaxf(acc[2 * i], fabsf(v.x));
+          acc[2 * i + 1] = fmaxf(acc[2 * i + 1], fabsf(v.y));
+        }
+      }
     }
   }
-  s_sum[ty][tx] = sum;
-  s_max[ty][tx] = mx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_acc[ty][tx][i] = acc[i];
   __syncthreads();
-  if (ty == 0 && pair < C) {
-    for (int i = 1; i < 8; ++i) {
-      sum.x += s_sum[i][tx].x;
-      sum.y += s_sum[i][tx].y;
-      mx.x = fmaxf(mx.x, s_max[i][tx].x);
-      mx.y = fmaxf(mx.y, s_max[i][tx].y);
-    }
-    const int col = 2 * pair;
-    if (col < C) {
-      const float inv = 1.0f / static_cast<float>(S);
-      kmean[static_cast<size_t>(seq) * C + col] = sum.x * inv;
-      kmean[static_cast<size_t>(seq) * C + col + 1] = sum.y * inv;
+  if (ty < 8 && col0 < 2 * C) {
+    // thread (tx, ty < 8) finishes channel col0 + ty
+    float r = s_acc[0][tx][ty];
+    for (int i = 1; i < 16; ++i) r = is_k ? r + s_acc[i][tx][ty] : fmaxf(r, s_acc[i][tx][ty]);
+    const int col = col0 + ty;
+    if (is_k) {
+      kmean[static_cast<size_t>(seq) * C + col] = r * (1.0f / static_cast<float>(S));
     } else {
-      const float a = mx.x / 127.0f, b = mx.y / 127.0f;
-      sv[static_cast<size_t>(seq) * C + col - C] = a > 0.f ? a : 1.0f;
-      sv[static_cast<size_t>(seq) * C + col - C + 1] = b > 0.f ? b : 1.0f;
+      float a = r / 127.0f;
+      a = a > 0.f ? a : 1.0f;
+      sv[static_cast<size_t>(seq) * C + col - C] = a;
+      svi[static_cast<size_t>(seq) * C + col - C] = 1.0f / a;
     }
   }
 }
 
-__device__ __forceinline__ int ia_code(float v, float s) {
-  const float r = rintf(__fdiv_rn(v, s));
-  return static_cast<int>(fminf(fmaxf(r, -127.0f), 127.0f));
+// code = rint(v * (1 / s)) clamped to +-127: one IEEE reciprocal per scale, then exact fp32 products — the oracle
+// (oracle/attn_i8_oracle.py quantise_qkv) evaluates the same two roundings
+__device__ __forceinline__ int ia_code(float v, float inv) {
+  return static_cast<int>(fminf(fmaxf(rintf(v * inv), -127.0f), 127.0f));
+}
+__device__ __forceinline__ uint32_t ia_pack4(int a, int b, int c, int d) {
+  return (static_cast<uint32_t>(a) & 0xffu) | ((static_cast<uint32_t>(b) & 0xffu) << 8) |
+         ((static_cast<uint32_t>(c) & 0xffu) << 16) | (static_cast<uint32_t>(d) << 24);
+}
+// 20 fp16 values of one (token, quarter row) from the staged tile (8-byte aligned), dims past `nd` read as zero
+__device__ __forceinline__ void ia_load20(const __half* tile, int token, int d0, int nd, float (&x)[20]) {
+  const __half* p = tile + token * IA_D + d0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    uint2 r = make_uint2(0u, 0u);
+    if (4 * i < nd) r = *reinterpret_cast<const uint2*>(p + 4 * i);
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    x[4 * i] = lo.x; x[4 * i + 1] = lo.y; x[4 * i + 2] = hi.x; x[4 * i + 3] = hi.y;
+  }
 }
 
-// per (64-token block, head): Q8 / K8 rows of 80 bytes, V8 transposed, the scales.  256 threads = 64 tokens x 4 quarter rows
-__global__ void __launch_bounds__(256) ia_quant_kernel(const __half* __restrict__ qkv, const float* __restrict__ kmean,
-                                                       const float* __restrict__ sv, int8_t* __restrict__ qk8,
-                                                       int8_t* __restrict__ vt8, float* __restrict__ sq,
-                                                       float* __restrict__ sk, int S, int H) {
+// per (64-token block, head): Q8 / K8 rows of 80 bytes, V8 transposed, the scales.  The three [64 x 72] fp16 tiles are
+// staged in shared memory with 16-byte loads, the codes leave through shared memory with 16-byte stores.  256 threads =
+// 64 tokens x 4 threads; thread `sub` owns dims [20 sub, 20 sub + 20) (sub 3: dims 60..71 and the 8 zero pad bytes).
+__global__ void __launch_bounds__(256, 3) ia_quant_kernel(const __half* __restrict__ qkv, const float* __restrict__ kmean,
+                                                          const float* __restrict__ svi, int8_t* __restrict__ qk8,
+                                                          int8_t* __restrict__ vt8, float* __restrict__ sq,
+                                                          float* __restrict__ sk, int S, int H) {
   grid_dep_sync();
-  __shared__ __align__(16) int8_t q_st[64 * IA_DP];
-  __shared__ __align__(16) int8_t k_st[64 * IA_DP];
+  __shared__ __align__(16) __half in_st[3][64 * IA_D];
+  __shared__ __align__(16) int8_t qk_st[2][64 * IA_DP];
   __shared__ __align__(16) int8_t v_st[IA_D * 64];
   __shared__ float s_red[8];
   const int C = H * IA_D;
@@ -167,66 +194,77 @@ __global__ void __launch_bounds__(256) ia_quant_kernel(const __half* __restrict_
   const size_t row0 = static_cast<size_t>(blockIdx.x) * 64;
   const size_t row = row0 + token;
   const int seq = static_cast<int>(row0 / S);
-  const int d0 = 18 * sub;
-  const __half2* src = reinterpret_cast<const __half2*>(qkv + row * 3 * C + h * IA_D + d0);
-  float q[18], k[18], v[18];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    const float2 a = __half22float2(src[i]);
-    const float2 b = __half22float2(src[C / 2 + i]);
-    const float2 c = __half22float2(src[C + i]);
-    q[2 * i] = a.x; q[2 * i + 1] = a.y;
-    k[2 * i] = b.x; k[2 * i + 1] = b.y;
-    v[2 * i] = c.x; v[2 * i + 1] = c.y;
+  const int d0 = 20 * sub;
+  const int nd = sub < 3 ? 20 : 12;
+  for (int c = tid; c < 3 * 64 * 9; c += 256) {
+    const int which = c / (64 * 9), r = (c % (64 * 9)) / 9, part = c % 9;
+    *reinterpret_cast<int4*>(&in_st[which][r * IA_D + part * 8]) =
+        *reinterpret_cast<const int4*>(qkv + (row0 + r) * 3 * C + which * C + h * IA_D + part * 8);
   }
+  __syncthreads();
+  float x[20];
+  // ---- Q: per (token, head) scale
+  ia_load20(in_st[0], token, d0, nd, x);
+  float am = 0.f;
+#pragma unroll
+  for (int i = 0; i < 20; ++i) am = fmaxf(am, fabsf(x[i]));
+  am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+  am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+  {
+    float s_q = am / 127.0f;
+    s_q = s_q > 0.f ? s_q : 1.0f;
+    const float inv = 1.0f / s_q;
+    if (sub == 0) sq[row * H + h] = s_q;
+    uint32_t* dq = reinterpret_cast<uint32_t*>(&qk_st[0][token * IA_DP + d0]);
+#pragma unroll
+    for (int w = 0; w < 5; ++w)
+      dq[w] = ia_pack4(ia_code(x[4 * w], inv), ia_code(x[4 * w + 1], inv), ia_code(x[4 * w + 2], inv),
+                       ia_code(x[4 * w + 3], inv));
+  }
+  // ---- K: minus the sequence mean, per (64-token block, head) scale
+  ia_load20(in_st[1], token, d0, nd, x);
   const float* km = kmean + static_cast<size_t>(seq) * C + h * IA_D + d0;
-  const float* svp = sv + static_cast<size_t>(seq) * C + h * IA_D + d0;
-  float qa = 0.f, ka = 0.f;
+  am = 0.f;
 #pragma unroll
-  for (int i = 0; i < 18; ++i) {
-    k[i] -= km[i];
-    qa = fmaxf(qa, fabsf(q[i]));
-    ka = fmaxf(ka, fabsf(k[i]));
+  for (int i = 0; i < 20; ++i) {
+    x[i] = i < nd ? x[i] - __ldg(km + i) : 0.f;
+    am = fmaxf(am, fabsf(x[i]));
   }
-  qa = fmaxf(qa, __shfl_xor_sync(0xffffffffu, qa, 1));
-  qa = fmaxf(qa, __shfl_xor_sync(0xffffffffu, qa, 2));
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ka = fmaxf(ka, __shfl_xor_sync(0xffffffffu, ka, o));
-  if ((tid & 31) == 0) s_red[tid >> 5] = ka;
+  for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = am;
   __syncthreads();
-  ka = s_red[0];
+  am = s_red[0];
 #pragma unroll
-  for (int i = 1; i < 8; ++i) ka = fmaxf(ka, s_red[i]);
-  float s_q = qa / 127.0f, s_k = ka / 127.0f;
-  s_q = s_q > 0.f ? s_q : 1.0f;
-  s_k = s_k > 0.f ? s_k : 1.0f;
-  if (sub == 0) sq[row * H + h] = s_q;
-  if (tid == 0) sk[static_cast<size_t>(blockIdx.x) * H + h] = s_k;
+  for (int i = 1; i < 8; ++i) am = fmaxf(am, s_red[i]);
+  {
+    float s_k = am / 127.0f;
+    s_k = s_k > 0.f ? s_k : 1.0f;
+    const float inv = 1.0f / s_k;
+    if (tid == 0) sk[static_cast<size_t>(blockIdx.x) * H + h] = s_k;
+    uint32_t* dk = reinterpret_cast<uint32_t*>(&qk_st[1][token * IA_DP + d0]);
 #pragma unroll
-  for (int i = 0; i < 18; ++i) {
-    q_st[token * IA_DP + d0 + i] = static_cast<int8_t>(ia_code(q[i], s_q));
-    k_st[token * IA_DP + d0 + i] = static_cast<int8_t>(ia_code(k[i], s_k));
-    v_st[(d0 + i) * 64 + token] = static_cast<int8_t>(ia_code(v[i], svp[i]));
+    for (int w = 0; w < 5; ++w)
+      dk[w] = ia_pack4(ia_code(x[4 * w], inv), ia_code(x[4 * w + 1], inv), ia_code(x[4 * w + 2], inv),
+                       ia_code(x[4 * w + 3], inv));
   }
-  if (sub == 3) {
+  // ---- V: per (sequence, channel) scale, transposed
+  ia_load20(in_st[2], token, d0, nd, x);
+  const float* svp = svi + static_cast<size_t>(seq) * C + h * IA_D + d0;
 #pragma unroll
-    for (int i = IA_D; i < IA_DP; ++i) {
-      q_st[token * IA_DP + i] = 0;
-      k_st[token * IA_DP + i] = 0;
-    }
-  }
+  for (int i = 0; i < 20; ++i)
+    if (i < nd) v_st[(d0 + i) * 64 + token] = static_cast<int8_t>(ia_code(x[i], __ldg(svp + i)));
   __syncthreads();
-  for (int c = tid; c < 64 * 5; c += 256) {
-    const int r = c / 5, part = c % 5;
-    int8_t* dq = qk8 + ((row0 + r) * 2 * H + h) * IA_DP + part * 16;
-    *reinterpret_cast<int4*>(dq) = *reinterpret_cast<const int4*>(q_st + r * IA_DP + part * 16);
-    *reinterpret_cast<int4*>(dq + static_cast<size_t>(H) * IA_DP) = *reinterpret_cast<const int4*>(k_st + r * IA_DP + part * 16);
+  for (int c = tid; c < 2 * 64 * 5; c += 256) {
+    const int which = c / (64 * 5), r = (c % (64 * 5)) / 5, part = c % 5;
+    *reinterpret_cast<int4*>(qk8 + ((row0 + r) * 2 * H + which * H + h) * IA_DP + part * 16) =
+        *reinterpret_cast<const int4*>(&qk_st[which][r * IA_DP + part * 16]);
   }
   const int tok0 = static_cast<int>(row0 % S);
   for (int c = tid; c < IA_D * 4; c += 256) {
     const int d = c >> 2, part = c & 3;
-    int8_t* dv = vt8 + ((static_cast<size_t>(seq) * H + h) * IA_D + d) * S + tok0 + part * 16;
-    *reinterpret_cast<int4*>(dv) = *reinterpret_cast<const int4*>(v_st + d * 64 + part * 16);
+    *reinterpret_cast<int4*>(vt8 + ((static_cast<size_t>(seq) * H + h) * IA_D + d) * S + tok0 + part * 16) =
+        *reinterpret_cast<const int4*>(v_st + d * 64 + part * 16);
   }
 }
 
@@ -254,6 +292,8 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
   uint64_t* p_full = s_full + 2 * IA_QT;       // [tile][buffer] P8 is in TMEM (and O rescaled if needed)
   uint64_t* o_full = p_full + 2 * IA_QT;       // [tile][buffer] the P V reading that buffer has retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2 * IA_QT);
+  // per-item scales of each softmax warpgroup, double-buffered by item parity: [tile][parity][64 key-block scales | 72 sv]
+  float* s_scales = reinterpret_cast<float*>(smem + IA_SMEM_SCALES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,7 +338,7 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      uint32_t kc = 0;
+      uint32_t kc = 0, vc = 0;
       int it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int qp = item % nqp;
@@ -312,16 +352,22 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
           tma_load_4d_hint(smem_q + t * IA_QTILE, &tmap_qa, q_full, 0, h, 0, row_q0 + t * IA_BM, kEvictFirst);
           tma_load_4d_hint(smem_q + t * IA_QTILE + IA_Q_A, &tmap_qb, q_full, 64, h, 0, row_q0 + t * IA_BM, kEvictFirst);
         }
-        for (int j = 0; j < nkv; ++j, ++kc) {
+        // K8 is streamed twice per item (pass A: row maxima, pass B: probabilities), V8^T once (pass B)
+        for (int i = 0; i < 2 * nkv; ++i, ++kc) {
+          const int j = i < nkv ? i : i - nkv;
           const int s = kc % IA_STAGES;
           const uint32_t ph = (kc / IA_STAGES) & 1;
           mbar_wait(&k_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[s], IA_KTILE);
           tma_load_4d_hint(smem_k + s * IA_KTILE, &tmap_ka, &k_full[s], 0, h, 1, row_kv0 + j * IA_BN, kEvictLast);
           tma_load_4d_hint(smem_k + s * IA_KTILE + IA_K_A, &tmap_kb, &k_full[s], 64, h, 1, row_kv0 + j * IA_BN, kEvictLast);
-          mbar_wait(&v_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[s], IA_VBYTES);
-          tma_load_3d_hint(smem_v + s * IA_VTILE, &tmap_vt, &v_full[s], j * IA_BN, 0, seq * a.H + h, kEvictLast);
+          if (i >= nkv) {
+            const int sv = vc % IA_STAGES;
+            mbar_wait(&v_empty[sv], ((vc / IA_STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(&v_full[sv], IA_VBYTES);
+            tma_load_3d_hint(smem_v + sv * IA_VTILE, &tmap_vt, &v_full[sv], j * IA_BN, 0, seq * a.H + h, kEvictLast);
+            ++vc;
+          }
         }
       }
     }
@@ -372,31 +418,35 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
         __syncwarp();
         ++kc;
       }
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t bph = (static_cast<uint32_t>(it) * (nkv >> 1) + (j >> 1)) & 1;
-        const int b = j & 1;
-        const bool more = j + 2 < nkv;
+      // 2 nkv score tiles per item: i < nkv are pass A (the softmax warps only take the row maximum: the buffer is handed
+      // back through p_full without a P V), i >= nkv are pass B (P8 written over the scores, O += P8 V8)
+      const int n2 = 2 * nkv;
+      for (int i = 0; i < n2; ++i) {
+        const uint32_t bph = (static_cast<uint32_t>(it) * nkv + (i >> 1)) & 1;   // phase of the per-buffer barriers
+        const int b = i & 1;
+        const bool pv = i >= nkv;
+        const bool more = i + 2 < n2;
         const int vs = vc % IA_STAGES;
         const int ks = kc % IA_STAGES;
-        mbar_wait(&v_full[vs], (vc / IA_STAGES) & 1);
+        if (pv) mbar_wait(&v_full[vs], (vc / IA_STAGES) & 1);
         if (more) mbar_wait(&k_full[ks], (kc / IA_STAGES) & 1);
 #pragma unroll
         for (int t = 0; t < IA_QT; ++t) {
           mbar_wait(&p_full[2 * t + b], bph);
           tc_fence_after();
           if (elect_one()) {
-            issue_pv(t, b, vs, j > 0 ? 1u : 0u);
+            if (pv) issue_pv(t, b, vs, i > nkv ? 1u : 0u);
             if (more) issue_s(t, b, ks);
           }
           __syncwarp();
         }
         if (elect_one()) {
-          tc_commit(&v_empty[vs]);
+          if (pv) tc_commit(&v_empty[vs]);
           if (more) tc_commit(&k_empty[ks]);
-          if (j + 3 == nkv) tc_commit(q_empty);   // the item's last score MMAs are in flight: Q8 may be refilled behind them
+          if (i + 3 == n2) tc_commit(q_empty);   // the item's last score MMAs are in flight: Q8 may be refilled behind them
         }
         __syncwarp();
-        ++vc;
+        if (pv) ++vc;
         if (more) ++kc;
       }
     }
@@ -410,72 +460,79 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
     const uint32_t s_addr = tmem_base + lane_off + t * 128;
     const uint32_t o_addr = tmem_base + lane_off + IA_O_COL + t * 128;
     uint8_t* ostage = smem_o + t * IA_OSTAGE;
-    float m_used = 0.f, l = 0.f;
+    // The scales an item needs — sq of this thread's row, the (sequence, head)'s key-block scales and V scales — are
+    // loaded one item ahead into registers and published through shared memory at the top of the item: a global load
+    // inside the key-tile loop put its whole latency into every iteration (ncu: long_scoreboard on the loop branch).
+    auto item_coords = [&](int item, int& qp, int& h, int& seq) {
+      qp = item % nqp;
+      h = (item / nqp) % a.H;
+      seq = item / (nqp * a.H);
+    };
+    auto prefetch = [&](int item, float& r_sq, float& r_a, float& r_b) {
+      int qp, h, seq;
+      item_coords(item, qp, h, seq);
+      const int grow = seq * a.S + qp * (IA_QT * IA_BM) + t * IA_BM + row;
+      r_sq = __ldg(a.sq + static_cast<size_t>(grow) * a.H + h);
+      // thread i < nkv of the warpgroup carries key-block scale i, thread d < 72 carries V scale d
+      r_a = wg_thread < nkv ? __ldg(a.sk + (static_cast<size_t>(seq) * nkv + wg_thread) * a.H + h) : 0.f;
+      r_b = wg_thread < IA_D ? __ldg(a.sv + (static_cast<size_t>(seq) * a.H + h) * IA_D + wg_thread) : 0.f;
+    };
+    float r_sq = 0.f, r_a = 0.f, r_b = 0.f;
+    if (static_cast<int>(blockIdx.x) < num_items) prefetch(blockIdx.x, r_sq, r_a, r_b);
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int qp = item % nqp;
-      const int h = (item / nqp) % a.H;
-      const int seq = item / (nqp * a.H);
-      const int grow = seq * a.S + qp * (IA_QT * IA_BM) + t * IA_BM + row;      // this thread's query row
-      const float c_row = __ldg(a.sq + static_cast<size_t>(grow) * a.H + h) * a.scale_log2e;
-      const float* skp = a.sk + (static_cast<size_t>(seq) * nkv) * a.H + h;      // key-block scales of this (sequence, head)
-      float sk_next = __ldg(skp);
-      for (int j = 0; j < nkv; ++j) {
-        const int b = j & 1;
+      int qp, h, seq;
+      item_coords(item, qp, h, seq);
+      float* sc = s_scales + (t * 2 + (it & 1)) * IA_SCALES;
+      if (wg_thread < nkv) sc[wg_thread] = r_a;
+      if (wg_thread < IA_D) sc[64 + wg_thread] = r_b;
+      const float c_row = r_sq * a.scale_log2e;
+      named_bar_sync(1 + t, 128);   // also orders this item's writes behind every thread's reads of two items ago
+      if (item + static_cast<int>(gridDim.x) < num_items) prefetch(item + gridDim.x, r_sq, r_a, r_b);
+      const float* skp = sc;
+      const uint32_t uses = static_cast<uint32_t>(it) * nkv;   // completions of every per-buffer barrier before this item
+      // ---- pass A: the exact row maximum (log2 units) over all key tiles — integer maximum per tile, one multiply
+      float m = -INFINITY;
+      for (int i = 0; i < nkv; ++i) {
+        const int b = i & 1;
         const uint32_t sa = s_addr + b * IA_BN;
-        const uint32_t pairs = static_cast<uint32_t>(it) * (nkv >> 1);
-        const float c_rt = c_row * sk_next;
-        if (j + 1 < nkv) sk_next = __ldg(skp + static_cast<size_t>(j + 1) * a.H);
-        mbar_wait(&s_full[2 * t + b], (pairs + (j >> 1)) & 1);
+        const float c_rt = c_row * skp[i];
+        mbar_wait(&s_full[2 * t + b], (uses + (i >> 1)) & 1);
         tc_fence_after();
         uint32_t v0[32], v1[32];
         tmem_ld_32x32b_x32(sa, v0);
         tmem_ld_32x32b_x32(sa + 32, v1);
         tmem_ld_wait();
-        // ---- row maximum of the 64 integer scores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * t + b]);   // the buffer may take the scores of tile i + 2
         int mi0 = INT_MIN, mi1 = INT_MIN, mi2 = INT_MIN, mi3 = INT_MIN;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mi0 = max(mi0, max(static_cast<int>(v0[i]), static_cast<int>(v0[i + 1])));
-          mi1 = max(mi1, max(static_cast<int>(v0[i + 2]), static_cast<int>(v0[i + 3])));
-          mi2 = max(mi2, max(static_cast<int>(v1[i]), static_cast<int>(v1[i + 1])));
-          mi3 = max(mi3, max(static_cast<int>(v1[i + 2]), static_cast<int>(v1[i + 3])));
+        for (int k = 0; k < 32; k += 4) {
+          mi0 = max(mi0, max(static_cast<int>(v0[k]), static_cast<int>(v0[k + 1])));
+          mi1 = max(mi1, max(static_cast<int>(v0[k + 2]), static_cast<int>(v0[k + 3])));
+          mi2 = max(mi2, max(static_cast<int>(v1[k]), static_cast<int>(v1[k + 1])));
+          mi3 = max(mi3, max(static_cast<int>(v1[k + 2]), static_cast<int>(v1[k + 3])));
         }
-        const float mx = static_cast<float>(max(max(mi0, mi1), max(mi2, mi3))) * c_rt;   // log2 units
-        if (j == 0) {
-          m_used = mx;
-          l = 0.f;
-        } else {
-          const bool need = (mx - m_used) > 1.0f;    // P8 = 127 * 2^(x - m) must stay <= 254
-          if (__any_sync(0xffffffffu, need)) {
-            const float m_new = fmaxf(m_used, mx);
-            const float f = ia_exp2(m_used - m_new);
-            m_used = m_new;
-            l *= f;
-            mbar_wait(&o_full[2 * t + (b ^ 1)], (pairs + ((j - 1) >> 1)) & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int piece = 0; piece < 3; ++piece) {
-              uint32_t w[32];
-              if (piece < 2) tmem_ld_32x32b_x32(o_addr + 32 * piece, w);
-              else tmem_ld_32x32b_x16(o_addr + 64, *reinterpret_cast<uint32_t(*)[16]>(w));
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (piece < 2 || i < 16)
-                  w[i] = static_cast<uint32_t>(__float2int_rn(__int2float_rn(static_cast<int>(w[i])) * f));
-              if (piece < 2) tmem_st_32x32b_x32(o_addr + 32 * piece, w);
-              else tmem_st_32x32b_x16(o_addr + 64, *reinterpret_cast<uint32_t(*)[16]>(w));
-            }
-            tmem_st_wait();
-          }
-        }
-        // ---- P8 = rint(2^(S c - m + log2 127)) as bytes over the first 16 columns of S; row sum of the un-rounded values
-        const float neg = IA_LOG2_127 - m_used;
-        const float2 neg2 = make_float2(neg, neg);
+        m = fmaxf(m, static_cast<float>(max(max(mi0, mi1), max(mi2, mi3))) * c_rt);
+      }
+      // ---- pass B: P8 = rint(255 * 2^(S c - m)) as bytes over the first 16 columns of S; row sum of the un-rounded values
+      const float neg = IA_LOG2_255 - m;
+      const float2 neg2 = make_float2(neg, neg);
+      const float2 nmagic = make_float2(-IA_MAGIC, -IA_MAGIC);
+      const float2 pmagic = make_float2(IA_MAGIC, IA_MAGIC);
+      float l = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        const uint32_t sa = s_addr + b * IA_BN;
+        const float c_rt = c_row * skp[j];
+        mbar_wait(&s_full[2 * t + b], (uses + ((nkv + j) >> 1)) & 1);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(sa, v0);
+        tmem_ld_32x32b_x32(sa + 32, v1);
+        tmem_ld_wait();
         const float2 c2 = make_float2(c_rt, c_rt);
-        const float2 nmagic = make_float2(-IA_MAGIC, -IA_MAGIC);
-        const float2 pmagic = make_float2(IA_MAGIC, IA_MAGIC);
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
         uint32_t pk[16];
 #pragma unroll
@@ -521,13 +578,13 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
         tmem_ld_32x32b_x8(o_addr + 64, w);
         tmem_ld_wait();
         const float inv = __fdividef(1.0f, l);
-        const float* svp = a.sv + (static_cast<size_t>(seq) * a.H + h) * IA_D;
+        const float* svp = sc + 64;
         uint32_t pk[36];
 #pragma unroll
         for (int i = 0; i < 36; ++i) {
           const int x0 = static_cast<int>(i < 16 ? v0[2 * i] : (i < 32 ? v1[2 * i - 32] : w[2 * i - 64]));
           const int x1 = static_cast<int>(i < 16 ? v0[2 * i + 1] : (i < 32 ? v1[2 * i - 31] : w[2 * i - 63]));
-          const float2 s2 = __ldg(reinterpret_cast<const float2*>(svp) + i);
+          const float2 s2 = *(reinterpret_cast<const float2*>(svp) + i);
           const __half2 hv = __floats2half2_rn(__int2float_rn(x0) * (s2.x * inv), __int2float_rn(x1) * (s2.y * inv));
           pk[i] = *reinterpret_cast<const uint32_t*>(&hv);
         }
@@ -584,7 +641,7 @@ static int ia_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, cons
 
 // workspace layout (all pieces 256-byte aligned)
 struct IaLayout {
-  size_t qk8, vt8, sq, sk, sv, kmean, total;
+  size_t qk8, vt8, sq, sk, sv, kmean, svi, total;
 };
 static IaLayout ia_layout(int n_seq, int S, int H) {
   const size_t rows = static_cast<size_t>(n_seq) * S, C = static_cast<size_t>(H) * IA_D;
@@ -596,13 +653,14 @@ static IaLayout ia_layout(int n_seq, int S, int H) {
   L.sk = up(L.sq + rows * H * 4);
   L.sv = up(L.sk + rows / IA_BN * H * 4);
   L.kmean = up(L.sv + static_cast<size_t>(n_seq) * C * 4);
-  L.total = up(L.kmean + static_cast<size_t>(n_seq) * C * 4);
+  L.svi = up(L.kmean + static_cast<size_t>(n_seq) * C * 4);
+  L.total = up(L.svi + static_cast<size_t>(n_seq) * C * 4);
   return L;
 }
 
 static int ia_check(const void* a, const void* b, int n_seq, int S, int H, int head_dim) {
   if (!a || !b || n_seq <= 0 || S <= 0 || H <= 0) return VQ_ERR_ARG;
-  if (head_dim != IA_D || (S % (IA_QT * IA_BM)) != 0 || S < 4 * IA_BN) return VQ_ERR_UNSUPPORTED;
+  if (head_dim != IA_D || (S % (IA_QT * IA_BM)) != 0 || S < 4 * IA_BN || S > 64 * IA_BN) return VQ_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a) & 255) || (reinterpret_cast<uintptr_t>(b) & 15)) return VQ_ERR_ARG;
   if (static_cast<uint64_t>(n_seq) * S * 3 * H * IA_D >= (1ull << 40)) return VQ_ERR_UNSUPPORTED;
   return VQ_OK;
@@ -614,11 +672,12 @@ static int ia_quantise(const void* qkv, void* ws, int n_seq, int S, int H, cudaS
   const int C = H * IA_D;
   float* kmean = reinterpret_cast<float*>(w + L.kmean);
   float* sv = reinterpret_cast<float*>(w + L.sv);
-  launch_pdl(ia_stats_kernel, dim3((C + 127) / 128, n_seq), dim3(128, 8), 0, st, static_cast<const __half*>(qkv), kmean,
-             sv, S, C);
+  float* svi = reinterpret_cast<float*>(w + L.svi);
+  launch_pdl(ia_stats_kernel, dim3((2 * C + 255) / 256, n_seq), dim3(32, 16), 0, st, static_cast<const __half*>(qkv), kmean,
+             sv, svi, S, C);
   if (cudaGetLastError() != cudaSuccess) return VQ_ERR_LAUNCH;
   launch_pdl(ia_quant_kernel, dim3(static_cast<unsigned>(static_cast<size_t>(n_seq) * S / 64), H), dim3(256), 0, st,
-             static_cast<const __half*>(qkv), static_cast<const float*>(kmean), static_cast<const float*>(sv),
+             static_cast<const __half*>(qkv), static_cast<const float*>(kmean), static_cast<const float*>(svi),
              reinterpret_cast<int8_t*>(w + L.qk8), reinterpret_cast<int8_t*>(w + L.vt8),
              reinterpret_cast<float*>(w + L.sq), reinterpret_cast<float*>(w + L.sk), S, H);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
@@ -697,7 +756,8 @@ static int ia_attend(const void* ws, void* out, int n_seq, int S, int H, float s
 }  // namespace vq
 
 extern "C" int64_t vq_attn_i8_workspace_bytes(int n_seq, int S, int H, int head_dim) {
-  if (n_seq <= 0 || S <= 0 || H <= 0 || head_dim != vq::IA_D || (S % (vq::IA_QT * vq::IA_BM)) != 0) return -1;
+  if (n_seq <= 0 || S <= 0 || H <= 0 || head_dim != vq::IA_D || (S % (vq::IA_QT * vq::IA_BM)) != 0 || S > 64 * vq::IA_BN)
+    return -1;
   return static_cast<int64_t>(vq::ia_layout(n_seq, S, H).total);
 }
 

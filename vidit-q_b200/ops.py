@@ -491,7 +491,8 @@ def attn_i8_workspace_layout(n_seq, S, H, head_dim=72):
     off["sk"] = up(off["sq"] + rows * H * 4)
     off["sv"] = up(off["sk"] + rows // 64 * H * 4)
     off["kmean"] = up(off["sv"] + n_seq * C * 4)
-    off["total"] = up(off["kmean"] + n_seq * C * 4)
+    off["svi"] = up(off["kmean"] + n_seq * C * 4)
+    off["total"] = up(off["svi"] + n_seq * C * 4)
     return off
 
 
