@@ -210,8 +210,8 @@ def measure_int8_peak(dev):
 KERNEL_CLASSES = [
     # (class, regex on the kernel name, bound)
     ("gemm", r"vq_gemm_w8a8_kernel|vq_linear_fused_kernel", "tensor"),
-    ("quant", r"vq_act_quant|vq_col_absmax", "hbm"),
-    ("attn_tc", r"vq_attn_spatial_kernel", "tensor"),
+    ("quant", r"vq_act_quant|vq_col_absmax|ia_stats_kernel|ia_quant_kernel", "hbm"),
+    ("attn_tc", r"vq_attn_spatial_kernel|vq_attn_i8_kernel", "tensor"),
     ("attn_small", r"vq_attn_temporal|vq_attn_cross_kernel", "hbm"),
     ("embed_sampler", r"vq_patch_embed_kernel|vq_cfg_ddim_kernel", "hbm"),
 ]
@@ -292,6 +292,11 @@ class WorkMeter:
             wrap(name, quant)
         wrap("col_absmax", lambda x, **k: me.add("quant", 1, 0, 2 * x.numel()))
         wrap("attn_spatial", lambda qkv, n_seq, S, H, D, scale, **k: me.add("attn_tc", 1, 4.0 * n_seq * H * S * S * D, 8 * n_seq * S * H * D))
+        # opt-in INT8 attention: the same 4 S^2 D operations per head (now integer), plus the two operand passes (statistics:
+        # read k|v; codes: read q|k|v, write the 80-byte Q8/K8 rows and V8^T)
+        wrap("attn_spatial_i8", lambda qkv, n_seq, S, H, D, scale, **k: (
+            me.add("attn_tc", 1, 4.0 * n_seq * H * S * S * D, n_seq * S * H * (2 * 80 + D) + 2 * n_seq * S * H * D),
+            me.add("quant", 2, 0, n_seq * S * H * D * (4 + 6) + n_seq * S * H * (2 * 80 + D))))
         wrap("attn_cross", lambda q, kv, ks, kl, B, N, H, D, max_len, scale, **k: me.add(
             "attn_tc" if N % 256 == 0 else "attn_small", 1, 4.0 * N * kv.shape[0] * H * D, 4 * B * N * H * D + 2 * kv.numel()))
         wrap("attn_temporal", lambda qkv, B, T, S, H, D, scale, **k: me.add("attn_small", 1, 4.0 * B * S * H * T * T * D, 8 * B * T * S * H * D))
@@ -522,6 +527,9 @@ def main():
     ap.add_argument("--cfg-mode", default="stacked", choices=["stacked", "split", "split2"],
                     help="cfg_split's cond / uncond forwards as one stacked launch sequence (default), as two calls, or as two "
                          "calls on two CUDA streams (split2: one branch's tail waves and HBM-bound passes may overlap the other's)")
+    ap.add_argument("--attn-int8", action="store_true",
+                    help="OPT-IN: spatial attention on INT8 Q/K/V (vq_attn_spatial_i8).  Leaves the reference's numerics (its "
+                         "attention is fp16): the line is then NOT the headline metric and says so in config")
     ap.add_argument("--parallelism", default="samples", choices=["samples", "cfg-branch", "frames"],
                     help="samples: one sample per rank, no data-path collective (the metric, weak scaling). cfg-branch: "
                          "two ranks per sample, one CFG branch each, model outputs exchanged every step (latency / "
@@ -530,6 +538,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.attn_int8:
+        os.environ["VQ_ATTN_INT8"] = "1"      # read by stdit.FusedBlocks when the schedule is built
 
     import torch
     import torch.distributed as dist
@@ -862,6 +872,8 @@ def main():
                                                              "%d graph segments around %d NCCL calls" % seg_graph.counts()),
                        "depth": args.depth,
                        "cfg_mode": args.cfg_mode,
+                       "spatial_attention": ("INT8 Q/K/V (opt-in vq_attn_spatial_i8: NOT the reference's numerics, own tolerance)"
+                                             if args.attn_int8 else "fp16 (the reference's arithmetic)"),
                        "l2": ("256 MB buffer written between timed iterations (working set fits the 126 MB L2)" if flush is not None
                               else "working set per step (0.74 GB weight codes + >1 GB activations) exceeds the 126 MB L2"),
                        "linear_TOP_per_step": total_linear_top},

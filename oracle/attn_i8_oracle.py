@@ -14,7 +14,9 @@ Scheme (per sequence of S tokens, per head, head_dim 72):
   V8 = rint(V / sv), sv = max|V[:, head, dim]| / 127 over the sequence        per channel
   S  = (Q8 K8^T) * sq * sk * scale      integer dot products, exact
   P8 = rint(255 * exp(S - m)) as u8, m = the exact row maximum (the kernel takes it in a first pass over the key tiles)
-  O  = (sum_k P8 V8) * sv / sum_k (255 * exp(S - m))                          integer accumulation, exact
+  O  = (sum_k P8 V8) * sv / sum_k (255 * exp(S - m))                          integer accumulation, exact; the normaliser is
+                                                                              the un-rounded sum (the rounded bytes' sum would
+                                                                              drop the small probabilities from it: 1.6x the error)
 """
 import torch
 
@@ -54,7 +56,7 @@ def attention_i8(qkv, n_seq, S, H, scale, D=72):
     e = 255.0 * torch.exp(s - m)
     p8 = torch.round(e)
     o_int = p8 @ v8
-    o = o_int * z["sv"][:, :, None, :].double() / e.sum(dim=-1, keepdim=True)
+    o = o_int * z["sv"][:, :, None, :].double() / e.sum(dim=-1, keepdim=True)      # normaliser: the UN-rounded sum
     return o.permute(0, 2, 1, 3).reshape(n_seq * S, H * D).float()
 
 
@@ -68,7 +70,7 @@ def attention_fp(qkv, n_seq, S, H, scale, D=72):
 def attention_i8_tiled(z, scale):
     """The kernel's own order of operations on the codes / scales `z` (quantise_qkv's dict), fp32 where the kernel
     computes in fp32: pass A takes the row maximum tile by tile (integer maximum x the tile's fp32 scale), pass B forms
-    x = fma(S, c, log2(255) - m), P8 = rint(2^x), the fp32 row sum of the un-rounded 2^x and the exact integer P8 V8."""
+    x = fma(S, c, log2(255) - m), P8 = rint(2^x), the exact integer P8 V8 and the fp32 row sum of the un-rounded 2^x."""
     q8, k8, v8 = (z[n].permute(0, 2, 1, 3).contiguous().double() for n in ("q8", "k8", "v8"))     # [n_seq, H, S, D]
     n_seq, H, S, D = q8.shape
     f32 = torch.float32
@@ -84,6 +86,6 @@ def attention_i8_tiled(z, scale):
     x = (s_int * c_rt.repeat_interleave(BLOCK_K, dim=-1).double() + neg.double()).to(f32)  # one rounding, as the FMA
     e = torch.exp2(x.double()).to(f32)
     p8 = torch.round(e.double())                                                          # half to even, as the magic add
-    l = e.double().sum(dim=-1)
-    out = (p8 @ v8) * z["sv"][:, :, None, :].double() / l[..., None]
+    l = e.double().sum(dim=-1, keepdim=True)
+    out = (p8 @ v8) * z["sv"][:, :, None, :].double() / l
     return out.permute(0, 2, 1, 3).reshape(n_seq * S, H * D).float()
