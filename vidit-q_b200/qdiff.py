@@ -236,14 +236,21 @@ class QuantLayer(nn.Module):
         ema = old * m + cur_act_scale * (1 - m)
         aq.act_scale[tr_id] = torch.where(old.abs().mean() == 0, cur_act_scale, ema)
 
+    @staticmethod
+    def _col_absmax(input, gelu=False):
+        """`input.abs().max(dim=-2)[0]` of quant_layer.py:116,119,147 for any rank (2-D timestep embeddings, 3-D token
+        tensors, 4-D caption tensors): the per-channel maxima over the second-to-last dimension, from vq_col_absmax."""
+        lead, n, K = input.shape[:-2], input.shape[-2], input.shape[-1]
+        x3 = input.reshape(-1, n, K)
+        return ops.col_absmax(x3 if x3.is_contiguous() else x3.contiguous(), gelu=gelu).reshape(*lead, K)
+
     def live_channel_scale(self, input, gelu=False):
         """Channel scale of the two input-dependent smooth-quant modes, [K] fp16.  The per-channel |x| maxima come from
         vq_col_absmax (one pass, exact); the [G, K] -> [K] arithmetic behind it is the reference's, op for op, on tiny
         tensors.  gelu=True: `input` is the pre-activation and the statistics are those of gelu_tanh(input)."""
         tr = self._timerange_id()
         alpha = self._alpha(tr)
-        x3 = input if input.dim() == 3 else input.reshape(1, -1, input.shape[-1])
-        colmax = ops.col_absmax(x3, gelu=gelu)                          # input.abs().max(dim=-2)[0]  -> [G, K]
+        colmax = self._col_absmax(input, gelu=gelu)                     # input.abs().max(dim=-2)[0]  -> [G, K]
         if self.smooth_mode() == "dynamic":
             s = colmax.pow(alpha).mean(dim=0, keepdim=True) / self._weight_colmax_pow(alpha)
         else:
@@ -359,8 +366,7 @@ class QuantLayer(nn.Module):
         if (not self.smooth_quant and getattr(self, "smooth_quant_running_stat", False)
                 and "momentum" in getattr(self, "channel_wise_scale_type", "")):
             # quant_layer.py:141-153: statistics collection without scaling (calibration-time; kept for API parity)
-            x3 = input if input.dim() == 3 else input.reshape(1, -1, input.shape[-1])
-            self._update_running_act_scale(ops.col_absmax(x3).mean(dim=0, keepdim=True), self._timerange_id())
+            self._update_running_act_scale(self._col_absmax(input).mean(dim=0, keepdim=True), self._timerange_id())
         if self.weight_quant and act_q:
             if _is_dynamic(self.act_quantizer):
                 # the whole QuantLayer forward as ONE call (vq_linear_w8a8): a single fused kernel where the shape allows
@@ -624,21 +630,34 @@ class QuantModel(nn.Module):
                 self.load_bitwidth_config(model=module, bit_config=bit_config, bit_type=bit_type, prefix=full + ".")
 
     @torch.no_grad()
-    def init_weight_quant_params(self):
+    def init_weight_quant_params(self, only_enabled=False, dtype=torch.float32):
         """Min-max per-output-channel weight parameters for every bit-width in `mixed_precision` — what the reference's
         PTQ weight pass (ptq.py:266-294 -> base_quantizer.py:166-228, 'channel' branch) stores into ckpt.pth.  Load-time
-        torch ops on the weight's device; provided so synthetic-weight models can be benchmarked without a PTQ run."""
+        torch ops on the weight's device; used by viditq_b200.ptq and so that synthetic-weight models can be benchmarked
+        without a PTQ run.
+        only_enabled: skip layers whose weight quantisation is off (the reference's calibration forward never initialises
+        the remain_fp layers' quantisers: their buffers stay None in ckpt.pth).
+        dtype: the arithmetic type.  The reference computes in the MODEL's dtype, op for op (x.min / x.max,
+        (max - min) / (2^b - 1), round(-min / delta)) — fp16 when ptq.py runs with `dtype = "fp16"` (its 16x512x512
+        config), fp32 otherwise; dtype=None reproduces that (the weight's own dtype).  The fp32 default is the
+        higher-precision variant used for synthetic-weight benchmarks (pinned against an fp32 reference run)."""
         for _, m in self.quant_layers():
+            if only_enabled and not m.weight_quant:
+                continue
             wq = m.weight_quantizer
-            w = m.weight.data.float()
+            wdt = m.weight.dtype if dtype is None else dtype
+            w = m.weight.data.to(wdt)
             bits = wq.mixed_precision if wq.mixed_precision is not None else [wq.n_bits]
             n_t = len(m.timerange) if m.smooth_quant else 1
-            dl = torch.empty(len(bits), n_t, w.shape[0], 1, device=w.device)
+            dl = torch.empty(len(bits), n_t, w.shape[0], 1, device=w.device, dtype=wdt)
             zl = torch.empty_like(dl)
             for t in range(n_t):
-                wt = w * m.channel_wise_scale(t).float()[None, :] if m.smooth_quant else w
-                mn = wt.min(dim=-1)[0].clamp(max=0.0)
-                mx = wt.max(dim=-1)[0].clamp(min=0.0)
+                # quant_layer.py:178: weight_quantizer(self.weight * channel_wise_scale)
+                wt = w * m.channel_wise_scale(t).to(wdt)[None, :] if m.smooth_quant else w
+                mn = wt.min(dim=-1)[0]
+                mn = torch.where(mn > 0, torch.zeros_like(mn), mn)
+                mx = wt.max(dim=-1)[0]
+                mx = torch.where(mx < 0, torch.zeros_like(mx), mx)
                 for i, b in enumerate(bits):
                     delta = (mx - mn) / (2 ** b - 1)
                     if delta.min() < 1e-6:
