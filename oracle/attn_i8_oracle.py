@@ -33,14 +33,17 @@ def quantise_qkv(qkv, n_seq, S, H, D=72, kmean=None):
     ks = k - kmean
     sq = q.abs().amax(dim=-1) / 127.0                                   # [n_seq, S, H]
     sq = torch.where(sq > 0, sq, torch.ones_like(sq))
-    q8 = torch.clamp(torch.round(q * (1.0 / sq)[..., None]), -127, 127)        # one reciprocal per scale, fp32 products
+    # code = rint(v * inv), inv = fp32(1 / s): the EXACT product (fp64 holds 24 x 24 bits) rounded once, half to even — what
+    # the kernel's fused multiply-add with the 1.5 * 2^23 constant does; |v| <= the scale's maximum, so no clamp is needed
+    code = lambda v, s: torch.round(v.double() * (1.0 / s).double()).float()
+    q8 = code(q, sq[..., None])
     kb = ks.reshape(n_seq, S // BLOCK_K, BLOCK_K, H, D)
     sk = kb.abs().amax(dim=(2, 4)) / 127.0                              # [n_seq, S / 64, H]
     sk = torch.where(sk > 0, sk, torch.ones_like(sk))
-    k8 = torch.clamp(torch.round(kb * (1.0 / sk)[:, :, None, :, None]), -127, 127).reshape(n_seq, S, H, D)
+    k8 = code(kb, sk[:, :, None, :, None]).reshape(n_seq, S, H, D)
     sv = v.abs().amax(dim=1) / 127.0                                    # [n_seq, H, D]
     sv = torch.where(sv > 0, sv, torch.ones_like(sv))
-    v8 = torch.clamp(torch.round(v * (1.0 / sv)[:, None]), -127, 127)
+    v8 = code(v, sv[:, None])
     return dict(q8=q8, k8=k8, v8=v8, sq=sq, sk=sk, sv=sv, kmean=kmean[:, 0])
 
 

@@ -155,14 +155,20 @@ __global__ void __launch_bounds__(512) ia_stats_kernel(const __half* __restrict_
   }
 }
 
-// code = rint(v * (1 / s)) clamped to +-127: one IEEE reciprocal per scale, then exact fp32 products — the oracle
-// (oracle/attn_i8_oracle.py quantise_qkv) evaluates the same two roundings
-__device__ __forceinline__ int ia_code(float v, float inv) {
-  return static_cast<int>(fminf(fmaxf(rintf(v * inv), -127.0f), 127.0f));
+// code = rint(v * (1 / s)): one IEEE reciprocal per scale, then ONE fused multiply-add per pair with the 1.5 * 2^23 magic
+// constant — the exact product is rounded to the nearest integer (half to even) in a single step and the code is the low
+// byte of the result's bit pattern (two's complement).  No clamp: |v| <= the maximum the scale was taken from, so
+// |v / s| <= 127 (1 + 2^-22) and rounds to at most 127.  The oracle (oracle/attn_i8_oracle.py quantise_qkv) forms the same
+// exact product in fp64 and rounds it once.
+__device__ __forceinline__ uint32_t ia_code4(const float (&x)[20], int i, float2 inv2) {
+  const float2 magic = make_float2(IA_MAGIC, IA_MAGIC);
+  const float2 a = __ffma2_rn(make_float2(x[i], x[i + 1]), inv2, magic);
+  const float2 b = __ffma2_rn(make_float2(x[i + 2], x[i + 3]), inv2, magic);
+  return __byte_perm(__byte_perm(__float_as_uint(a.x), __float_as_uint(a.y), 0x0040),
+                     __byte_perm(__float_as_uint(b.x), __float_as_uint(b.y), 0x0040), 0x5410);
 }
-__device__ __forceinline__ uint32_t ia_pack4(int a, int b, int c, int d) {
-  return (static_cast<uint32_t>(a) & 0xffu) | ((static_cast<uint32_t>(b) & 0xffu) << 8) |
-         ((static_cast<uint32_t>(c) & 0xffu) << 16) | (static_cast<uint32_t>(d) << 24);
+__device__ __forceinline__ int8_t ia_code1(float v, float inv) {
+  return static_cast<int8_t>(__float_as_uint(fmaf(v, inv, IA_MAGIC)) & 0xffu);
 }
 // 20 fp16 values of one (token, quarter row) from the staged tile (8-byte aligned), dims past `nd` read as zero
 __device__ __forceinline__ void ia_load20(const __half* tile, int token, int d0, int nd, float (&x)[20]) {
@@ -219,9 +225,7 @@ __global__ void __launch_bounds__(256, 3) ia_quant_kernel(const __half* __restri
     if (sub == 0) sq[row * H + h] = s_q;
     uint32_t* dq = reinterpret_cast<uint32_t*>(&qk_st[0][token * IA_DP + d0]);
 #pragma unroll
-    for (int w = 0; w < 5; ++w)
-      dq[w] = ia_pack4(ia_code(x[4 * w], inv), ia_code(x[4 * w + 1], inv), ia_code(x[4 * w + 2], inv),
-                       ia_code(x[4 * w + 3], inv));
+    for (int w = 0; w < 5; ++w) dq[w] = ia_code4(x, 4 * w, make_float2(inv, inv));
   }
   // ---- K: minus the sequence mean, per (64-token block, head) scale
   ia_load20(in_st[1], token, d0, nd, x);
@@ -246,16 +250,14 @@ __global__ void __launch_bounds__(256, 3) ia_quant_kernel(const __half* __restri
     if (tid == 0) sk[static_cast<size_t>(blockIdx.y) * H + h] = s_k;
     uint32_t* dk = reinterpret_cast<uint32_t*>(&qk_st[1][token * IA_DP + d0]);
 #pragma unroll
-    for (int w = 0; w < 5; ++w)
-      dk[w] = ia_pack4(ia_code(x[4 * w], inv), ia_code(x[4 * w + 1], inv), ia_code(x[4 * w + 2], inv),
-                       ia_code(x[4 * w + 3], inv));
+    for (int w = 0; w < 5; ++w) dk[w] = ia_code4(x, 4 * w, make_float2(inv, inv));
   }
   // ---- V: per (sequence, channel) scale, transposed
   ia_load20(in_st[2], token, d0, nd, x);
   const float* svp = svi + static_cast<size_t>(seq) * C + h * IA_D + d0;
 #pragma unroll
   for (int i = 0; i < 20; ++i)
-    if (i < nd) v_st[(d0 + i) * 64 + token] = static_cast<int8_t>(ia_code(x[i], __ldg(svp + i)));
+    if (i < nd) v_st[(d0 + i) * 64 + token] = ia_code1(x[i], __ldg(svp + i));
   __syncthreads();
   for (int c = tid; c < 2 * 64 * 5; c += 256) {
     const int which = c / (64 * 5), r = (c % (64 * 5)) / 5, part = c % 5;
