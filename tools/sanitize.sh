@@ -27,3 +27,6 @@ run $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kerne
 run $CS --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_linear.py -q -x -k "109 or 2-1024-1152"
 race gemm tools/gemm_selftest --case 256 384 1152 2
 race linear python -m pytest tests/test_gpu_linear.py -q -x -k "1-109-2304 or 1-300-1152-2"
+# opt-in INT8 attention (vq_attn_i8.cu): operand passes + the two-pass tcgen05 kind::i8 kernel, small shapes
+run $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_attn_i8.py -q -x -m gpu -k "256-1 or 512-2 or refuses"
+run $CS --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_attn_i8.py -q -x -m gpu -k "256-1"

@@ -294,8 +294,8 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
   uint64_t* v_empty = v_full + IA_STAGES;
   uint64_t* s_full = v_empty + IA_STAGES;      // [tile][buffer] scores are in TMEM
   uint64_t* p_full = s_full + 2 * IA_QT;       // [tile][buffer] P8 is in TMEM (and O rescaled if needed)
-  uint64_t* o_full = p_full + 2 * IA_QT;       // [tile][buffer] the P V reading that buffer has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2 * IA_QT);
+  uint64_t* o_full = p_full + 2 * IA_QT;       // [tile] the item's last P V has retired: O is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + IA_QT);
   // per-item scales of each softmax warpgroup, double-buffered by item parity: [tile][parity][64 key-block scales | 72 sv]
   float* s_scales = reinterpret_cast<float*>(smem + IA_SMEM_SCALES);
 
@@ -325,8 +325,8 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
     for (int i = 0; i < 2 * IA_QT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);   // one arrival per softmax warp of the tile
-      mbar_init(&o_full[i], 1);
     }
+    for (int i = 0; i < IA_QT; ++i) mbar_init(&o_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -398,13 +398,13 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
       tc_commit(&s_full[2 * t + b]);
     };
     // O[t] (+)= P8[t][b] V8: K = 64 keys = two 32-byte steps of the [80 dims x 64 keys] tile
-    auto issue_pv = [&](int t, int b, int vs, uint32_t acc) {
+    auto issue_pv = [&](int t, int b, int vs, uint32_t acc, bool last) {
       const uint32_t va = v_lo + vs * (IA_VTILE >> 4);
       const uint32_t p = tmem_base + t * 128 + b * IA_BN;
       const uint32_t o = tmem_base + IA_O_COL + t * 128;
       tc_mma_i8_ts(o, p, hi_sw64 | va, idesc_pv, acc);
       tc_mma_i8_ts(o, p + 8, hi_sw64 | (va + 2), idesc_pv, 1u);
-      tc_commit(&o_full[2 * t + b]);
+      if (last) tc_commit(&o_full[t]);   // one completion per item: the epilogue is its only waiter
     };
     uint32_t kc = 0, vc = 0;
     int it = 0;
@@ -439,7 +439,7 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
           mbar_wait(&p_full[2 * t + b], bph);
           tc_fence_after();
           if (elect_one()) {
-            if (pv) issue_pv(t, b, vs, i > nkv ? 1u : 0u);
+            if (pv) issue_pv(t, b, vs, i > nkv ? 1u : 0u, i + 1 == n2);
             if (more) issue_s(t, b, ks);
           }
           __syncwarp();
@@ -576,7 +576,7 @@ vq_attn_i8_kernel(const __grid_constant__ CUtensorMap tmap_qa, const __grid_cons
       }
       // ---- epilogue: O * sv / l -> fp16 -> dense staging tile -> one TMA store of [128 queries x 72 dims]
       {
-        mbar_wait(&o_full[2 * t + 1], (static_cast<uint32_t>(it) * (nkv >> 1) + (nkv >> 1) - 1) & 1);
+        mbar_wait(&o_full[t], it & 1);
         tc_fence_after();
         uint32_t v0[32], v1[32], w[8];
         tmem_ld_32x32b_x32(o_addr, v0);
