@@ -129,6 +129,41 @@ def main():
                 assert val.dtype == torch.float16
                 rec[f"ckpt16/{name}/{bname}"] = val.detach().numpy()
                 n16 += 1
+    # ---- static activation quantisers (w8a8_naive.yaml: `per_group: False, dynamic: False`), model in fp16 as ptq.py runs
+    # it: weight pass, then ptq.py:311-327 — the calibration set walked in order with weights AND activations quantised,
+    # every ActQuantizer re-initialising itself from each tensor it sees.  Two variants: last batch wins (running_stat
+    # False, the shipped config) and the min / max EMA (running_stat True).
+    for tag, running in (("static", False), ("static_ema", True)):
+        refs = RefSTDiT(enable_flashattn=False, **CFG)
+        refs.load_state_dict(mine.state_dict(), strict=True)
+        refs.eval()
+        wq_s, aq_s = ref_shims.w8a8_dynamic_configs(n_temporal=T, n_spatial=S, n_prompt=120)
+        aq_s["dynamic"] = False
+        aq_s["per_group"] = False
+        aq_s["running_stat"] = running
+        qs = RefQuantModel(refs, wq_s, aq_s)
+        qs.set_module_name_for_quantizer(module=qs.model)
+        qs.half()
+        refs.dtype = torch.float16
+        qs.set_quant_state(True, False)
+        qs.set_layer_quant(model=qs, module_name_list=FP_LAYERS, quant_level="per_layer", weight_quant=False,
+                           act_quant=False, prefix="")
+        _ = qs(calib_xs[:calib_batch_size], calib_ts[:calib_batch_size], calib_cs[:calib_batch_size].half(), **tmp_kwargs)
+        qs.set_quant_init_done("weight")
+        qs.set_quant_state(True, True)
+        qs.set_layer_quant(model=qs, module_name_list=FP_LAYERS, quant_level="per_layer", weight_quant=False,
+                           act_quant=False, prefix="")
+        for i in range(int(calib_xs.size(0) / calib_batch_size)):
+            sel = slice(i * calib_batch_size, (i + 1) * calib_batch_size)
+            _ = qs(calib_xs[sel], calib_ts[sel], calib_cs[sel].half(), mask=calib_masks[sel][::2])
+        qs.set_quant_init_done("activation")
+        n_s = 0
+        for name, (bufs, params) in qs.get_quant_params_dict().items():
+            for bname, val in bufs.items():
+                if val is not None:
+                    rec[f"{tag}/{name}/{bname}"] = val.detach().float().numpy()
+                    n_s += 1
+        print(f"{tag}: {n_s} buffers")
     np.savez_compressed(OUT, **rec)
     print(f"fp16 weight pass: {n16} buffers")
     print(f"wrote {OUT} ({os.path.getsize(OUT) / 1e6:.2f} MB): {len(ckpt)} quantisers, {n_buf} buffers")

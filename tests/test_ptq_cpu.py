@@ -131,7 +131,54 @@ def test_weight_parameters_bit_exact_given_the_reference_statistics(gold, dtype)
     assert n == 2 * 26
 
 
-def test_static_activation_calibration_is_refused_not_faked(monkeypatch):
+@pytest.mark.parametrize("tag,running", [("static", False), ("static_ema", True)])
+def test_static_activation_calibration_against_the_reference_flow(gold, monkeypatch, tag, running):
+    """w8a8_naive.yaml's static per-tensor activation quantisers, model in fp16 (how ptq.py runs): the reference walks the
+    calibration set with its SIMULATED quantisation, this producer with the integer form (here the oracle's, on CPU) — the
+    two agree to <= 1e-3 per layer, so the calibrated ranges agree to that order; zero points to one step."""
+    import cpu_ops
+    from viditq_b200 import ptq
+    from viditq_b200.qdiff import QuantModel
+    from viditq_b200.stdit import STDiT
+    cpu_ops.patch_ops(monkeypatch)
+    model = STDiT(input_size=(4, 16, 16), depth=2)
+    model.init_synthetic(seed=0)
+    model.eval()
+    sq = Cfg(enable=False, channel_wise_scale_type="momentum_act_max", momentum=0.95, alpha=0.625)
+    wq = Cfg(n_bits=8, per_group="channel", channel_dim=0, scale_method="min_max", round_mode="nearest")
+    aq = Cfg(n_bits=8, per_group=False, scale_method="min_max", round_mode="nearest_ste", running_stat=running,
+             dynamic=False, sym=False, n_spatial_token=model.num_spatial, n_temporal_token=model.num_temporal, n_prompt=120,
+             smooth_quant=sq)
+    qnn = QuantModel(model, wq, aq)
+    qnn.half()
+    model.dtype = torch.float16
+    xs, ts, cs, masks = _calib()
+    ckpt = ptq.run_ptq(qnn, (xs, ts, cs.half(), masks), n_samples=2, batch_size=1, fp_layer_list=FP_LAYERS)
+    mine = _bufs(ckpt)
+    ref = {k[len(tag) + 1:]: v for k, v in gold.items() if k.startswith(tag + "/")}
+    assert sorted(mine.keys()) == sorted(ref.keys())
+    worst_w = worst_a = 0.0
+    zp_off = n_act = 0
+    for k, r in ref.items():
+        m = mine[k].detach().float().numpy()
+        assert m.shape == r.shape, (k, m.shape, r.shape)
+        kind = k.rsplit("/", 1)[1]
+        if "weight_quantizer" in k:
+            assert np.array_equal(m, r), k                      # weight parameters: bit-exact (fp16 arithmetic)
+        elif kind in ("delta", "delta_list"):
+            worst_a = max(worst_a, float(np.abs(m - r).max() / np.abs(r).max()))
+        else:
+            zp_off = max(zp_off, float(np.abs(m - r).max()))
+            n_act += 1
+    print("%s: activation delta worst relative deviation %.2e, zero point worst |diff| %.0f over %d quantisers"
+          % (tag, worst_a, zp_off, n_act // 2))
+    # last-batch-wins: the range of one tensor that both flows compute to <= 1e-3.  EMA: an fp16 accumulator updated on
+    # every calibration forward — a few fp16 ulps (4.9e-4 each) on top of that
+    assert worst_a <= (1e-2 if running else 2e-3) and zp_off <= 1
+    assert all(l.act_quantizer.init_done and not l.calibrating for _, l in qnn.quant_layers())
+
+
+def test_timestep_wise_static_calibration_is_refused_not_faked(monkeypatch):
     import cpu_ops
     from viditq_b200 import ptq
     from viditq_b200.qdiff import QuantModel
@@ -144,5 +191,6 @@ def test_static_activation_calibration_is_refused_not_faked(monkeypatch):
     aq = Cfg(n_bits=8, per_group=False, scale_method="min_max", round_mode="nearest_ste", running_stat=True,
              dynamic=False, sym=False, n_spatial_token=64, n_temporal_token=4, n_prompt=120, smooth_quant=sq)
     qnn = QuantModel(model, wq, aq)
-    with pytest.raises(NotImplementedError, match="static activation calibration"):
+    qnn.timestep_wise = True
+    with pytest.raises(NotImplementedError, match="timestep-wise"):
         ptq.run_ptq(qnn, _calib(), n_samples=2, batch_size=1, fp_layer_list=FP_LAYERS)

@@ -1,7 +1,7 @@
 """PTQ producer: what the reference's t2v/scripts/ptq.py:213-362 does between "calibration data
-loaded" and "ckpt.pth saved", for the configurations whose activations are quantised DYNAMICALLY (w8a8_dynamic.yaml, the
-headline; the smooth-quant / timestep-aware variants w4a8_timestep_aware_cb.yaml, w8a8_smooth_quant.yaml with
-`dynamic: True`).  The result is the reference's checkpoint format: `QuantModel.get_quant_params_dict()` — loadable by the
+loaded" and "ckpt.pth saved": the dynamic-activation configurations (w8a8_dynamic.yaml, the headline; the smooth-quant /
+timestep-aware variants w4a8_timestep_aware_cb.yaml, w8a8_smooth_quant.yaml with `dynamic: True`) and the static ones
+(w8a8_naive.yaml).  The result is the reference's checkpoint format: `QuantModel.get_quant_params_dict()` — loadable by the
 reference's own `load_quant_params` (qdiff/utils.py:66) and by `viditq_b200.qdiff.load_quant_params`.
 
 Steps, in the reference's order:
@@ -15,9 +15,11 @@ Steps, in the reference's order:
      bit-exact against the reference's ckpt on 364 layers, tests/test_gpu_deep.py, and under smooth-quant,
      tests/test_ptq_cpu.py).
   3. activation parameters (ptq.py:296-362): dynamic quantisers have none ("Adopting dynamic quant params, skip
-     calculating fixed quant params", ptq.py:308-309).  STATIC calibration (running min/max over the calibration set,
-     base_quantizer.py:146-228 with momentum) is not restated here: it raises, and such checkpoints are produced by the
-     reference's script (this library loads and runs them: vq_act_quant_static).
+     calculating fixed quant params", ptq.py:308-309).  STATIC quantisers (w8a8_naive.yaml: per tensor; or per token) are
+     calibrated by walking the calibration set with weights AND activations quantised (ptq.py:311-327): every call
+     re-derives (delta, zero_point) from the live tensor (base_quantizer.py:146-228; min / max EMA with `running_stat`)
+     and the forward continues on the quantised activations — here through the integer kernels.  Timestep-wise static
+     parameters (ptq.py:328-356) raise.
 Not part of the denoising hot path: plain torch on the model's device plus one own kernel; nothing here is timed by
 bench.py.
 """
@@ -65,6 +67,30 @@ def collect_smooth_quant_statistics(qnn, calib, n_samples, batch_size, fp_layer_
 
 
 @torch.no_grad()
+def calibrate_static_activations(qnn, layers, calib, batch_size, device=None):
+    """ptq.py:311-327 (`timestep_wise: False`): with the weights quantised on their final grid, the calibration set is walked
+    in order in mini-batches of 2 * batch_size; every static ActQuantizer re-derives its parameters from each tensor it sees
+    (QuantLayer.calibrate_static_act: last batch wins, or the min / max EMA with `running_stat`) and the forward continues
+    on the activations quantised with them — here through the integer kernels (vq_act_quant_static + vq_gemm_w8a8), which
+    equal the reference's simulated quantisation to <= 1e-3 per layer."""
+    if getattr(qnn, "timestep_wise", False):
+        raise NotImplementedError("timestep-wise static activation parameters (ptq.py:328-356) are not restated")
+    xs, ts, cs, masks = calib
+    calib_batch_size = batch_size * 2
+    to = (lambda v: v.to(device)) if device is not None else (lambda v: v)
+    for layer in layers:
+        layer.calibrating = True
+        layer.act_quantizer.init_done = False
+    try:
+        for i in range(int(xs.size(0) / calib_batch_size)):
+            sel = slice(i * calib_batch_size, (i + 1) * calib_batch_size)
+            qnn(to(xs[sel]), to(ts[sel]), to(cs[sel]), mask=to(masks[sel][::2]))
+    finally:
+        for layer in layers:
+            layer.calibrating = False
+
+
+@torch.no_grad()
 def run_ptq(qnn, calib, n_samples, batch_size, fp_layer_list=(), device=None):
     """The training-free PTQ of ptq.py:213-362 on `qnn` (a viditq_b200.qdiff.QuantModel); returns the checkpoint dict
     (`torch.save` it as ckpt.pth).  Leaves the model in the inference state of quant_txt2video.py:195-207: weights and
@@ -83,12 +109,9 @@ def run_ptq(qnn, calib, n_samples, batch_size, fp_layer_list=(), device=None):
     qnn.set_quant_state(True, True)
     qnn.set_layer_quant(model=qnn, module_name_list=fp_layer_list, quant_level="per_layer", weight_quant=False,
                         act_quant=False, prefix="")
-    for name, layer in qnn.quant_layers():
-        if layer.act_quant and not _is_dynamic(layer.act_quantizer):
-            raise NotImplementedError(
-                f"{name}: static activation calibration (ptq.py:311-356, running min/max over the calibration set) is not "
-                "restated in viditq_b200.ptq; produce such checkpoints with the reference's t2v/scripts/ptq.py — this "
-                "library loads and runs them (vq_act_quant_static)")
+    static = [layer for _, layer in qnn.quant_layers() if layer.act_quant and not _is_dynamic(layer.act_quantizer)]
+    if static:
+        calibrate_static_activations(qnn, static, calib, batch_size, device)
     qnn.set_quant_init_done("activation")
     return qnn.get_quant_params_dict()
 

@@ -11,8 +11,8 @@ PTQ-calibrated `ckpt.pth` files work unchanged:
 What differs is what `forward` executes: when both weight and activation quantisation are enabled the layer runs
   vq_act_quant (per-token dynamic u8 codes) -> vq_gemm_w8a8 (tcgen05 INT8 GEMM + dequant epilogue)
 on prepared u8 weight codes, instead of fake-quantising in fp16 and calling F.linear.  Layers left in floating point
-(`remain_fp.txt`) run F.linear as in the reference.  PTQ-time modes (weight-only simulation, static activation
-calibration, learned rounding, running-stat smooth-quant collection) are out of scope and raise NotImplementedError.
+(`remain_fp.txt`) run F.linear as in the reference.  PTQ-time work lives in viditq_b200.ptq (smooth-quant statistics,
+weight parameters, static activation calibration); weight-only simulation and learned rounding are out of scope and raise.
 Nothing here falls back to a CPU or fake-quant path.
 """
 import logging
@@ -135,6 +135,7 @@ class QuantLayer(nn.Module):
             dyn = _cfg_get(act_quant_params, "dynamic", False)
             self.act_quantizer = DynamicActQuantizer(act_quant_params) if dyn else ActQuantizer(act_quant_params)
         self.split = 0
+        self.calibrating = False     # set by viditq_b200.ptq while static activation quantisers are being calibrated
         self.activation_function = StraightThrough()
         self.ignore_reconstruction = False
         self.cur_timestep_id = 0
@@ -305,9 +306,55 @@ class QuantLayer(nn.Module):
         if _is_dynamic(aq):
             if aq.per_group != "token":
                 raise NotImplementedError("dynamic activation quantisation is per-token (the ViDiT-Q W8A8 / W4A8 configs)")
-        elif aq.per_group not in (False, None, "token") or aq.delta is None or not aq.init_done:
+        elif aq.per_group not in (False, None, "token") or aq.delta is None or not (aq.init_done or self.calibrating):
             raise NotImplementedError("static activation quantisation needs calibrated per-tensor / per-token delta and "
                                       "zero_point from a PTQ checkpoint (set_quant_params_dict + set_quant_init_done)")
+
+    def calibrate_static_act(self, input):
+        """PTQ-time (viditq_b200.ptq): what the reference's static ActQuantizer does on every call while init_done is False
+        (base_quantizer.py:112-127 -> init_quant_params :146-228): (delta, zero_point) re-derived from the live tensor —
+        one pair per tensor (`per_group: False`, w8a8_naive.yaml) or per token of the layer's pooled view ('token') —,
+        for every bit-width of `mixed_precision`, through the min / max EMA (momentum 0.95) when `running_stat` is set.
+        Quirk kept: with mixed precision the reference calls init_quant_params once PER BIT-WIDTH, so the EMA advances
+        n_bitwidth times per forward.  Arithmetic in the tensor's own dtype, op for op."""
+        aq = self.act_quantizer
+        G, rows = self._pool_view(input)
+        x = input.reshape(G, rows, input.shape[-1])
+        if aq.per_group == "token":
+            xr = x.permute(1, 0, 2).reshape(rows, -1)
+        elif not aq.per_group:
+            xr = x.reshape(-1)
+        else:
+            raise NotImplementedError(f"static activation calibration with per_group={aq.per_group!r}")
+        if aq.scale_method not in ("min_max", "max") or aq.sym:
+            raise NotImplementedError("static activation calibration: asymmetric min_max only (the shipped configs)")
+        bits = aq.mixed_precision if aq.mixed_precision is not None else [aq.n_bits]
+        momentum = 0.95 if aq.running_stat else None          # base_quantizer.py:47
+        for i, b in enumerate(bits):
+            x_min = xr.min(dim=-1)[0]
+            x_min = torch.where(x_min > 0, torch.zeros_like(x_min), x_min)
+            x_max = xr.max(dim=-1)[0]
+            x_max = torch.where(x_max < 0, torch.zeros_like(x_max), x_max)
+            if momentum:
+                if getattr(aq, "x_min", None) is None:
+                    aq.x_min, aq.x_max = x_min, x_max
+                else:
+                    aq.x_min = aq.x_min * momentum + x_min * (1 - momentum)
+                    aq.x_max = aq.x_max * momentum + x_max * (1 - momentum)
+                    x_min, x_max = aq.x_min, aq.x_max
+            delta = (x_max - x_min) / (2 ** b - 1)
+            if delta.min() < 1e-6:
+                delta = torch.full_like(delta, 1e-6)
+            zp = torch.round(-x_min / delta)
+            shape = [1, rows, 1] if aq.per_group == "token" else [1, 1, 1]
+            delta, zp = delta.reshape(shape), zp.reshape(shape)
+            if aq.delta_list is None:
+                aq.delta_list = torch.full([len(bits), 1] + shape, -1.0, dtype=delta.dtype, device=delta.device)
+                aq.zero_point_list = torch.full([len(bits), 1] + shape, -1.0, dtype=zp.dtype, device=zp.device)
+            aq.delta_list[i, 0] = delta
+            aq.zero_point_list[i, 0] = zp
+        aq.delta = aq.delta_list[aq.bit_idx, 0]
+        aq.zero_point = aq.zero_point_list[aq.bit_idx, 0]
 
     def _static_act_params(self):
         """(delta, zp) of a calibrated ActQuantizer as flat fp16 CUDA tensors: 1 element (per_group False,
@@ -378,6 +425,8 @@ class QuantLayer(nn.Module):
                     x = x.contiguous()
                 out = ops.linear_w8a8(x, pw, n_bits=self.act_quantizer.n_bits, smooth=getattr(pw, "smooth", None))
             else:
+                if self.calibrating and not self.act_quantizer.init_done:
+                    self.calibrate_static_act(input)      # PTQ: parameters from this call's tensor, then quantise with them
                 a = self.quantize_input(input)
                 out = ops.gemm_w8a8(a, a.pw)
             return out.view(*input.shape[:-1], self.out_features)
