@@ -81,3 +81,28 @@ def test_argument_validation_returns_error_codes_without_touching_the_device():
     assert lib.vq_add_act_quant(fake, fake, 1024, 16, 1, 64, 4608, None, 8, fake, fake, fake, fake, None, None) == -5
     assert lib.vq_gemm_w8a8(fake, fake, fake, fake, 64, fake, fake, 64, 100, 1152, 0, None, 0, None, 0, fake, 100, None) == -1  # N % 8
     assert lib.vq_gemm_w8a8(fake, fake, fake, fake, 64, fake, fake, 64, 1152, 1152, 2, None, 0, None, 0, fake, 1152, None) == -1  # residual epilogue without res
+
+
+def test_int8_attention_boundary_without_a_device():
+    """vq_attn_i8_*: the workspace size the library reports equals the layout the host side mirrors (tests read codes and
+    scales through it), unsupported shapes answer -1 / VQ_ERR_UNSUPPORTED, bad pointers VQ_ERR_ARG — no CUDA call is made."""
+    import viditq_b200
+    from viditq_b200 import ops
+    lib = ctypes.CDLL(viditq_b200.build_library())
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    lib.vq_attn_i8_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.vq_attn_i8_workspace_bytes.restype = i64
+    lib.vq_attn_spatial_i8.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.vq_attn_i8_quantise.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.vq_attn_i8_attend.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    for n_seq, S, H in [(1, 256, 1), (3, 1024, 16), (32, 1024, 16), (2, 4096, 16)]:
+        assert lib.vq_attn_i8_workspace_bytes(n_seq, S, H, 72) == ops.attn_i8_workspace_layout(n_seq, S, H)["total"]
+    assert lib.vq_attn_i8_workspace_bytes(1, 384, 16, 72) == -1      # S not a multiple of 256
+    assert lib.vq_attn_i8_workspace_bytes(1, 8192, 16, 72) == -1     # more than 64 key blocks
+    assert lib.vq_attn_i8_workspace_bytes(1, 1024, 16, 64) == -1     # head_dim != 72
+    fake = 0x10000
+    assert lib.vq_attn_spatial_i8(None, fake, fake, 1, 1024, 16, 72, 0.1, None) == -1
+    assert lib.vq_attn_spatial_i8(fake, fake, fake + 16, 1, 1024, 16, 72, 0.1, None) == -1    # workspace not 256-byte aligned
+    assert lib.vq_attn_spatial_i8(fake, fake, fake, 1, 1000, 16, 72, 0.1, None) == -5
+    assert lib.vq_attn_i8_quantise(fake, None, 1, 1024, 16, 72, None) == -1
+    assert lib.vq_attn_i8_attend(fake, fake, 1, 1024, 16, 80, 0.1, None) == -5
