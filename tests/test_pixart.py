@@ -191,3 +191,14 @@ def test_pixart_512_fused_schedule_uses_the_attention_kernels():
     inf, l2 = _rel(fused, ref)
     print("pixart-512 fused (own attention, fused patch embed) vs layerwise schedule: %.3e %.3e" % (inf, l2))
     assert l2 <= 8e-3, (inf, l2)
+    # the opt-in INT8 Q/K/V attention on the same model (own tolerance: DESIGN.md 4.2d; default off)
+    assert not getattr(model, "attn_int8", False)
+    model.attn_int8 = True
+    try:
+        with torch.no_grad():
+            i8 = model.forward_fused(x, t, y, mask=mask).float().cpu().numpy()
+    finally:
+        model.attn_int8 = False
+    inf8, l28 = _rel(i8, fused)
+    print("pixart-512 fused with INT8 attention vs fp16 attention: %.3e %.3e" % (inf8, l28))
+    assert np.isfinite(i8).all() and 0 < l28 <= 2e-2

@@ -9,6 +9,8 @@ cond/uncond pair (quirk Q1) — the kernels take that as the pool group G.
 `forward` = reference schedule (one QuantLayer call per linear); `forward_fused` = LN+modulate+quantise fused, GELU and
 gated residuals in the GEMM epilogues, in-place residual stream.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -17,6 +19,8 @@ import torch.nn.functional as F
 from . import ops
 from .stdit import (CaptionEmbedder, Mlp, MultiHeadCrossAttention, STDiT, T2IFinalLayer, TimestepEmbedder,
                     _sincos_1d)
+
+_ATTN_INT8_ENV = os.environ.get("VQ_ATTN_INT8", "0") == "1"
 
 
 def pixart_pos_embed(dim, gh, gw, pe_interpolation=1.0, base_size=16):
@@ -197,7 +201,9 @@ class PixArtMS(nn.Module):
             # modulate + quantise in the producer warps, dequant + bias / gated residual in the epilogue
             qkv = ops.linear_w8a8(x, blk.attn.qkv.prepared_weight(), n_bits=nb, ln=(shift_msa, scale_msa))
             if ops.attn_spatial_supported(N, D):   # tcgen05 flash attention, q|k|v read in place (one sequence per image)
-                o = ops.attn_spatial(qkv, B, N, H, D, D ** -0.5).view(B, N, C)
+                # VQ_ATTN_INT8=1 / .attn_int8: the opt-in INT8 Q/K/V attention (vq_attn_spatial_i8; own tolerance)
+                attend = ops.attn_spatial_i8 if getattr(self, "attn_int8", _ATTN_INT8_ENV) else ops.attn_spatial
+                o = attend(qkv, B, N, H, D, D ** -0.5).view(B, N, C)
             else:
                 o = AttentionImg.attend(qkv, B, N, H, D)
             self._linear(blk.attn.proj, o, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
