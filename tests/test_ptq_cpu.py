@@ -100,6 +100,29 @@ def test_run_ptq_reproduces_the_reference_checkpoint(gold, monkeypatch):
     assert all(l.smooth_quant == n.startswith("blocks.") for n, l in qnn.quant_layers())
 
 
+def test_checkpoint_round_trip_through_the_reference_format(gold, monkeypatch, tmp_path):
+    """save_ckpt writes what the reference's torch.save(qnn.get_quant_params_dict()) writes; load_quant_params
+    (qdiff/utils.py:65-70) restores every buffer of every quantiser into a fresh QuantModel."""
+    import cpu_ops
+    from viditq_b200 import ptq
+    from viditq_b200.qdiff import load_quant_params
+    cpu_ops.patch_ops(monkeypatch)
+    qnn, _ = _build()
+    np.random.seed(int(gold["seed"]))
+    ckpt = ptq.run_ptq(qnn, _calib(), n_samples=2, batch_size=1, fp_layer_list=FP_LAYERS)
+    path = str(tmp_path / "ckpt.pth")
+    ptq.save_ckpt(ckpt, path)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert sorted(raw.keys()) == sorted(gold["ckpt_names"].tolist())
+    assert all(isinstance(v, (list, tuple)) and len(v) == 2 and len(v[1]) == 0 for v in raw.values())
+    qnn2, _ = _build()
+    load_quant_params(qnn2, path)
+    a, b = _bufs(ckpt), _bufs(qnn2.get_quant_params_dict())
+    assert sorted(a) == sorted(b)
+    for k in a:
+        assert torch.equal(a[k].float(), b[k].float()), k
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "fp16"])
 def test_weight_parameters_bit_exact_given_the_reference_statistics(gold, dtype):
     """Teacher-forced: with the reference's act_scale loaded, the per-timerange weight parameters equal the reference's bit
