@@ -217,3 +217,46 @@ def test_timestep_wise_static_calibration_is_refused_not_faked(monkeypatch):
     qnn.timestep_wise = True
     with pytest.raises(NotImplementedError, match="timestep-wise"):
         ptq.run_ptq(qnn, _calib(), n_samples=2, batch_size=1, fp_layer_list=FP_LAYERS)
+
+
+def test_reference_quantmodel_loads_the_produced_checkpoint(gold, monkeypatch, tmp_path):
+    """Format compatibility in the other direction: the UNMODIFIED reference QuantModel + its own load_quant_params
+    (qdiff/utils.py:65-70) read the ckpt.pth this producer wrote and run with it (skips where /root/reference is absent)."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("needs /root/reference (not on the GPU box)")
+    import cpu_ops
+    from viditq_b200 import ptq
+    cpu_ops.patch_ops(monkeypatch)
+    qnn, mine = _build()
+    np.random.seed(int(gold["seed"]))
+    path = str(tmp_path / "ckpt.pth")
+    ptq.save_ckpt(ptq.run_ptq(qnn, _calib(), n_samples=2, batch_size=1, fp_layer_list=FP_LAYERS), path)
+    ref_shims.install_opensora()
+    from opensora.models.stdit.stdit import STDiT as RefSTDiT
+    from qdiff.models.quant_model import QuantModel as RefQuantModel
+    from qdiff.utils import load_quant_params as ref_load
+    from viditq_b200.stdit import STDiT
+    plain = STDiT(input_size=(4, 16, 16), depth=2)          # un-wrapped: the same seeded weights, reference key names
+    plain.init_synthetic(seed=0)
+    ref = RefSTDiT(enable_flashattn=False, input_size=(4, 16, 16), depth=2)
+    ref.load_state_dict(plain.state_dict(), strict=True)
+    ref.eval()
+    wq, aq = ref_shims.w8a8_dynamic_configs(n_temporal=ref.num_temporal, n_spatial=ref.num_spatial, n_prompt=120, w_bits=4,
+                                            smooth=SMOOTH)
+    wq["mixed_precision"] = [4, 6, 8]
+    rq = RefQuantModel(ref, wq, aq)
+    ref_load(rq, path)
+    rq.set_quant_init_done("weight")
+    rq.set_quant_init_done("activation")
+    rq.set_smooth_quant(smooth_quant=True, smooth_quant_running_stat=False)
+    rq.set_layer_smooth_quant(model=rq, module_name_list=FP_LAYERS, smooth_quant=False, smooth_quant_running_stat=False)
+    rq.set_quant_state(True, True)
+    rq.set_layer_quant(model=rq, module_name_list=FP_LAYERS, quant_level="per_layer", weight_quant=False, act_quant=False,
+                       prefix="")
+    got = rq.model.blocks[0].attn.q.weight_quantizer.delta_list.float().numpy()
+    assert np.allclose(got, gold["ckpt/blocks.0.attn.q.weight_quantizer/delta_list"], rtol=1e-5)
+    xs, ts, cs, masks = _calib()
+    with torch.no_grad():
+        out = rq(xs[:2], ts[:2], cs[:2], mask=masks[:2][::2])
+    assert torch.isfinite(out).all()
