@@ -7,7 +7,7 @@ seeded random-init weights, min-max weight scales.  One process per GPU; ranks h
 no data-path collective — SURVEY.md §8e); value = steps of all ranks / max-over-ranks device time.
 
   python bench.py [--gpus N --steps K --warmup W]           the metric (BASELINE config 3 / 5 as a step rate)
-  python bench.py --schedule hook                            same step through the reference's hook API (QuantModel.forward:
+  python bench.py --schedule hook[-graph]                      same step through the reference's hook API (QuantModel.forward:
                                                              one QuantLayer call per linear, torch SDPA attention)
   python bench.py --workload linear | pixart512 | w4a8mp     BASELINE configs 1, 2, 4
   python bench.py --impl reference ...                       the reference's simulated-quant path on the host cores (port)
@@ -516,7 +516,7 @@ def main():
                     help="stdit: the metric (BASELINE configs 3 / 5). linear: config 1, one QuantLinear 1152->4608 through the "
                          "hook API. pixart512: config 2, one PixArt-alpha 512 solver step (CFG batch 2) under w8a8.yaml. "
                          "w4a8mp: config 4, STDiT W4A8 timestep-aware smooth-quant + per-layer mixed precision")
-    ap.add_argument("--schedule", default="fused", choices=["fused", "hook"],
+    ap.add_argument("--schedule", default="fused", choices=["fused", "hook", "hook-graph"],
                     help="fused: forward_fused in a CUDA graph. hook: the reference's hook API — QuantModel.forward, one "
                          "QuantLayer call per linear, eager (its .item() / mask_select host syncs are the reference's own)")
     ap.add_argument("--depth", type=int, default=DEPTH, help="debug only: fewer blocks (result is then NOT the metric)")
@@ -560,7 +560,7 @@ def main():
         raise SystemExit("--parallelism cfg-branch needs an even number of ranks")
     pair_group = shard.cfg_pair_groups() if pairs else None
     fsh = args.parallelism == "frames" and world > 1
-    if (pairs or fsh or args.schedule == "hook") and args.workload not in ("stdit",):
+    if (pairs or fsh or args.schedule != "fused") and args.workload not in ("stdit",):
         raise SystemExit("--parallelism / --schedule hook apply to --workload stdit")
     sample_id = rank // 2 if pairs else (0 if fsh else rank)   # ranks sharing a sample hold the same inputs and weights
     torch.manual_seed(1234 + sample_id)
@@ -625,8 +625,9 @@ def main():
             h_t.fill_(sched[i][0])
             h_coef.copy_(sched[i][1])
             return i
-        hook = args.schedule == "hook"
-        if hook:
+        hook = args.schedule in ("hook", "hook-graph")
+        hook_graph = args.schedule == "hook-graph"
+        if hook and not hook_graph:
             use_graph = False
         side_streams = [torch.cuda.Stream(), torch.cuda.Stream()] if args.cfg_mode == "split2" else []
 
@@ -634,7 +635,12 @@ def main():
             """The denoise step on device-resident inputs (iddpm forward_with_cfg + ddim_sample, cfg_split): the cond and
             uncond forwards of cfg_split run as one stacked launch sequence with un-pooled statistics (== two batch-1 calls,
             tests/test_gpu_stdit.py::test_stacked_cfg_split_equals_two_separate_forwards)."""
-            if hook:      # the reference's own call sequence: QuantModel.forward twice (iddpm/__init__.py:156-157)
+            if hook_graph:   # the same layer-by-layer schedule, sync-free so that a CUDA graph can hold it: the wrapped model
+                # is called directly (QuantModel.forward reads t[0].item(); the timestep is set outside the graph) with
+                # the mask-select plan computed once per prompt
+                out_c = qnn.model(d_z, d_t, d_yc, plan=plan1)
+                out_u = qnn.model(d_z, d_t, d_yu, plan=plan1)
+            elif hook:    # the reference's own call sequence: QuantModel.forward twice (iddpm/__init__.py:156-157)
                 out_c = qnn(d_z, d_t, d_yc, mask=d_mask)
                 out_u = qnn(d_z, d_t, d_yu, mask=d_mask)
             elif fsh:
@@ -676,7 +682,10 @@ def main():
                  "+ CFG + DDIM per step") if wl == "stdit" else (
                  "STDiT-XL/2 16x512x512 W4A8 (w4a8_timestep_aware_cb.yaml: 4-bit weights, timerange-aware smooth-quant) + "
                  "per-layer mixed precision (t20_*_mp.yaml shape: MLP layers of 3 blocks at 8 bit), cfg 7.0, step 12 of 20")
-        if hook:
+        if hook_graph:
+            label += (" — HOOK schedule in a CUDA graph: the wrapped model's layer-by-layer forward x2 (13 QuantLayer calls per "
+                      "block, torch SDPA attention), mask-select plan precomputed, timestep set outside the graph")
+        elif hook:
             label += " — HOOK schedule: QuantModel.forward x2, 13 QuantLayer calls per block, torch SDPA attention, eager"
         total_linear_top = 2 * linear_ops_per_forward() / 1e12 * args.depth / DEPTH
     elif wl == "pixart512":

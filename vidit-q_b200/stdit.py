@@ -304,8 +304,11 @@ class STDiT(nn.Module):
         x = x.view(B, Nt, Nh, Nw, Tp, Hp, Wp, self.out_channels)
         return x.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(B, self.out_channels, Nt * Tp, Nh * Hp, Nw * Wp)
 
-    def forward(self, x, timestep, y, mask=None):
-        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask)
+    def forward(self, x, timestep, y, mask=None, plan=None):
+        """The reference's schedule, layer by layer (stdit.py:246-312).  plan: a host-precomputed mask_select_plan(mask)
+        replaces the masked_select + `.tolist()` of the MASK_SELECT branch, which makes the call free of host syncs — the
+        whole layer-by-layer forward can then be captured in a CUDA graph (bench.py --schedule hook-graph)."""
+        x, t, t0, y, y_lens = self.embed(x, timestep, y, mask, plan)
         tpe = self.pos_embed_temporal.to(x.dtype)
         for i, block in enumerate(self.blocks):
             x = block(x, y, t0, y_lens, tpe if i == 0 else None)
