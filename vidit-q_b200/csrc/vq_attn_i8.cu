@@ -8,27 +8,32 @@
 // (oracle/attn_i8_oracle.py is its restatement).
 //
 // Scheme (per sequence of S tokens, per head, head_dim 72):
-//   Q8 = rint(Q / sq),  sq = max|Q[token, head, :]| / 127                    per token and head
-//   K8 = rint((K - mean_tokens K) / sk), sk per 64-key block and head        (softmax is invariant to the mean)
-//   V8 = rint(V / sv),  sv = max over the sequence of |V[:, head, dim]| / 127   per channel, stored TRANSPOSED
-//   S  = Q8 K8^T                       exact s32;  x = S * (sq sk scale log2e) - m + log2(127)
-//   P8 = rint(2^x) as u8 (<= 254: the running maximum m lags the true one by at most one octave, see below)
-//   O  = sum_k P8 V8                   exact s32 accumulation in TMEM;  out = O * sv / sum_k 2^x
+//   Q8 = rint(Q * (1 / sq)),  sq = max|Q[token, head, :]| / 127              per token and head
+//   K8 = rint((K - mean_tokens K) * (1 / sk)), sk per 64-key block and head  (softmax is invariant to the mean)
+//   V8 = rint(V * (1 / sv)),  sv = max over the sequence of |V[:, head, dim]| / 127   per channel, stored TRANSPOSED
+//   S  = Q8 K8^T                       exact s32;  x = S * (sq sk scale log2e) - m + log2(255),  m = the EXACT row maximum
+//   P8 = rint(2^x) as u8 (<= 255)
+//   O  = sum_k P8 V8                   exact s32 accumulation in TMEM;  out = O * sv / sum_k 2^x   (un-rounded row sum)
 // Two passes in front of the attention kernel produce the operands from the fused q|k|v GEMM output [n_seq * S, 3 * H * 72]:
 //   ia_stats_kernel   per (sequence, channel): mean of K, max |V|                      (reads 2/3 of q|k|v)
 //   ia_quant_kernel   per (64-token block, head): codes into [rows, {q,k}, H, 80] (72 codes + 8 zero bytes: TMA strides
 //                     must be multiples of 16 B) and V8^T [n_seq, H, 72, S] (K-major B operand of P V), scales beside.
-// The attention kernel has the structure of vq_attn_spatial_kernel (persistent CTAs, 12 warps: TMA producer, MMA issuer,
+// The attention kernel has the skeleton of vq_attn_spatial_kernel (persistent CTAs, 12 warps: TMA producer, MMA issuer,
 // TMEM owner, two softmax warpgroups with one thread per query row; work item = (sequence, head, 256 queries); two score
-// buffers per query tile; lazy rescale) with these differences:
+// buffers per query tile) with these differences:
+//   * TWO PASSES over the key tiles per item instead of an online rescale: a u8 probability leaves one octave of head-room
+//     for a lagging maximum, and on real score distributions that triggered an in-TMEM rescale of the integer accumulators
+//     on every second key tile (first version: 380 us).  Pass A streams K8 and takes the exact row maximum (integer
+//     maximum per 64-key tile x the tile's fp32 scale: score MMAs are cheap at INT8 rate, the buffer goes straight back to
+//     the MMA warp); pass B streams K8 again and V8^T once, with a fixed maximum: no rescale, no branch, full 8-bit P;
 //   * operands are bytes: Q8 / K8 rows are a 64-byte SWIZZLE_64B tile (dims 0..63: two K = 32 steps) plus a 32-byte
 //     SWIZZLE_32B tile (dims 64..95; bytes past the tensor map's 80-byte extent are TMA zero fill): K = 96 for the MMA;
 //     V8^T tiles are [80 dims (72..79 zero fill) x 64 keys] SWIZZLE_64B, two K = 32 steps of one N = 80 instruction each;
 //   * Q8 is the A operand from shared memory (12 KB per score tile), P8 the A operand from TMEM (16 columns written over S);
 //   * scores become floats with the 1.5 * 2^23 magic add (integer add + exact fp32 subtract: no I2F on the MUFU pipe), the
 //     probabilities become bytes with the same constant (fp32 add rounds to nearest even, the byte is the low mantissa byte);
-//   * the lazy-rescale threshold is ONE octave (P8 must fit a byte) and the rescale multiplies the integer accumulators in
-//     place: O = rint(O * f) — at most half a unit of an accumulator that holds >= 127 per key.
+//   * the scales an item needs are prefetched one item ahead and published through shared memory (no global load inside
+//     the key-tile loops).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
