@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--depth", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--hook", action="store_true", help="the layer-by-layer (hook API) schedule instead of forward_fused")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(1234)
@@ -42,7 +43,13 @@ def main():
     segments = model.kv_segments(plan[1], dev)
     qnn.set_timestep_id_for_quantlayer(float(d_t[0]))
 
+    plan1 = model.mask_select_plan(mask.to(dev))
+
     def step():
+        if args.hook:
+            oc = model(d_z, d_t, d_yc, plan=plan1)
+            ou = model(d_z, d_t, d_yu, plan=plan1)
+            return ops.cfg_ddim_step(oc, ou, d_z, d_coef, ddim.cfg_scale)
         o = model.forward_fused(torch.cat([d_z, d_z]), d_t.expand(2), torch.cat([d_yc, d_yu]), plan=plan,
                                 segments=segments, independent=True)
         return ops.cfg_ddim_step(o[:1], o[1:], d_z, d_coef, ddim.cfg_scale)
