@@ -52,7 +52,7 @@ class Cfg(dict):
     __getattr__ = dict.get
 
 
-def quant_cfgs(w_bits=8, smooth=None, n_spatial=S_TOKENS, n_temporal=T_FRAMES):
+def quant_cfgs(w_bits=8, smooth=None, n_spatial=S_TOKENS, n_temporal=T_FRAMES, static=False):
     sq = Cfg(enable=False, channel_wise_scale_type="momentum_act_max", momentum=0.95, alpha=0.625)
     if smooth is not None:
         sq = Cfg(enable=True, channel_wise_scale_type="momentum_act_max", momentum=0.95, **smooth)
@@ -61,6 +61,8 @@ def quant_cfgs(w_bits=8, smooth=None, n_spatial=S_TOKENS, n_temporal=T_FRAMES):
     aq = Cfg(n_bits=8, per_group="token", scale_method="min_max", round_mode="nearest_ste", running_stat=False,
              dynamic=True, sym=False, n_spatial_token=n_spatial, n_temporal_token=n_temporal, n_prompt=PROMPT_LEN,
              smooth_quant=sq)
+    if static:      # w8a8_naive.yaml: one calibrated (delta, zero point) per activation tensor
+        aq["per_group"], aq["dynamic"] = False, False
     return wq, aq
 
 
@@ -371,13 +373,13 @@ def rooflines(work, prof, peaks, int8_peak, busy_ms, ms_per_step_timed):
 # --------------------------------------------------------------------------------------------------------------------
 # models
 # --------------------------------------------------------------------------------------------------------------------
-def build_model(device, depth, w_bits=8, smooth=None):
+def build_model(device, depth, w_bits=8, smooth=None, static=False):
     import torch
     from viditq_b200.qdiff import QuantModel
     from viditq_b200.stdit import STDiT
     model = STDiT(input_size=(T_FRAMES, 64, 64), depth=depth, hidden_size=HIDDEN, num_heads=HEADS)
     model.eval()
-    wq, aq = quant_cfgs(w_bits, smooth)
+    wq, aq = quant_cfgs(w_bits, smooth, static=static)
     qnn = QuantModel(model, wq, aq)
     qnn.cfg_split = True
     if smooth is not None:      # synthetic calibration statistics (act_scale = |randn| + 0.5)
@@ -392,6 +394,18 @@ def build_model(device, depth, w_bits=8, smooth=None):
     model.dtype = torch.float16
     qnn.set_module_name_for_quantizer(module=qnn.model)
     qnn.fp_layer_list = FP_LAYERS
+    if static:
+        # the activation scales come from this repo's PTQ producer on a synthetic calibration set (two timesteps, one
+        # cond + uncond pair each): ptq.py:296-327 through the integer kernels, layer-by-layer schedule
+        from viditq_b200 import ptq
+        g = torch.Generator().manual_seed(11)
+        xs = torch.randn(4, 4, T_FRAMES, 64, 64, generator=g)
+        ts = torch.tensor([800.0, 800.0, 200.0, 200.0])
+        cs = torch.randn(4, 1, PROMPT_LEN, 4096, generator=g).half()
+        masks = torch.zeros(4, PROMPT_LEN, dtype=torch.int64)
+        masks[:, :109] = 1
+        ptq.run_ptq(qnn, (xs, ts, cs, masks), n_samples=1, batch_size=1, fp_layer_list=FP_LAYERS, device=device)
+        return qnn, model
     qnn.init_weight_quant_params()
     qnn.set_quant_init_done("weight")
     qnn.set_quant_init_done("activation")
@@ -512,7 +526,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="stdit", choices=["stdit", "linear", "pixart512", "w4a8mp"],
+    ap.add_argument("--workload", default="stdit", choices=["stdit", "linear", "pixart512", "w4a8mp", "w8a8static"],
                     help="stdit: the metric (BASELINE configs 3 / 5). linear: config 1, one QuantLinear 1152->4608 through the "
                          "hook API. pixart512: config 2, one PixArt-alpha 512 solver step (CFG batch 2) under w8a8.yaml. "
                          "w4a8mp: config 4, STDiT W4A8 timestep-aware smooth-quant + per-layer mixed precision")
@@ -560,7 +574,8 @@ def main():
         raise SystemExit("--parallelism cfg-branch needs an even number of ranks")
     pair_group = shard.cfg_pair_groups() if pairs else None
     fsh = args.parallelism == "frames" and world > 1
-    if (pairs or fsh or args.schedule != "fused") and args.workload not in ("stdit",):
+    if (pairs or fsh) and args.workload not in ("stdit",) or (args.schedule != "fused" and
+                                                               args.workload not in ("stdit", "w8a8static")):
         raise SystemExit("--parallelism / --schedule hook apply to --workload stdit")
     sample_id = rank // 2 if pairs else (0 if fsh else rank)   # ranks sharing a sample hold the same inputs and weights
     torch.manual_seed(1234 + sample_id)
@@ -573,8 +588,14 @@ def main():
     # ================================================================================================================
     g = torch.Generator().manual_seed(99 + sample_id)
     use_graph = not args.no_graph
-    if wl in ("stdit", "w4a8mp"):
-        if wl == "w4a8mp":
+    if wl in ("stdit", "w4a8mp", "w8a8static"):
+        if wl == "w8a8static":
+            # w8a8_naive.yaml: static per-tensor activation scales, calibrated here by viditq_b200.ptq; same step otherwise
+            qnn, model = build_model(dev, args.depth, static=True)
+            ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
+            mp = None
+            metric = "stdit_16x512x512_w8a8_static_denoise_steps_per_sec"
+        elif wl == "w4a8mp":
             # w4a8_timestep_aware_cb.yaml: 4-bit weights, timerange-aware smooth-quant (alpha 0.11 / 0.11), 20 steps, cfg 7
             qnn, model = build_model(dev, args.depth, w_bits=4,
                                      smooth=dict(alpha=[0.11, 0.11], timerange=[[0, 500], [501, 1000]]))
@@ -680,6 +701,8 @@ def main():
         label = ("STDiT-XL/2 16x512x512 (T=16,S=1024 -> 16384 tokens, 28 blocks) W8A8 per-token dynamic (w8a8_dynamic.yaml), "
                  "cfg_split: cond + uncond forwards (one stacked launch sequence, un-pooled statistics == two batch-1 calls) "
                  "+ CFG + DDIM per step") if wl == "stdit" else (
+                 "STDiT-XL/2 16x512x512 W8A8 with STATIC per-tensor activation scales (w8a8_naive.yaml; calibrated by "
+                 "viditq_b200.ptq on a synthetic calibration set), cfg_split stacked + CFG + DDIM per step") if wl == "w8a8static" else (
                  "STDiT-XL/2 16x512x512 W4A8 (w4a8_timestep_aware_cb.yaml: 4-bit weights, timerange-aware smooth-quant) + "
                  "per-layer mixed precision (t20_*_mp.yaml shape: MLP layers of 3 blocks at 8 bit), cfg 7.0, step 12 of 20")
         if hook_graph:

@@ -75,3 +75,58 @@ def test_ptq_on_the_device_and_checkpoint_round_trip(tmp_path):
         b = model2.forward_fused(x, t, y, mask=mask).float().cpu()
     assert torch.isfinite(a).all() and ops.check_status() == 0
     assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_static_checkpoint_from_the_producer_runs_on_the_fused_schedule():
+    """w8a8_naive.yaml family end to end on the device: static per-tensor activation scales calibrated by
+    viditq_b200.ptq.run_ptq (through the integer kernels), then the SAME model on the fused schedule — which forms the
+    LayerNorm / add / GELU tensors first and quantises them with vq_act_quant_static, q|k|v through one shared pass —
+    against the layer-by-layer schedule.  Image-sized token counts (4 frames x 256 tokens) so that the own attention kernels run."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from test_stdit_graph_cpu import Cfg
+    from viditq_b200 import ops, ptq
+    from viditq_b200.qdiff import QuantModel
+    from viditq_b200.stdit import STDiT
+    T, S = 4, 256
+    model = STDiT(input_size=(T, 32, 32), depth=2)
+    model.init_synthetic(seed=3)
+    model.eval()
+    sq = Cfg(enable=False, channel_wise_scale_type="momentum_act_max", momentum=0.95, alpha=0.625)
+    wq = Cfg(n_bits=8, per_group="channel", channel_dim=0, scale_method="min_max", round_mode="nearest")
+    aq = Cfg(n_bits=8, per_group=False, scale_method="min_max", round_mode="nearest_ste", running_stat=False, dynamic=False,
+             sym=False, n_spatial_token=S, n_temporal_token=T, n_prompt=120, smooth_quant=sq)
+    qnn = QuantModel(model, wq, aq)
+    qnn.cuda()
+    qnn.half()
+    model.dtype = torch.float16
+    g = torch.Generator().manual_seed(17)
+    n = 4
+    xs = torch.randn(n, 4, T, 32, 32, generator=g)
+    ts = torch.tensor([800.0, 800.0, 200.0, 200.0])
+    cs = torch.randn(n, 1, 120, 4096, generator=g).half()
+    masks = torch.zeros(n, 120, dtype=torch.int64)
+    masks[:, :77] = 1
+    ptq.run_ptq(qnn, (xs, ts, cs, masks), n_samples=1, batch_size=1, fp_layer_list=FP_LAYERS, device=torch.device("cuda"))
+    x = torch.randn(1, 4, T, 32, 32, generator=g).cuda()
+    y = torch.randn(1, 1, 120, 4096, generator=g).cuda()
+    mask = torch.zeros(1, 120, dtype=torch.int64)
+    mask[0, :93] = 1
+    mask = mask.cuda()
+    t = torch.tensor([500.0], device="cuda")
+    with torch.no_grad():
+        n0 = ops.launch_count()
+        ref = qnn(x, t, y, mask=mask).float().cpu()
+        n1 = ops.launch_count()
+        out = model.forward_fused(x, t, y, mask=mask).float().cpu()
+        n2 = ops.launch_count()
+        both = model.forward_fused(torch.cat([x, x]), torch.cat([t, t]), torch.cat([y, y]), mask=mask,
+                                   independent=True).float().cpu()
+    assert model._engine.static and ops.check_status() == 0 and torch.isfinite(out).all()
+    assert all(v[1] for v in model._engine._static_same.values())       # q / k / v share their calibrated scales
+    rel = ((out - ref).norm() / ref.norm()).item()
+    print("static per-tensor scales: fused vs layer-by-layer schedule rel-L2 %.3e (%d vs %d own launches)"
+          % (rel, n2 - n1, n1 - n0))
+    assert rel <= 4e-3 and (n2 - n1) < (n1 - n0)
+    assert torch.equal(both[0], out[0]) and torch.equal(both[1], out[0])      # static scales: stacking changes nothing

@@ -366,13 +366,15 @@ class FusedBlocks:
         # (vq_attn_spatial_i8).  The reference keeps attention in fp16 (its Q/K/V quantisers are commented out,
         # quant_block.py:617-632), so this leaves the reference's numerics: own tolerance, DESIGN.md 4.2d.  Default off.
         self.attn_int8 = os.environ.get("VQ_ATTN_INT8", "0") == "1"
+        self.static = False          # set by check_state(): all block linears carry static per-tensor activation scales
+        self._static_same = {}       # (block, branch) -> (key, q / k / v share one calibrated (delta, zero point))
 
     @staticmethod
-    def _spatial_library(qkv, pj, scale, B, N, T, S, C, D, independent):
+    def _spatial_library(qkv, pj, scale, B, N, T, S, C, D, independent, static=False):
         """Library yardstick / shapes vq_attn_spatial does not cover (head_dim != 72 or S not a multiple of 256)."""
         o = F.scaled_dot_product_attention(qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2),
                                            qkv[:, :, 2].transpose(1, 2), scale=scale)   # [B*T, H, S, D]
-        if o.is_contiguous() and D == 72 and C == 1152 and not pj.smooth_quant:
+        if o.is_contiguous() and D == 72 and C == 1152 and not pj.smooth_quant and not static:
             # quantise straight from the head-major layout the library kernel emits (no transpose copy)
             a = (ops.act_quant_heads(o, 1, B * N, S, n_bits=pj.act_quantizer.n_bits) if independent
                  else ops.act_quant_heads(o, B, N, S, n_bits=pj.act_quantizer.n_bits))
@@ -383,11 +385,14 @@ class FusedBlocks:
     LN_FUSED = ("attn.q", "attn.k", "attn.v", "attn_temp.q", "attn_temp.k", "attn_temp.v", "mlp.fc1")
 
     def check_state(self):
-        """The fused schedule hard-wires per-token DYNAMIC W+A quantisation of all 13 block linears (the ViDiT-Q W8A8 /
-        W4A8 configs).  Anything else — a layer switched to FP by set_layer_quant, static (calibrated) activation scales
-        of w8a8_naive.yaml, input-dependent smooth-quant scales in front of an LN-fused quantiser, q/k/v with different
-        activation widths — must go through STDiT.forward (one QuantLayer call per linear); checked on EVERY call."""
+        """The fused schedule runs all 13 block linears W+A quantised, their activations either per-token DYNAMIC (the
+        ViDiT-Q W8A8 / W4A8 configs: quantisers fused with LayerNorm / add / GELU passes) or — all of them — with STATIC
+        per-tensor calibrated scales (w8a8_naive.yaml: the transformed fp16 tensor is formed first, then vq_act_quant_static).
+        Anything else — a layer switched to FP by set_layer_quant, static per-token scales, a mix of the two kinds,
+        input-dependent smooth-quant scales in front of an LN-fused quantiser, q/k/v with different activation widths —
+        must go through STDiT.forward (one QuantLayer call per linear); checked on EVERY call.  Sets self.static."""
         from .qdiff import _is_dynamic
+        kinds = set()
         for i, blk in enumerate(self.m.blocks):
             for path in ("attn.q", "attn.k", "attn.v", "attn.proj", "attn_temp.q", "attn_temp.k", "attn_temp.v",
                          "attn_temp.proj", "cross_attn.q_linear", "cross_attn.kv_linear", "cross_attn.proj", "mlp.fc1",
@@ -396,9 +401,17 @@ class FusedBlocks:
                 if not (isinstance(l, QuantLayer) and l.weight_quant and l.act_quant and not l.disable_act_quant):
                     raise NotImplementedError(f"forward_fused: blocks.{i}.{path} is not in W+A quantised state; use forward()")
                 aq = l.act_quantizer
-                if not _is_dynamic(aq) or aq.per_group != "token":
-                    raise NotImplementedError(f"forward_fused: blocks.{i}.{path} has static / non-per-token activation "
-                                              "scales (w8a8_naive.yaml family); use forward()")
+                if _is_dynamic(aq) and aq.per_group == "token":
+                    kinds.add("dynamic")
+                elif (not _is_dynamic(aq) and not aq.per_group and aq.init_done and aq.delta is not None
+                      and aq.delta.numel() == 1):
+                    kinds.add("static")
+                else:
+                    raise NotImplementedError(f"forward_fused: blocks.{i}.{path} has static per-token / un-calibrated / "
+                                              "non-per-token activation scales; use forward()")
+                if len(kinds) > 1:
+                    raise NotImplementedError(f"forward_fused: blocks.{i}.{path} mixes static and dynamic activation "
+                                              "quantisers with the layers before it; use forward()")
                 if path in self.LN_FUSED and l.smooth_mode() in ("dynamic", "running"):
                     raise NotImplementedError(f"forward_fused: blocks.{i}.{path} uses an input-dependent smooth-quant scale "
                                               "in front of a fused LayerNorm / add quantiser; use forward()")
@@ -406,6 +419,7 @@ class FusedBlocks:
                 if len({att.q.act_quantizer.n_bits, att.k.act_quantizer.n_bits, att.v.act_quantizer.n_bits}) != 1:
                     raise NotImplementedError(f"forward_fused: blocks.{i} q/k/v activation widths differ (shared quantise "
                                               "pass); use forward()")
+        self.static = kinds == {"static"}
 
     def _qkv_weight(self, attn, tag):
         layers = (attn.q, attn.k, attn.v)
@@ -420,10 +434,34 @@ class FusedBlocks:
             hit = self._qkv[tag] = (key, ops.PreparedWeight(codes, col, codes.shape[0], pws[0].K, pws[0].n_bits))
         return hit[1]
 
+    def _static_qkv(self, attn, tag, t):
+        """Static per-tensor scales: `t` is the fp16 tensor the three layers see (LayerNorm / add already applied).  q, k
+        and v were calibrated on the same tensor; when their (delta, zero point) are identical and no per-layer smooth-quant
+        scale is in the way, ONE vq_act_quant_static pass feeds the concatenated N = 3C GEMM, otherwise each layer
+        quantises for itself and the three GEMMs write column slices of one output."""
+        layers = (attn.q, attn.k, attn.v)
+        C = t.shape[-1]
+        pw = self._qkv_weight(attn, tag)
+        if pw is not None:
+            aqs = [l.act_quantizer for l in layers]
+            key = tuple((q.delta.data_ptr(), q.delta._version, q.zero_point.data_ptr(), q.zero_point._version) for q in aqs)
+            hit = self._static_same.get(tag)
+            if hit is None or hit[0] != key:   # one host comparison per checkpoint (outside any graph capture: warm-up call)
+                same = all(torch.equal(aqs[0].delta.reshape(-1), q.delta.reshape(-1)) and
+                           torch.equal(aqs[0].zero_point.reshape(-1), q.zero_point.reshape(-1)) for q in aqs[1:])
+                hit = self._static_same[tag] = (key, same)
+            if hit[1]:
+                return ops.gemm_w8a8(layers[0].quantize_input(t), pw)
+        out = torch.empty(t.numel() // C, 3 * C, dtype=t.dtype, device=t.device)
+        for j, layer in enumerate(layers):
+            a = layer.quantize_input(t)
+            ops.gemm_w8a8(a, a.pw, out=out[:, j * C:(j + 1) * C], ldo=3 * C)
+        return out
+
     def _qlin(self, layer, t, qi, unpooled, **kw):
         """Quantiser + GEMM of one block linear on `t` [.., n, C].  Overlapped mode (un-pooled statistics only): one call,
         the quantise arithmetic runs inside the GEMM kernel."""
-        if self.overlap and unpooled and layer.smooth_mode() in (None, "cached"):
+        if self.overlap and unpooled and not self.static and layer.smooth_mode() in (None, "cached"):
             pw = layer.prepared_weight()
             return ops.linear_w8a8(t.reshape(1, -1, t.shape[-1]), pw, n_bits=layer.act_quantizer.n_bits,
                                    smooth=getattr(pw, "smooth", None), **kw)
@@ -436,6 +474,15 @@ class FusedBlocks:
         its own channel scale, hence its own codes; the three GEMMs write column slices of the same output.
         add = (vectors [period, C], rows_per_add): an fp16 row-broadcast add fused in front of the quantiser (block 0's
         temporal position embedding) when K = 1152."""
+        if self.static:   # calibrated scales: form the fp16 tensor the layers see, then the static quantiser
+            if ln is not None:
+                rpm = x.shape[1] if independent else None
+                x = ops.ln_modulate_act_quant(x.view(1, -1, x.shape[2]) if independent else x, ln[0], ln[1], want_y=True,
+                                              rows_per_mod=rpm)[1]
+            elif add is not None:
+                vec, rpa = add
+                x = (x.reshape(-1, vec.shape[0], rpa, x.shape[-1]) + vec.view(1, -1, 1, x.shape[-1])).view(x.shape)
+            return self._static_qkv(attn, tag, x)
         pw = self._qkv_weight(attn, tag)
         nb = attn.q.act_quantizer.n_bits
         rpm = None
@@ -480,6 +527,8 @@ class FusedBlocks:
             grp, P, prank = frames
             if not (independent or B == 1):
                 raise NotImplementedError("frame sharding moves per-token codes: needs un-pooled statistics")
+            if self.static:
+                raise NotImplementedError("frame sharding exchanges per-token codes with their dynamic (delta, zp) tails")
             if T * P != m.num_temporal or S % P:
                 raise ValueError(f"frame sharding: {T} local frames x {P} ranks != {m.num_temporal} or {S} % {P} != 0")
             t_first = prank * T
@@ -487,6 +536,8 @@ class FusedBlocks:
         def qi(layer, t, gelu=False):
             """The layer's activation quantiser. Frame-sharded: a rank holds T / P frames, which the reference layers'
             (B, T*S) pooling views do not describe — every row is quantised on its own (un-pooled, as checked above)."""
+            if self.static:   # no GELU inside vq_act_quant_static: the activation is a torch pass in front of it
+                return layer.quantize_input(F.gelu(t, approximate="tanh") if gelu else t)
             if frames is None:
                 return layer.quantize_input(t, gelu=gelu, independent=independent)
             if layer.smooth_quant:
@@ -513,7 +564,8 @@ class FusedBlocks:
                 self._qlin(pj, o.view(B * T, S, C), qi, unpooled, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa,
                            rows_per_gate=N, out=xr)
             else:
-                a = self._spatial_library(qkv.view(B * T, S, 3, H, D), pj, blk.attn.scale, B, N, T, S, C, D, independent)
+                a = self._spatial_library(qkv.view(B * T, S, 3, H, D), pj, blk.attn.scale, B, N, T, S, C, D, independent,
+                                          self.static)
                 ops.gemm_w8a8(a, a.pw, epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr, gate=gate_msa, rows_per_gate=N, out=xr)
             # ---- temporal attention on the (T S) layout (+ temporal pos-emb in block 0)
             if frames is not None:
@@ -537,13 +589,13 @@ class FusedBlocks:
                 a = shard.exchange_act_codes(a, B, T, S, P, False, grp)
                 ops.gemm_w8a8(a, blk.attn_temp.proj.prepared_weight(), epi=ops.VQ_EPI_GATE_RESIDUAL, res=xr,
                               gate=gate_msa, rows_per_gate=N, out=xr)
-            elif i == 0 and C == 1152:   # x + tpe rides in the quantise pass (vq_add_act_quant): frame t = (row // S) % T
+            elif i == 0 and C == 1152 and not self.static:   # x + tpe rides in the quantise pass (vq_add_act_quant): frame t = (row // S) % T
                 qkv = self._qkv_project(blk.attn_temp, (i, "t"), x, independent=independent, add=(tpe.view(T, C), S))
             else:
                 xt = x if i != 0 else (x.view(B, T, S, C) + tpe.view(1, T, 1, C)).view(B, N, C)
                 qkv = self._qkv_project(blk.attn_temp, (i, "t"), xt, independent=independent)
             pjt = blk.attn_temp.proj
-            if (frames is None and self.temporal_fused_quant and (independent or B == 1)
+            if (frames is None and self.temporal_fused_quant and (independent or B == 1) and not self.static
                     and ops.attn_temporal_quant_supported(T, H, D) and pjt.smooth_mode() in (None, "cached")):
                 # temporal attention + the projection's quantiser in ONE kernel (all 16 heads of a position in one block):
                 # no fp16 attention output, no separate quantise pass
@@ -576,7 +628,12 @@ class FusedBlocks:
             # ---- MLP: LN + modulate + quantise, fc1 (+GELU), quantise, fc2 (+gate, residual)
             fc1w = blk.mlp.fc1.prepared_weight()
             # GELU rides in fc2's quantise pass (HBM-bound, idle MUFU) instead of fc1's epilogue (epilogue-bound)
-            if self.overlap and unpooled:
+            if self.static:
+                yln = ops.ln_modulate_act_quant(x.view(1, M, C) if independent else x, shift_mlp, scale_mlp, want_y=True,
+                                                rows_per_mod=N if independent else None)[1]
+                a = blk.mlp.fc1.quantize_input(yln)
+                h = ops.gemm_w8a8(a, a.pw).view(B, N, -1)
+            elif self.overlap and unpooled:
                 h = ops.linear_w8a8(x.view(1, M, C), fc1w, n_bits=blk.mlp.fc1.act_quantizer.n_bits,
                                     smooth=getattr(fc1w, "smooth", None), ln=(shift_mlp, scale_mlp), rows_per_mod=N).view(B, N, -1)
             else:
