@@ -92,9 +92,13 @@ def main():
     launches(tag)
     for rep in sorted(glob.glob(os.path.join(SRC, "*.ncu-rep"))):
         report(tag, rep)
+    # session logs written beside the reports: only those of THIS session (newer than the oldest report minus an hour) —
+    # gpurun_out/ accumulates across calls, an old log must not be re-filed under a new tag
+    reps = glob.glob(os.path.join(SRC, "*.ncu-rep"))
+    fresh = (min(os.path.getmtime(r) for r in reps) - 3600) if reps else float("inf")
     for log in ("selftest.log", "attn_selftest.log", "prof_kernels.log", "bench.log", "timeline.log", "smi.txt"):
         p = os.path.join(SRC, log)
-        if os.path.exists(p):
+        if os.path.exists(p) and os.path.getmtime(p) >= fresh:
             with open(p) as fi, open(os.path.join(OUT, f"{tag}_{log}"), "w") as fo:
                 fo.write(fi.read())
 
