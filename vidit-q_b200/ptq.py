@@ -80,7 +80,10 @@ def calibrate_static_activations(qnn, layers, calib, batch_size, device=None):
     to = (lambda v: v.to(device)) if device is not None else (lambda v: v)
     for layer in layers:
         layer.calibrating = True
-        layer.act_quantizer.init_done = False
+        aq = layer.act_quantizer
+        aq.init_done = False
+        aq.x_min = aq.x_max = None                    # a fresh calibration: no EMA state, no parameters of an earlier run
+        aq.delta_list = aq.zero_point_list = aq.delta = aq.zero_point = None
     try:
         for i in range(int(xs.size(0) / calib_batch_size)):
             sel = slice(i * calib_batch_size, (i + 1) * calib_batch_size)
