@@ -1,6 +1,8 @@
-"""Bring-up / timing of the opt-in INT8 attention (vq_attn_spatial_i8): operand codes against oracle/attn_i8_oracle.py,
-the attention kernel against the oracle's tile-ordered restatement on the kernel's own codes, the scheme against fp16
-attention, and the launch times beside vq_attn_spatial.  python tools/attn_i8_check.py [--full]"""
+"""TEST INFRASTRUCTURE (lives under tests/ because it executes the oracle): helper of tests/test_gpu_attn_i8.py and
+bring-up / timing script of the opt-in INT8 attention (vq_attn_spatial_i8) — operand codes against
+oracle/attn_i8_oracle.py, the attention kernel against the oracle's restatement of its arithmetic on the kernel's own
+codes, the scheme against fp16 attention, and the launch times beside vq_attn_spatial.
+    python tests/attn_i8_check.py [--full] [--no-timing]"""
 import argparse
 import os
 import sys
@@ -10,7 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import attn_i8_oracle as A   # noqa: E402  (tool = test infrastructure)
+from oracle import attn_i8_oracle as A   # noqa: E402
 from viditq_b200 import ops              # noqa: E402
 
 
