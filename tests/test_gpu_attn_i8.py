@@ -55,7 +55,8 @@ def test_k_mean_subtraction_leaves_the_exact_attention_unchanged():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_seq,S,H,seed,gain", [(1, 256, 1, 0, 1.0), (1, 512, 2, 1, 1.0), (2, 1024, 4, 2, 2.0),
-                                                 (3, 1024, 16, 3, 1.0)])
+                                                 (3, 1024, 16, 3, 1.0),
+                                                 (1, 4096, 1, 4, 1.0)])     # the largest sequence: 64 key blocks
 def test_int8_attention_codes_bit_exact_and_kernel_matches_its_oracle(n_seq, S, H, seed, gain):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
