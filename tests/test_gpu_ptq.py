@@ -130,3 +130,14 @@ def test_static_checkpoint_from_the_producer_runs_on_the_fused_schedule():
           % (rel, n2 - n1, n1 - n0))
     assert rel <= 4e-3 and (n2 - n1) < (n1 - n0)
     assert torch.equal(both[0], out[0]) and torch.equal(both[1], out[0])      # static scales: stacking changes nothing
+    # q / k / v with DIFFERENT calibrated scales (a hand-edited checkpoint): the shared pass must give way to three
+    for blk in model.blocks:
+        blk.attn.k.act_quantizer.delta.mul_(1.25)
+        blk.attn_temp.v.act_quantizer.delta.mul_(0.8)
+    with torch.no_grad():
+        ref2 = qnn(x, t, y, mask=mask).float().cpu()
+        out2 = model.forward_fused(x, t, y, mask=mask).float().cpu()
+    assert not any(v[1] for v in model._engine._static_same.values())
+    rel2 = ((out2 - ref2).norm() / ref2.norm()).item()
+    print("static per-tensor scales, q / k / v scales differing: fused vs layer-by-layer rel-L2 %.3e" % rel2)
+    assert rel2 <= 4e-3 and not torch.equal(out2, out)
