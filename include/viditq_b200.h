@@ -74,6 +74,19 @@ int vq_act_quant(const void* x, int G, int rows, int K, int64_t group_stride, in
 int vq_act_quant_static(const void* x, int M, int K, int64_t ld, const void* delta, const void* zp, int period,
                         const void* smooth, int n_bits, uint8_t* codes, int32_t* rowsum, void* stream);
 
+/* The same static quantiser with the producer's elementwise step fused in front, for the fused schedule of static
+ * checkpoints (the reference applies them as separate torch ops: nn.GELU(approximate="tanh") between fc1 and fc2, timm Mlp;
+ * LayerNorm + t2i_modulate of stdit.py:104,122 / blocks.py t2i_modulate): one pass instead of two.
+ *   vq_gelu_act_quant_static           codes of h(gelu_tanh(x))
+ *   vq_ln_modulate_act_quant_static    codes of h(h(LN(x) * h(1 + scale)) + shift); row m uses modulation vector
+ *                                      m / rows_per_mod; K <= 2304 (the row is held in registers)                       */
+int vq_gelu_act_quant_static(const void* x, int M, int K, int64_t ld, const void* delta, const void* zp, int period,
+                             const void* smooth, int n_bits, uint8_t* codes, int32_t* rowsum, void* stream);
+int vq_ln_modulate_act_quant_static(const void* x, const void* shift, const void* scale, int M, int K, int rows_per_mod,
+                                    const void* delta, const void* zp, int period, const void* smooth, int n_bits,
+                                    uint8_t* codes, int32_t* rowsum, void* stream);
+
+
 /* (a1) on h(x + addv[(r / rows_per_add) % add_period]): the temporal position embedding added in front of block 0's
  * temporal attention (stdit.py:113-115, `x + self.pos_embed_temporal` on the "(B S) T C" view; in the (T S) token order the
  * embedding of frame t belongs to rows [t S, (t + 1) S): rows_per_add = S, add_period = T), an fp16 add, fused into the

@@ -49,8 +49,11 @@ def act_quant(x, n_bits=8, smooth=None, out=None, gelu=False):
                         torch.from_numpy(r["zp"].astype(F16)), torch.from_numpy(r["rowsum"].reshape(-1)), G, rows, K)
 
 
-def act_quant_static(x, delta, zp, n_bits=8, smooth=None):
+def act_quant_static(x, delta, zp, n_bits=8, smooth=None, gelu=False, ln=None, rows_per_mod=None):
+    assert ln is None, "the LayerNorm-fused static form belongs to the fused schedule (GPU only)"
     xn = _np16(x)
+    if gelu:
+        xn = _gelu16(xn)
     K = xn.shape[-1]
     period = delta.numel()
     x3 = xn.reshape(-1, period, K) if period > 1 else xn.reshape(1, -1, K)

@@ -468,3 +468,38 @@ def test_temporal_attention_with_fused_quantiser_is_bit_identical(B, T, S):
         assert torch.equal(got.codes, ref.codes) and torch.equal(got.delta, ref.delta)
         assert torch.equal(got.zp, ref.zp) and torch.equal(got.rowsum, ref.rowsum)
     assert ops.check_status() == 0
+
+
+@pytest.mark.gpu
+def test_static_quantiser_fused_forms_equal_the_two_pass_forms():
+    """vq_gelu_act_quant_static / vq_ln_modulate_act_quant_static (the fused schedule of static checkpoints) against the
+    same static quantiser applied to the separately formed tensor: GELU — torch's nn.GELU(approximate="tanh") in fp16, the op
+    the reference runs — bit for bit; LayerNorm + modulate against the y of vq_ln_modulate_act_quant (two fp32 summation
+    orders of the same LayerNorm: a last-bit difference of y may move a code by one step on a vanishing share of elements)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import torch.nn.functional as F
+    from viditq_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    delta = torch.tensor([0.043], dtype=torch.float16, device="cuda")
+    zp = torch.tensor([117.0], dtype=torch.float16, device="cuda")
+    # ---- GELU, K = 4608 (the Mlp hidden tensor), values beyond the calibrated range saturate
+    h = (torch.randn(1, 777, 4608, generator=g) * 2.5).half().cuda()
+    a = ops.act_quant_static(h, delta, zp, gelu=True)
+    b = ops.act_quant_static(F.gelu(h, approximate="tanh"), delta, zp)
+    assert torch.equal(a.codes, b.codes) and torch.equal(a.rowsum, b.rowsum)
+    assert int(a.codes.max()) == 255 and int(a.codes.min()) < 117
+    # ---- LayerNorm + modulate, K = 1152, two modulation vectors (stacked cfg branches)
+    x = (torch.randn(1, 2 * 300, 1152, generator=g) * 1.7 + 0.3).half().cuda()
+    shift = (torch.randn(2, 1152, generator=g) * 0.2).half().cuda()
+    scale = (torch.randn(2, 1152, generator=g) * 0.2).half().cuda()
+    d2 = torch.tensor([0.021], dtype=torch.float16, device="cuda")
+    z2 = torch.tensor([131.0], dtype=torch.float16, device="cuda")
+    y = ops.ln_modulate_act_quant(x, shift, scale, want_y=True, rows_per_mod=300)[1]
+    a = ops.act_quant_static(x, d2, z2, ln=(shift, scale), rows_per_mod=300)
+    b = ops.act_quant_static(y, d2, z2)
+    diff = (a.codes.int() - b.codes.int()).abs()
+    frac = (diff > 0).float().mean().item()
+    print("LN-fused static quantiser vs two passes: codes differing %.2e, largest step %d" % (frac, int(diff.max())))
+    assert int(diff.max()) <= 1 and frac <= 1e-4
+    assert ops.check_status() == 0

@@ -13,7 +13,7 @@ VQ_EPI_BIAS, VQ_EPI_GELU_TANH, VQ_EPI_GATE_RESIDUAL = 0, 1, 2
 VQ_STATUS_EPS_DEGENERATE = 1
 _ERR = {-1: "VQ_ERR_ARG", -2: "VQ_ERR_DRIVER", -3: "VQ_ERR_TMAP", -4: "VQ_ERR_LAUNCH", -5: "VQ_ERR_UNSUPPORTED"}
 
-EXPORTS = ["vq_version", "vq_num_sms", "vq_prep_weight", "vq_act_quant", "vq_act_quant_static", "vq_add_act_quant", "vq_gelu_act_quant", "vq_act_quant_heads", "vq_ln_modulate_act_quant", "vq_gemm_w8a8",
+EXPORTS = ["vq_version", "vq_num_sms", "vq_prep_weight", "vq_act_quant", "vq_act_quant_static", "vq_gelu_act_quant_static", "vq_ln_modulate_act_quant_static", "vq_add_act_quant", "vq_gelu_act_quant", "vq_act_quant_heads", "vq_ln_modulate_act_quant", "vq_gemm_w8a8",
            "vq_col_absmax", "vq_row_pack", "vq_linear_w8a8", "vq_linear_workspace_bytes", "vq_linear_launch_count", "vq_linear_set_fused_policy", "vq_pack_u4", "vq_linear_w4a8",
            "vq_attn_temporal", "vq_attn_temporal_quant", "vq_attn_cross", "vq_attn_spatial", "vq_attn_i8_workspace_bytes", "vq_attn_i8_quantise", "vq_attn_i8_attend", "vq_attn_spatial_i8", "vq_cfg_ddim_step", "vq_patch_embed", "vq_status_read"]
 
@@ -40,6 +40,8 @@ def lib():
     L.vq_act_quant.argtypes = [vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp]
     L.vq_add_act_quant.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     L.vq_act_quant_static.argtypes = [vp, i32, i32, i64, vp, vp, i32, vp, i32, vp, vp, vp]
+    L.vq_gelu_act_quant_static.argtypes = [vp, i32, i32, i64, vp, vp, i32, vp, i32, vp, vp, vp]
+    L.vq_ln_modulate_act_quant_static.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp]
     L.vq_gelu_act_quant.argtypes = [vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp]
     L.vq_act_quant_heads.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.vq_ln_modulate_act_quant.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]

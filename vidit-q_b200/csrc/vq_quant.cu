@@ -426,8 +426,14 @@ struct StaticQuantArgs {
   float qmax;
   uint8_t* codes;
   int32_t* rowsum;
+  const __half* shift;   // LN variant: [M / rows_per_mod, K] modulation vectors
+  const __half* scale;
+  int rows_per_mod;
 };
 
+// GELU = true: nn.GELU(approximate="tanh") on the loaded values first (fc2's input in the fused schedule: no row statistics
+// are needed with calibrated scales, so the row streams through chunk by chunk)
+template <bool GELU>
 __global__ void __launch_bounds__(256) vq_act_quant_static_kernel(const StaticQuantArgs a) {
   grid_dep_sync();
   const int lane = threadIdx.x & 31;
@@ -446,6 +452,13 @@ __global__ void __launch_bounds__(256) vq_act_quant_static_kernel(const StaticQu
     for (int ci = lane; ci < (a.K >> 3); ci += 32) {
       uint4 xv = __ldg(reinterpret_cast<const uint4*>(xrow) + ci);
       __half2* x = reinterpret_cast<__half2*>(&xv);
+      if (GELU) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 gl = gelu_tanh_pair(__half22float2(x[e]));
+          x[e] = __floats2half2_rn(gl.x, gl.y);
+        }
+      }
       if (a.smooth) {   // quant_layer.py:140 input / channel_wise_scale
         uint4 sv = __ldg(reinterpret_cast<const uint4*>(a.smooth) + ci);
         const __half2* sm = reinterpret_cast<const __half2*>(&sv);
@@ -456,6 +469,36 @@ __global__ void __launch_bounds__(256) vq_act_quant_static_kernel(const StaticQu
       for (int e = 0; e < 4; ++e) x[e] = __hmin2(__hmax2(x[e], __hneg2(xl)), xl);
       reinterpret_cast<uint2*>(crow)[ci] = quant_chunk(xv, qc, sum);
     }
+    sum = warp_sum_i(sum);
+    if (lane == 0) a.rowsum[m] = sum;
+  }
+}
+
+// LayerNorm + t2i_modulate in front of the static quantiser (K <= 8 * 32 * MAXC: the row is held in registers for the two
+// LayerNorm passes; same apply_ln_modulate as the dynamic chunk-mapped kernel)
+template <int MAXC>
+__global__ void __launch_bounds__(256) vq_ln_act_quant_static_kernel(const StaticQuantArgs a) {
+  grid_dep_sync();
+  const int lane = threadIdx.x & 31;
+  const int nchunk = a.K >> 3;
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  for (int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < a.M; m += wstride) {
+    const int si = a.period == 1 ? 0 : m % a.period;
+    const float delta = __half2float(a.delta[si]);
+    const QuantConsts qc = make_consts(delta, __half2float(a.zp[si]), a.qmax);
+    const __half2 xl = __float2half2_rn(fminf(511.0f * delta, 65504.0f));
+    RowRegs<MAXC> regs;
+    load_row<MAXC>(regs, a.x + static_cast<size_t>(m) * a.ld, nchunk, lane);
+    const size_t mo = static_cast<size_t>(m / a.rows_per_mod) * a.K;
+    apply_ln_modulate<MAXC>(regs, a.shift + mo, a.scale + mo, a.K, nchunk, lane);
+    if (a.smooth) apply_smooth<MAXC>(regs, a.smooth, nchunk, lane);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      __half2* x = reinterpret_cast<__half2*>(&regs.c[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = __hmin2(__hmax2(x[e], __hneg2(xl)), xl);
+    }
+    int sum = quant_store_row<MAXC>(regs, a.codes + static_cast<size_t>(m) * a.K, nchunk, lane, qc);
     sum = warp_sum_i(sum);
     if (lane == 0) a.rowsum[m] = sum;
   }
@@ -597,13 +640,53 @@ extern "C" int vq_act_quant_static(const void* x, int M, int K, int64_t ld, cons
   if ((K % 8) != 0 || (ld % 8) != 0 || n_bits < 2 || n_bits > 8) return VQ_ERR_ARG;
   StaticQuantArgs a{static_cast<const __half*>(x), M, K, ld, static_cast<const __half*>(delta),
                     static_cast<const __half*>(zp), period, static_cast<const __half*>(smooth),
-                    static_cast<float>((1 << n_bits) - 1), codes, rowsum};
+                    static_cast<float>((1 << n_bits) - 1), codes, rowsum, nullptr, nullptr, 1};
   const int warps = 8;
   long long blocks = (M + warps - 1) / warps;
   const long long cap = 8LL * num_sms();
   if (blocks > cap) blocks = cap;
-  launch_pdl(vq_act_quant_static_kernel, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0,
+  launch_pdl(vq_act_quant_static_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0,
              static_cast<cudaStream_t>(stream), a);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+extern "C" int vq_gelu_act_quant_static(const void* x, int M, int K, int64_t ld, const void* delta, const void* zp,
+                                        int period, const void* smooth, int n_bits, uint8_t* codes, int32_t* rowsum,
+                                        void* stream) {
+  using namespace vq;
+  if (!x || !codes || !delta || !zp || !rowsum || M <= 0 || K <= 0 || period <= 0) return VQ_ERR_ARG;
+  if ((K % 8) != 0 || (ld % 8) != 0 || n_bits < 2 || n_bits > 8) return VQ_ERR_ARG;
+  StaticQuantArgs a{static_cast<const __half*>(x), M, K, ld, static_cast<const __half*>(delta),
+                    static_cast<const __half*>(zp), period, static_cast<const __half*>(smooth),
+                    static_cast<float>((1 << n_bits) - 1), codes, rowsum, nullptr, nullptr, 1};
+  long long blocks = (M + 7) / 8;
+  const long long cap = 8LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  launch_pdl(vq_act_quant_static_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+             static_cast<cudaStream_t>(stream), a);
+  return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
+}
+
+extern "C" int vq_ln_modulate_act_quant_static(const void* x, const void* shift, const void* scale, int M, int K,
+                                               int rows_per_mod, const void* delta, const void* zp, int period,
+                                               const void* smooth, int n_bits, uint8_t* codes, int32_t* rowsum,
+                                               void* stream) {
+  using namespace vq;
+  if (!x || !shift || !scale || !codes || !delta || !zp || !rowsum || M <= 0 || K <= 0 || period <= 0 || rows_per_mod <= 0)
+    return VQ_ERR_ARG;
+  if ((K % 8) != 0 || n_bits < 2 || n_bits > 8 || (M % rows_per_mod) != 0) return VQ_ERR_ARG;
+  if (K > 8 * 32 * 9) return VQ_ERR_UNSUPPORTED;   // the row lives in registers (hidden sizes up to 2304)
+  StaticQuantArgs a{static_cast<const __half*>(x), M, K, K, static_cast<const __half*>(delta),
+                    static_cast<const __half*>(zp), period, static_cast<const __half*>(smooth),
+                    static_cast<float>((1 << n_bits) - 1), codes, rowsum, static_cast<const __half*>(shift),
+                    static_cast<const __half*>(scale), rows_per_mod};
+  long long blocks = (M + 7) / 8;
+  const long long cap = 8LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  const dim3 grid(static_cast<unsigned>(blocks)), block(256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (K <= 8 * 32 * 5) launch_pdl(vq_ln_act_quant_static_kernel<5>, grid, block, 0, st, a);
+  else launch_pdl(vq_ln_act_quant_static_kernel<9>, grid, block, 0, st, a);
   return cudaGetLastError() == cudaSuccess ? VQ_OK : VQ_ERR_LAUNCH;
 }
 

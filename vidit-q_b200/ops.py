@@ -265,9 +265,12 @@ def unpack_rows(buf, K, dims, strides) -> ActCodes:
 
 
 @_nvtx
-def act_quant_static(x, delta, zp, n_bits=8, smooth=None) -> ActCodes:
+def act_quant_static(x, delta, zp, n_bits=8, smooth=None, gelu=False, ln=None, rows_per_mod=None) -> ActCodes:
     """Static (calibrated) activation scales: x fp16 [..., K]; delta / zp: fp16 CUDA [period] (1 = per-tensor, the
-    w8a8_naive.yaml case; rows = static per-token). Row m uses index m % period."""
+    w8a8_naive.yaml case; rows = static per-token). Row m uses index m % period.
+    gelu=True: the codes of h(gelu_tanh(x)) (vq_gelu_act_quant_static); ln=(shift, scale) fp16 [M / rows_per_mod, K]: the
+    codes of LayerNorm + t2i_modulate of x (vq_ln_modulate_act_quant_static; rows_per_mod defaults to x.shape[-2]) — the
+    fused schedule's one-pass forms of the static quantiser."""
     _need_cuda_f16(x, "x")
     _need_cuda_f16(delta, "delta")
     _need_cuda_f16(zp, "zp")
@@ -276,13 +279,27 @@ def act_quant_static(x, delta, zp, n_bits=8, smooth=None) -> ActCodes:
     period = delta.numel()
     if zp.numel() != period or M % period != 0:
         raise _lib.VqError(f"act_quant_static: {M} rows are not a multiple of the {period} (delta, zp) pairs")
+    if gelu and ln is not None:
+        raise _lib.VqError("act_quant_static: gelu and ln are exclusive")
     codes = torch.empty((M, K), dtype=torch.uint8, device=x.device)
     rowsum = torch.empty(M, dtype=torch.int32, device=x.device)
     if smooth is not None:
         _need_cuda_f16(smooth, "smooth")
-    rc = _lib.lib().vq_act_quant_static(_ptr(x), M, K, K, _ptr(delta), _ptr(zp), period, _ptr(smooth), n_bits,
-                                        _ptr(codes), _ptr(rowsum), _stream())
-    _lib.check(rc, "vq_act_quant_static")
+    L = _lib.lib()
+    if ln is not None:
+        shift, scale = ln
+        _need_cuda_f16(shift, "shift")
+        _need_cuda_f16(scale, "scale")
+        rpm = x.shape[-2] if rows_per_mod is None else int(rows_per_mod)
+        if shift.numel() != (M // rpm) * K or scale.numel() != shift.numel() or not x.is_contiguous():
+            raise _lib.VqError(f"act_quant_static: shift/scale of {shift.numel()} elements do not match {M} rows / {rpm}")
+        rc = L.vq_ln_modulate_act_quant_static(_ptr(x), _ptr(shift), _ptr(scale), M, K, rpm, _ptr(delta), _ptr(zp), period,
+                                               _ptr(smooth), n_bits, _ptr(codes), _ptr(rowsum), _stream())
+        _lib.check(rc, "vq_ln_modulate_act_quant_static")
+    else:
+        fn = L.vq_gelu_act_quant_static if gelu else L.vq_act_quant_static
+        rc = fn(_ptr(x), M, K, K, _ptr(delta), _ptr(zp), period, _ptr(smooth), n_bits, _ptr(codes), _ptr(rowsum), _stream())
+        _lib.check(rc, "vq_gelu_act_quant_static" if gelu else "vq_act_quant_static")
     _count()
     return ActCodes(codes, delta.reshape(-1), zp.reshape(-1), rowsum, M // period, period, K)
 

@@ -373,7 +373,7 @@ class QuantLayer(nn.Module):
             return self.prepared_weight(live_smooth=self.live_channel_scale(input, gelu=gelu))
         return self.prepared_weight()
 
-    def quantize_input(self, input, gelu=False, independent=False):
+    def quantize_input(self, input, gelu=False, independent=False, ln=None, rows_per_mod=None):
         """Activation quantisation of a [*, n, C] fp16 tensor -> ops.ActCodes, with `.pw` = the prepared weight the codes
         belong to (the cached one, or — for the input-dependent smooth-quant modes — the one re-quantised for this call).
         gelu=True: `input` is the pre-activation of the preceding nn.GELU(approximate="tanh"); the activation is applied
@@ -384,16 +384,19 @@ class QuantLayer(nn.Module):
         pw = self._weight_for(input, gelu, independent)
         smooth = getattr(pw, "smooth", None)
         if not _is_dynamic(self.act_quantizer):
-            # static scales (base_quantizer.py:112-144 with init_done): nothing is computed from the live tensor
-            if gelu:
-                raise NotImplementedError("GELU fused into a static-scale quantise pass")
+            # static scales (base_quantizer.py:112-144 with init_done): nothing is computed from the live tensor.
+            # gelu / ln = (shift, scale): the fused schedule's one-pass forms (the transform in front of the quantiser)
             delta, zp = self._static_act_params()
             x = input if input.is_contiguous() else input.contiguous()
             if delta.numel() > 1:   # static per-token: index = token position inside the layer's pooled view
                 G, rows = self._pool_view(input)
                 if rows != delta.numel():
                     raise NotImplementedError(f"static per-token scales for {delta.numel()} tokens, input has {rows}")
-            a = ops.act_quant_static(x, delta, zp, n_bits=self.act_quantizer.n_bits, smooth=smooth)
+            a = ops.act_quant_static(x, delta, zp, n_bits=self.act_quantizer.n_bits, smooth=smooth, gelu=gelu, ln=ln,
+                                     rows_per_mod=rows_per_mod)
+        elif ln is not None:
+            raise NotImplementedError("quantize_input(ln=...) is the static-scale form; dynamic layers use "
+                                      "ops.ln_modulate_act_quant")
         else:
             G, rows = self._pool_view(input)
             if independent:

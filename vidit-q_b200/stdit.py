@@ -434,11 +434,12 @@ class FusedBlocks:
             hit = self._qkv[tag] = (key, ops.PreparedWeight(codes, col, codes.shape[0], pws[0].K, pws[0].n_bits))
         return hit[1]
 
-    def _static_qkv(self, attn, tag, t):
-        """Static per-tensor scales: `t` is the fp16 tensor the three layers see (LayerNorm / add already applied).  q, k
-        and v were calibrated on the same tensor; when their (delta, zero point) are identical and no per-layer smooth-quant
-        scale is in the way, ONE vq_act_quant_static pass feeds the concatenated N = 3C GEMM, otherwise each layer
-        quantises for itself and the three GEMMs write column slices of one output."""
+    def _static_qkv(self, attn, tag, t, ln=None, rpm=None):
+        """Static per-tensor scales: `t` is the fp16 tensor in front of the three layers; ln = (shift, scale) has the static
+        quantiser apply LayerNorm + modulate on the fly (vq_ln_modulate_act_quant_static).  q, k and v were calibrated on
+        the same tensor; when their (delta, zero point) are identical and no per-layer smooth-quant scale is in the way, ONE
+        quantise pass feeds the concatenated N = 3C GEMM, otherwise each layer quantises for itself and the three GEMMs
+        write column slices of one output."""
         layers = (attn.q, attn.k, attn.v)
         C = t.shape[-1]
         pw = self._qkv_weight(attn, tag)
@@ -451,10 +452,10 @@ class FusedBlocks:
                            torch.equal(aqs[0].zero_point.reshape(-1), q.zero_point.reshape(-1)) for q in aqs[1:])
                 hit = self._static_same[tag] = (key, same)
             if hit[1]:
-                return ops.gemm_w8a8(layers[0].quantize_input(t), pw)
+                return ops.gemm_w8a8(layers[0].quantize_input(t, ln=ln, rows_per_mod=rpm), pw)
         out = torch.empty(t.numel() // C, 3 * C, dtype=t.dtype, device=t.device)
         for j, layer in enumerate(layers):
-            a = layer.quantize_input(t)
+            a = layer.quantize_input(t, ln=ln, rows_per_mod=rpm)
             ops.gemm_w8a8(a, a.pw, out=out[:, j * C:(j + 1) * C], ldo=3 * C)
         return out
 
@@ -474,12 +475,10 @@ class FusedBlocks:
         its own channel scale, hence its own codes; the three GEMMs write column slices of the same output.
         add = (vectors [period, C], rows_per_add): an fp16 row-broadcast add fused in front of the quantiser (block 0's
         temporal position embedding) when K = 1152."""
-        if self.static:   # calibrated scales: form the fp16 tensor the layers see, then the static quantiser
+        if self.static:   # calibrated scales: LayerNorm + modulate inside the static quantiser; adds formed first
             if ln is not None:
-                rpm = x.shape[1] if independent else None
-                x = ops.ln_modulate_act_quant(x.view(1, -1, x.shape[2]) if independent else x, ln[0], ln[1], want_y=True,
-                                              rows_per_mod=rpm)[1]
-            elif add is not None:
+                return self._static_qkv(attn, tag, x, ln=ln, rpm=x.shape[1])
+            if add is not None:
                 vec, rpa = add
                 x = (x.reshape(-1, vec.shape[0], rpa, x.shape[-1]) + vec.view(1, -1, 1, x.shape[-1])).view(x.shape)
             return self._static_qkv(attn, tag, x)
@@ -536,8 +535,8 @@ class FusedBlocks:
         def qi(layer, t, gelu=False):
             """The layer's activation quantiser. Frame-sharded: a rank holds T / P frames, which the reference layers'
             (B, T*S) pooling views do not describe — every row is quantised on its own (un-pooled, as checked above)."""
-            if self.static:   # no GELU inside vq_act_quant_static: the activation is a torch pass in front of it
-                return layer.quantize_input(F.gelu(t, approximate="tanh") if gelu else t)
+            if self.static:   # calibrated scales: GELU rides in the static quantise pass (vq_gelu_act_quant_static)
+                return layer.quantize_input(t, gelu=gelu)
             if frames is None:
                 return layer.quantize_input(t, gelu=gelu, independent=independent)
             if layer.smooth_quant:
@@ -629,9 +628,7 @@ class FusedBlocks:
             fc1w = blk.mlp.fc1.prepared_weight()
             # GELU rides in fc2's quantise pass (HBM-bound, idle MUFU) instead of fc1's epilogue (epilogue-bound)
             if self.static:
-                yln = ops.ln_modulate_act_quant(x.view(1, M, C) if independent else x, shift_mlp, scale_mlp, want_y=True,
-                                                rows_per_mod=N if independent else None)[1]
-                a = blk.mlp.fc1.quantize_input(yln)
+                a = blk.mlp.fc1.quantize_input(x, ln=(shift_mlp, scale_mlp), rows_per_mod=N)
                 h = ops.gemm_w8a8(a, a.pw).view(B, N, -1)
             elif self.overlap and unpooled:
                 h = ops.linear_w8a8(x.view(1, M, C), fc1w, n_bits=blk.mlp.fc1.act_quantizer.n_bits,
