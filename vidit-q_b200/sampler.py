@@ -149,3 +149,78 @@ def ddim_sample_loop(ddim: SpacedDDIM, model_forward, z, y_cond, y_uncond, mask,
         if on_step is not None:
             on_step(i, z)
     return z
+
+
+class GraphedSampler:
+    """The complete DDIM sampling loop of one prompt (IDDPM.sample(..., 'ddim') with cfg_split) on the fused schedule, one
+    CUDA-graph replay per step: the cond + uncond forwards run as ONE stacked launch sequence (un-pooled statistics == two
+    batch-1 calls) followed by the fused CFG + DDIM update (vq_cfg_ddim_step), the latent is updated in place on the
+    device, the timestep and the four DDIM coefficients are device tensors refreshed between replays.
+
+    The kernels a step launches depend on which prepared weights it reads: one graph is captured per KEY =
+    (smooth-quant timerange of the step's timestep, mixed-precision range of the step index) and reused for every step
+    with that key — one graph for w8a8_dynamic.yaml, two for the two-timerange W4A8 config, one per range with
+    per-timestep mixed precision (the per-(timerange, bit-config) graphs of SURVEY.md section 7 step 8)."""
+
+    def __init__(self, qnn, model, ddim: SpacedDDIM, y_cond, y_uncond, mask, latent_shape):
+        if not (y_cond.is_cuda and y_cond.shape[0] == 1 and latent_shape[0] == 1):
+            raise ValueError("GraphedSampler runs one prompt (batch 1) per instance on a CUDA device")
+        dev = y_cond.device
+        self.qnn, self.model, self.ddim = qnn, model, ddim
+        self.z = torch.zeros(latent_shape, device=dev)
+        self.t = torch.zeros(1, device=dev)
+        self.coef = torch.zeros(4, device=dev)
+        self.y = torch.cat([y_cond, y_uncond]).contiguous()
+        self.plan = model.mask_select_plan(mask.to(dev).repeat(2, 1) if mask.shape[0] == 1 else mask.to(dev))
+        self.segments = model.kv_segments(self.plan[1], dev)
+        self.mp = TimestepMixedPrecision(qnn)
+        self.graphs = {}
+
+    def _step(self):
+        from . import ops
+        out = self.model.forward_fused(torch.cat([self.z, self.z]), self.t.expand(2), self.y, plan=self.plan,
+                                       segments=self.segments, independent=True)
+        self.z.copy_(ops.cfg_ddim_step(out[:1], out[1:], self.z, self.coef, self.ddim.cfg_scale))
+
+    def _key(self, i):
+        from .qdiff import find_interval
+        t = self.ddim.model_timestep(i)
+        tr = 0
+        for _, layer in self.qnn.quant_layers():
+            if getattr(layer, "smooth_quant", False) and hasattr(layer, "timerange"):
+                tr = find_interval(layer.timerange, t)
+                break
+        rng = get_key_for_value(self.qnn.time_mp_config_weight, i) if getattr(self.qnn, "timestep_wise_mp", False) else None
+        return tr, rng
+
+    @torch.no_grad()
+    def sample(self, z, on_step=None):
+        """z: the initial noise [1, C, T, H, W] (any device) -> the final latent (a clone of the in-place buffer)."""
+        self.z.copy_(z)
+        for i in range(self.ddim.num_timesteps - 1, -1, -1):
+            self.mp.before_step(i)
+            t = self.ddim.model_timestep(i)
+            self.qnn.set_timestep_id_for_quantlayer(t)
+            self.t.fill_(t)
+            self.coef.copy_(self.ddim.coefficients(i, "cpu"), non_blocking=True)
+            key = self._key(i)
+            g = self.graphs.get(key)
+            if g is None:
+                # a new key: run the step once eagerly on a copy of the state (prepares this key's weight codes, warms the
+                # allocator), restore the latent, then capture
+                keep = self.z.clone()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._step()
+                torch.cuda.current_stream().wait_stream(side)
+                self.z.copy_(keep)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step()
+                self.graphs[key] = g
+                self.z.copy_(keep)      # the capture does not execute: the replay below is this step
+            g.replay()
+            if on_step is not None:
+                on_step(i, self.z)
+        return self.z.clone()
