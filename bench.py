@@ -520,13 +520,73 @@ def multi_gpu_selfcheck(dev, world, rank):
 # --------------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------------
+def run_full_sample(args, dev, world, rank):
+    """BASELINE config 3 as the reference states it: ONE complete 100-step DDIM sample of the 16x512x512 STDiT under
+    w8a8_dynamic.yaml (cfg_split, cfg 4.0) through viditq_b200.sampler.GraphedSampler — host noise in, host latent out,
+    every step a CUDA-graph replay.  --steps = number of samples timed (each rank its own sample; default bench K would be
+    10 samples = 40 s, 2 are enough), --warmup = samples run first (the first one captures the graph)."""
+    import torch
+    import torch.distributed as dist
+    from viditq_b200 import ops
+    from viditq_b200.sampler import GraphedSampler, SpacedDDIM
+    qnn, model = build_model(dev, args.depth)
+    ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
+    g = torch.Generator().manual_seed(99 + rank)
+    h_z = torch.randn(1, 4, T_FRAMES, 64, 64, generator=g).pin_memory()
+    yc = torch.randn(1, 1, PROMPT_LEN, 4096, generator=g).to(dev)
+    yu = torch.randn(1, 1, PROMPT_LEN, 4096, generator=g).to(dev)
+    mask = torch.zeros(1, PROMPT_LEN, dtype=torch.int64)
+    mask[0, :109] = 1
+    gs = GraphedSampler(qnn, model, ddim, yc, yu, mask.to(dev), h_z.shape)
+    h_out = torch.empty_like(h_z).pin_memory()
+    n_samples = max(1, min(args.steps, 3))
+    for _ in range(max(1, min(args.warmup, 1))):
+        gs.sample(h_z.to(dev, non_blocking=True))
+    torch.cuda.synchronize()
+    clk = ClockSampler(dev.index or 0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with clk:
+        clk.t0 = time.time()
+        e0.record()
+        for _ in range(n_samples):
+            h_out.copy_(gs.sample(h_z.to(dev, non_blocking=True)), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        clk.t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    if not torch.isfinite(h_out).all() or ops.check_status() != 0:
+        raise SystemExit("sample100: non-finite latent")
+    if rank == 0:
+        sec = ms.item() / 1e3 / n_samples
+        print(json.dumps({
+            "metric": "stdit_16x512x512_w8a8_100step_sample_seconds", "value": sec, "unit": "s/sample", "n_gpus": world,
+            "steps": n_samples, "warmup": 1, "ms_per_step": sec * 1e3 / ddim.num_timesteps, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "STDiT-XL/2 16x512x512 W8A8 per-token dynamic, ONE full 100-step DDIM sample per rank "
+                                   "(cfg_split stacked, cfg 4.0) through sampler.GraphedSampler: pinned host noise in, pinned "
+                                   "host latent out, one CUDA-graph replay per step",
+                       "samples_timed_per_gpu": n_samples, "denoise_steps_per_sec_per_gpu": ddim.num_timesteps / sec,
+                       "depth": args.depth, "l2": "working set per step exceeds the 126 MB L2"},
+            "e2e": {"value": sec, "unit": "s/sample", "h2d_bytes_per_step": h_z.numel() * 4 // ddim.num_timesteps,
+                    "d2h_bytes_per_step": h_out.numel() * 4 // ddim.num_timesteps},
+            "gpu_launches": gs.launches_per_step * ddim.num_timesteps * n_samples, "clocks": clk.summary()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="stdit", choices=["stdit", "linear", "pixart512", "w4a8mp", "w8a8static"],
+    ap.add_argument("--workload", default="stdit", choices=["stdit", "linear", "pixart512", "w4a8mp", "w8a8static", "sample100"],
                     help="stdit: the metric (BASELINE configs 3 / 5). linear: config 1, one QuantLinear 1152->4608 through the "
                          "hook API. pixart512: config 2, one PixArt-alpha 512 solver step (CFG batch 2) under w8a8.yaml. "
                          "w4a8mp: config 4, STDiT W4A8 timestep-aware smooth-quant + per-layer mixed precision")
@@ -580,6 +640,8 @@ def main():
     sample_id = rank // 2 if pairs else (0 if fsh else rank)   # ranks sharing a sample hold the same inputs and weights
     torch.manual_seed(1234 + sample_id)
     wl = args.workload
+    if wl == "sample100":
+        return run_full_sample(args, dev, world, rank)
     metric, unit = METRIC, UNIT
     peaks = load_peaks()
 

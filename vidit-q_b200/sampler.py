@@ -175,6 +175,7 @@ class GraphedSampler:
         self.segments = model.kv_segments(self.plan[1], dev)
         self.mp = TimestepMixedPrecision(qnn)
         self.graphs = {}
+        self.launches_per_step = 0
 
     def _step(self):
         from . import ops
@@ -211,13 +212,16 @@ class GraphedSampler:
                 keep = self.z.clone()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
+                from . import ops
                 with torch.cuda.stream(side):
                     self._step()
                 torch.cuda.current_stream().wait_stream(side)
                 self.z.copy_(keep)
                 g = torch.cuda.CUDAGraph()
+                n0 = ops.launch_count()
                 with torch.cuda.graph(g):
                     self._step()
+                self.launches_per_step = ops.launch_count() - n0    # own kernels inside one captured step
                 self.graphs[key] = g
                 self.z.copy_(keep)      # the capture does not execute: the replay below is this step
             g.replay()
