@@ -79,3 +79,34 @@ def test_graphed_sampling_loop_equals_the_eager_loop(smooth):
     assert torch.equal(got, want)
     again = gs.sample(z0)                                           # the captured graphs are reusable
     assert torch.equal(again, want) and len(gs.graphs) == (2 if smooth else 1)
+
+
+@pytest.mark.gpu
+def test_graphed_sampling_loop_with_per_timestep_mixed_precision():
+    """Config 4's mechanics inside the graphed loop: the per-timestep bit tables (quant_txt2video_mp.py:533-540) switch layer
+    widths when the step index enters a new range — a new key, hence a new captured graph; latents equal the eager loop's."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from viditq_b200.sampler import GraphedSampler, SpacedDDIM, ddim_sample_loop
+    qnn, model = _model(True)
+    names = ["model." + n for n, _ in qnn.quant_layers() if n.startswith("blocks.")]
+    tab = {n: (8 if ".mlp." in n else 4) for n in names}
+    qnn.timestep_wise_mp = True
+    qnn.time_mp_config_weight = {"5-4": {n: 8 for n in names}, "3-0": tab, "fp_layers": {"5-4": FP_LAYERS, "3-0": FP_LAYERS}}
+    qnn.time_mp_config_act = {"5-4": {n: 8 for n in names}, "3-0": {n: 8 for n in names}}
+    ddim = SpacedDDIM(num_sampling_steps=6, cfg_scale=7.0)
+    g = torch.Generator().manual_seed(9)
+    z0 = torch.randn(1, 4, 4, 32, 32, generator=g).cuda()
+    yc = torch.randn(1, 1, 120, 4096, generator=g).cuda()
+    yu = torch.randn(1, 1, 120, 4096, generator=g).cuda()
+    mask = torch.zeros(1, 120, dtype=torch.int64)
+    mask[0, :77] = 1
+    mask = mask.cuda()
+    with torch.no_grad():
+        want = ddim_sample_loop(ddim, model.forward_fused, z0.clone(), yc, yu, mask, qnn=qnn,
+                                stacked_forward=functools.partial(model.forward_fused, independent=True))
+    gs = GraphedSampler(qnn, model, ddim, yc, yu, mask, z0.shape)
+    got = gs.sample(z0)
+    # timesteps 999, 799 (range 5-4, timerange 1) | 599 (3-0, timerange 1) | 400, 200, 0 (3-0, timerange 0): three keys
+    assert sorted(gs.graphs.keys()) == [(0, "3-0"), (1, "3-0"), (1, "5-4")]
+    assert torch.equal(got, want)
