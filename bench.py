@@ -520,6 +520,23 @@ def multi_gpu_selfcheck(dev, world, rank):
 # --------------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------------
+def build_w4a8mp(dev, depth):
+    """BASELINE config 4: w4a8_timestep_aware_cb.yaml (4-bit weights, timerange-aware smooth-quant, alpha 0.11 / 0.11, 20
+    steps, cfg 7) + per-timestep mixed precision tables shaped like t20_weight_4_mp.yaml / t20_act_8_mp.yaml: range 19-15
+    all 8 bit, the others 4 bit except the MLP layers of the first and last blocks (58 of 364 layers) at 8."""
+    from viditq_b200.sampler import SpacedDDIM
+    qnn, model = build_model(dev, depth, w_bits=4, smooth=dict(alpha=[0.11, 0.11], timerange=[[0, 500], [501, 1000]]))
+    ddim = SpacedDDIM(num_sampling_steps=20, cfg_scale=7.0)
+    names = ["model." + n for n, _ in qnn.quant_layers() if n.startswith("blocks.")]
+    hot = {n for n in names if ".mlp." in n and int(n.split(".")[2]) in (0, 1, depth - 1)}
+    tab4 = {n: (8 if n in hot else 4) for n in names}
+    qnn.timestep_wise_mp = True
+    qnn.time_mp_config_weight = {"19-15": {n: 8 for n in names}, "14-10": tab4, "9-5": tab4, "4-0": tab4,
+                                 "fp_layers": {k: FP_LAYERS for k in ("19-15", "14-10", "9-5", "4-0")}}
+    qnn.time_mp_config_act = {k: {n: 8 for n in names} for k in ("19-15", "14-10", "9-5", "4-0")}
+    return qnn, model, ddim
+
+
 def run_full_sample(args, dev, world, rank):
     """BASELINE config 3 as the reference states it: ONE complete 100-step DDIM sample of the 16x512x512 STDiT under
     w8a8_dynamic.yaml (cfg_split, cfg 4.0) through viditq_b200.sampler.GraphedSampler — host noise in, host latent out,
@@ -529,8 +546,12 @@ def run_full_sample(args, dev, world, rank):
     import torch.distributed as dist
     from viditq_b200 import ops
     from viditq_b200.sampler import GraphedSampler, SpacedDDIM
-    qnn, model = build_model(dev, args.depth)
-    ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
+    mp20 = args.workload == "sample20mp"
+    if mp20:      # BASELINE config 4 as one full 20-step sample: the graphed loop re-captures per (timerange, bit range)
+        qnn, model, ddim = build_w4a8mp(dev, args.depth)
+    else:
+        qnn, model = build_model(dev, args.depth)
+        ddim = SpacedDDIM(num_sampling_steps=100, cfg_scale=4.0)
     g = torch.Generator().manual_seed(99 + rank)
     h_z = torch.randn(1, 4, T_FRAMES, 64, 64, generator=g).pin_memory()
     yc = torch.randn(1, 1, PROMPT_LEN, 4096, generator=g).to(dev)
@@ -565,12 +586,16 @@ def run_full_sample(args, dev, world, rank):
     if rank == 0:
         sec = ms.item() / 1e3 / n_samples
         print(json.dumps({
-            "metric": "stdit_16x512x512_w8a8_100step_sample_seconds", "value": sec, "unit": "s/sample", "n_gpus": world,
+            "metric": ("stdit_16x512x512_w4a8_mp_20step_sample_seconds" if mp20 else
+                       "stdit_16x512x512_w8a8_100step_sample_seconds"), "value": sec, "unit": "s/sample", "n_gpus": world,
             "steps": n_samples, "warmup": 1, "ms_per_step": sec * 1e3 / ddim.num_timesteps, "higher_is_better": False,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "STDiT-XL/2 16x512x512 W8A8 per-token dynamic, ONE full 100-step DDIM sample per rank "
-                                   "(cfg_split stacked, cfg 4.0) through sampler.GraphedSampler: pinned host noise in, pinned "
-                                   "host latent out, one CUDA-graph replay per step",
+            "config": {"workload": ("STDiT-XL/2 16x512x512 W4A8 timestep-aware smooth-quant + per-timestep mixed precision, ONE full "
+                                    "20-step DDIM sample per rank (cfg 7.0)" if mp20 else
+                                    "STDiT-XL/2 16x512x512 W8A8 per-token dynamic, ONE full 100-step DDIM sample per rank "
+                                    "(cfg_split stacked, cfg 4.0)") + " through sampler.GraphedSampler: pinned host noise in, "
+                                   "pinned host latent out, one CUDA-graph replay per step",
+                       "graphs_captured": len(gs.graphs),
                        "samples_timed_per_gpu": n_samples, "denoise_steps_per_sec_per_gpu": ddim.num_timesteps / sec,
                        "depth": args.depth, "l2": "working set per step exceeds the 126 MB L2"},
             "e2e": {"value": sec, "unit": "s/sample", "h2d_bytes_per_step": h_z.numel() * 4 // ddim.num_timesteps,
@@ -586,7 +611,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="stdit", choices=["stdit", "linear", "pixart512", "w4a8mp", "w8a8static", "sample100"],
+    ap.add_argument("--workload", default="stdit", choices=["stdit", "linear", "pixart512", "w4a8mp", "w8a8static", "sample100", "sample20mp"],
                     help="stdit: the metric (BASELINE configs 3 / 5). linear: config 1, one QuantLinear 1152->4608 through the "
                          "hook API. pixart512: config 2, one PixArt-alpha 512 solver step (CFG batch 2) under w8a8.yaml. "
                          "w4a8mp: config 4, STDiT W4A8 timestep-aware smooth-quant + per-layer mixed precision")
@@ -640,7 +665,7 @@ def main():
     sample_id = rank // 2 if pairs else (0 if fsh else rank)   # ranks sharing a sample hold the same inputs and weights
     torch.manual_seed(1234 + sample_id)
     wl = args.workload
-    if wl == "sample100":
+    if wl in ("sample100", "sample20mp"):
         return run_full_sample(args, dev, world, rank)
     metric, unit = METRIC, UNIT
     peaks = load_peaks()
@@ -658,19 +683,7 @@ def main():
             mp = None
             metric = "stdit_16x512x512_w8a8_static_denoise_steps_per_sec"
         elif wl == "w4a8mp":
-            # w4a8_timestep_aware_cb.yaml: 4-bit weights, timerange-aware smooth-quant (alpha 0.11 / 0.11), 20 steps, cfg 7
-            qnn, model = build_model(dev, args.depth, w_bits=4,
-                                     smooth=dict(alpha=[0.11, 0.11], timerange=[[0, 500], [501, 1000]]))
-            ddim = SpacedDDIM(num_sampling_steps=20, cfg_scale=7.0)
-            # per-timestep mixed precision tables shaped like t20_weight_4_mp.yaml / t20_act_8_mp.yaml: range 19-15 all 8 bit,
-            # the others 4 bit except the MLP layers of the first and last blocks (58 of 364 layers) at 8
-            names = ["model." + n for n, _ in qnn.quant_layers() if n.startswith("blocks.")]
-            hot = {n for n in names if ".mlp." in n and int(n.split(".")[2]) in (0, 1, args.depth - 1)}
-            tab4 = {n: (8 if n in hot else 4) for n in names}
-            qnn.timestep_wise_mp = True
-            qnn.time_mp_config_weight = {"19-15": {n: 8 for n in names}, "14-10": tab4, "9-5": tab4, "4-0": tab4,
-                                         "fp_layers": {k: FP_LAYERS for k in ("19-15", "14-10", "9-5", "4-0")}}
-            qnn.time_mp_config_act = {k: {n: 8 for n in names} for k in ("19-15", "14-10", "9-5", "4-0")}
+            qnn, model, ddim = build_w4a8mp(dev, args.depth)
             mp = TimestepMixedPrecision(qnn)
             metric = "stdit_16x512x512_w4a8_mp_denoise_steps_per_sec"
         else:
