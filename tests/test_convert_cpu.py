@@ -4,7 +4,6 @@ kernel wrappers swapped for the oracle's stand-ins."""
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 
