@@ -7,10 +7,18 @@ timeout 1500 python -m pytest tests -m gpu -q -x -s > gpurun_out/pytest_gpu.log 
 grep -E "passed|failed|rc=" gpurun_out/pytest_gpu.log | tail -3
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
 grep '^{' gpurun_out/bench.log | tail -1 | cut -c1-300
-for wl in linear pixart512 w4a8mp; do
+for wl in linear pixart512 w4a8mp w8a8static; do
   timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$wl.log 2>&1
   echo "== $wl"; grep '^{' gpurun_out/bench_$wl.log | tail -1 | cut -c1-200
 done
+for wl in sample100 sample20mp; do
+  timeout 600 python bench.py --workload $wl --steps 2 --warmup 1 > gpurun_out/bench_$wl.log 2>&1
+  echo "== $wl"; grep '^{' gpurun_out/bench_$wl.log | tail -1 | cut -c1-200
+done
+timeout 600 python bench.py --attn-int8 --steps 5 --warmup 3 --no-cpu-baseline --no-peak > gpurun_out/bench_attn_int8.log 2>&1
+echo "== attn-int8"; grep '^{' gpurun_out/bench_attn_int8.log | tail -1 | cut -c1-200
+timeout 900 python bench.py --schedule hook-graph --steps 5 --warmup 3 --no-cpu-baseline --no-peak > gpurun_out/bench_hook_graph.log 2>&1
+echo "== hook-graph"; grep '^{' gpurun_out/bench_hook_graph.log | tail -1 | cut -c1-200
 VQ_PDL=1 timeout 600 python bench.py --workload pixart512 --steps 10 --warmup 3 --no-cpu-baseline --no-peak > gpurun_out/bench_pixart512_pdl.log 2>&1
 echo "== pixart512 PDL"; grep '^{' gpurun_out/bench_pixart512_pdl.log | tail -1 | cut -c1-200
 timeout 900 python bench.py --schedule hook --steps 5 --warmup 3 --no-cpu-baseline --no-peak > gpurun_out/bench_hook.log 2>&1
